@@ -1,0 +1,160 @@
+/*
+ * tsp_b200.h - C ABI of the B200-native surface-projection library (libtsp_b200.so).
+ *
+ * One entry point per call the reference makes on its projection hot path.  The reference is
+ * pure Python (no FFI of its own); the interface each function replaces is cited as
+ * file:line of kasirershahartau/tissue_image_processing:
+ *
+ *   SP  = tissue_analyzing_tool/surface_projection.py
+ *   SPM = tissue_analyzing_tool/surface_proj_m.py
+ *   BIM = tissue_analyzing_tool/basic_image_manipulations.py
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative
+ * TSP_ERR_* code and never throws; tsp_last_error() gives the text for the calling thread.
+ * "d_" pointers are device memory on the handle's GPU, "h_" pointers are host memory (pinned
+ * host memory makes the copies asynchronous DMA; pageable memory works but is staged by the
+ * driver).  Stacks are uint16, C-contiguous (C, Z, Y, X) with X fastest - the layout the
+ * reference operator works on after BIM:199-231 / SP:21-26.
+ */
+#ifndef TSP_B200_H
+#define TSP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSP_ABI_VERSION 1
+
+/* error codes */
+#define TSP_OK 0
+#define TSP_ERR_INVALID (-1)      /* bad argument (shape, channel, mode ...)                      */
+#define TSP_ERR_CUDA (-2)         /* CUDA runtime failure, text in tsp_last_error()               */
+#define TSP_ERR_WORKSPACE (-3)    /* workspace smaller than tsp_project_workspace_bytes()         */
+#define TSP_ERR_BAND_INDEX (-4)   /* height map indexes past the cropped stack: the reference     */
+                                  /* raises IndexError at SP:68-69 (min_z>0 or atoh_shift)        */
+#define TSP_ERR_CHOOSE_LIMIT (-5) /* surface_projection_m with 64 or more planes: np.choose      */
+                                  /* raises ValueError at SPM:40                                  */
+
+/* score-stage variants (all feed the same argmax + band projection) */
+#define TSP_MODE_FAST 0      /* multirate sigma=30 stage, one uint16 read; |score err| ~1e-5 rel  */
+#define TSP_MODE_EXACT 1     /* direct separable FIR, fp32 accumulate, reference pass order       */
+#define TSP_MODE_BITEXACT 2  /* direct FIR, fp64 accumulate in scipy's summation order, f32 store */
+
+typedef struct tsp_handle tsp_handle; /* per-GPU context: tables, status words, staging buffers */
+
+/* Frame descriptor = the arguments of time_point_surface_projection (SP:17-19) that reach the
+ * arithmetic, for bin_size == 1 and build_manifold == False. */
+typedef struct tsp_frame_desc {
+    int32_t channels, planes, rows, cols; /* C, Z, Y, X of the uint16 stack                      */
+    int32_t reference_channel;            /* SP:32                                               */
+    int32_t min_z, max_z;                 /* SP:30-31: crop [min_z, max_z) when max_z > 0        */
+    int32_t airyscan;                     /* SP:27-29: subtract 10000, clamp at 0                */
+    int32_t atoh_shift;                   /* SP:62: plane offset for the non-reference channels  */
+    int32_t mode;                         /* TSP_MODE_*                                          */
+    int32_t reserved[6];                  /* must be 0                                           */
+} tsp_frame_desc;
+
+/* What the operator learned about the frame (filled by the *_host calls and tsp_get_frame_status) */
+typedef struct tsp_frame_status {
+    int32_t band_index_error; /* 1 when the reference would raise IndexError (SP:68-69)          */
+    int32_t has_nonzero;      /* 0 when the reference channel is all zero after SP:27-29 (no clip)*/
+    float percentile95;       /* clip value of SP:35 (undefined when has_nonzero == 0)           */
+    int32_t zmap_min, zmap_max;
+    int64_t nonzero_count;    /* voxels > 0 of the reference channel after SP:27-31              */
+    int32_t near_tie_pixels;  /* fast mode: pixels whose top-2 score gap is below 2.5e-4 rel.    */
+    int32_t reserved[5];
+} tsp_frame_status;
+
+int tsp_abi_version(void);
+const char* tsp_last_error(void);
+
+int tsp_create(int device, tsp_handle** out);
+int tsp_destroy(tsp_handle* h);
+
+/* ---- the operator: SP:17-85 (time_point_surface_projection) ------------------------------- */
+
+/* Bytes of device scratch tsp_project_frame needs for this frame shape and mode. */
+size_t tsp_project_workspace_bytes(const tsp_frame_desc* desc);
+
+/* Device-resident call.  d_stack (C,Z,Y,X) uint16; d_proj (C,Y,X) float32 = SP:72-79 (the
+ * reference's float64 values are float32-exact); d_zmap (Y,X) int32 = chosen_z of SP:61
+ * (min_z already added).  Stream ordered, returns without synchronising; call
+ * tsp_get_frame_status() afterwards to learn about TSP_ERR_BAND_INDEX. */
+int tsp_project_frame(tsp_handle* h, const tsp_frame_desc* desc, const uint16_t* d_stack,
+                      float* d_proj, int32_t* d_zmap, void* d_workspace, size_t workspace_bytes,
+                      void* cuda_stream);
+
+/* Synchronises the stream and reports on the last tsp_project_frame issued with d_workspace.
+ * Returns TSP_ERR_BAND_INDEX when the reference would have raised IndexError. */
+int tsp_get_frame_status(tsp_handle* h, const void* d_workspace, void* cuda_stream,
+                     tsp_frame_status* out);
+
+/* Host-buffer call = the plugin boundary `result = apply_function(chunk, **params)` of BIM:129.
+ * h_stack (C,Z,Y,X) uint16 in host memory; h_proj (C,Y,X) float64 and h_zmap (Y,X) int64 are
+ * the dtypes the reference returns (SP:73, SP:61).  Copies in, runs, copies out, synchronises.
+ * Device scratch is owned (and reused) by the handle. */
+int tsp_project_frame_host(tsp_handle* h, const tsp_frame_desc* desc, const uint16_t* h_stack,
+                           double* h_proj, int64_t* h_zmap, tsp_frame_status* status);
+
+/* ---- building blocks (also used one by one by the parity tests) --------------------------- */
+
+/* BIM:373-390 blur_image = scipy.ndimage.gaussian_filter(mode='nearest') on a 3-D float32
+ * volume (z,y,x), passes z -> y -> x with a float32 store between passes.  fp64_accumulate != 0
+ * reproduces scipy's float64 line sums bit for bit.  d_tmp: scratch of the same size. */
+int tsp_gaussian_blur_f32(tsp_handle* h, const float* d_in, float* d_out, float* d_tmp,
+                          int planes, int rows, int cols, const double sigma[3],
+                          int fp64_accumulate, void* cuda_stream);
+
+/* Same on uint16 with scipy's integer-output behaviour: every pass truncates toward zero
+ * (SPM:18 blurs the uint16 stack). */
+int tsp_gaussian_blur_u16(tsp_handle* h, const uint16_t* d_in, uint16_t* d_out, uint16_t* d_tmp,
+                          int planes, int rows, int cols, const double sigma[3],
+                          void* cuda_stream);
+
+/* SP:32-36: 95th percentile (numpy 'linear', float32 index arithmetic) of the voxels that are
+ * > 0 after the optional airyscan pedestal.  Synchronises; results through `out`. */
+int tsp_percentile95_nonzero_u16(tsp_handle* h, const uint16_t* d_volume, size_t count,
+                                 int airyscan, void* cuda_stream, tsp_frame_status* out);
+
+/* SP:26-37 + SP:55: the focus score volume (planes,rows,cols) float32 of one channel, in the
+ * exact / bit-exact variants (the fast variant never materialises it).  d_tmp: same size. */
+int tsp_focus_score_f32(tsp_handle* h, const uint16_t* d_channel, float* d_score, float* d_tmp,
+                        int planes, int rows, int cols, int airyscan, int fp64_accumulate,
+                        void* cuda_stream);
+
+/* SP:61: first-maximum argmax over z (+ z_offset). */
+int tsp_argmax_z_f32(tsp_handle* h, const float* d_score, int32_t* d_zmap, int planes, int rows,
+                     int cols, int z_offset, void* cuda_stream);
+
+/* SP:62-81: band mask from a height map and weighted max projection of every channel, without
+ * materialising the one-hot volume.  d_zmap indexes the (already cropped) stack.  Channels other
+ * than reference_channel use clip(zmap + atoh_shift, 0, planes).  Out-of-range indices set the
+ * handle's band_index_error status (see tsp_get_frame_status). */
+int tsp_band_project(tsp_handle* h, const uint16_t* d_stack, const int32_t* d_zmap, float* d_proj,
+                     int channels, int planes, int rows, int cols, int reference_channel,
+                     int atoh_shift, int airyscan, void* d_workspace, size_t workspace_bytes,
+                     void* cuda_stream);
+size_t tsp_band_workspace_bytes(int channels, int planes, int rows, int cols);
+
+/* ---- SPM:14-35 surface_projection_m ------------------------------------------------------- */
+/* d_channel: (planes,rows,cols) uint16 = image[reference_channel][min_z:max_z]; method 0 =
+ * "max_averages" (block mean), 1 = "max_std" (block variance); d_out (rows,cols) uint16. */
+size_t tsp_project_m_workspace_bytes(int planes, int rows, int cols, int bin_size);
+int tsp_project_m(tsp_handle* h, const uint16_t* d_channel, uint16_t* d_out, int planes, int rows,
+                  int cols, int method, int bin_size, void* d_workspace, size_t workspace_bytes,
+                  void* cuda_stream);
+
+/* ---- introspection used by tests ---------------------------------------------------------- */
+/* Copies the fast-mode coarse FIR taps c[0..n) (symmetric half, c[0] = centre) designed by the
+ * library; returns the number of taps, or a negative error. */
+int tsp_debug_coarse_taps(double* out, int capacity);
+/* Number of CUDA kernels launched through this handle so far (bench.py reports it). */
+int64_t tsp_launch_count(const tsp_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSP_B200_H */

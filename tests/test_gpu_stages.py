@@ -1,0 +1,140 @@
+"""Stage-level GPU tests: every kernel of the path against the numpy/scipy statement of the same stage."""
+import numpy as np
+import pytest
+
+from oracle import synth
+from oracle import surface_projection_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def nat():
+    import torch
+    assert torch.cuda.is_available()
+    from tissue_image_processing_b200 import _native
+    _native.load_library()
+    return _native
+
+
+def _cuda(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("sigma", [orc.SIGMA_PRE, orc.SIGMA_SCORE, orc.SIGMA_MASK, (0.5, 3.0, 7.5)])
+@pytest.mark.parametrize("shape", [(9, 70, 65), (5, 300, 257), (1, 33, 1030), (3, 1, 17)])
+def test_gaussian_blur_f32_bit_exact(nat, sigma, shape):
+    rng = np.random.default_rng(sum(shape))
+    vol = rng.integers(0, 4096, size=shape).astype(np.float32) + rng.random(shape).astype(np.float32)
+    got = nat.gaussian_blur(_cuda(vol), sigma, fp64_accumulate=True).cpu().numpy()
+    want = orc.blur_image(vol, sigma)
+    assert np.array_equal(got, want)
+    got32 = nat.gaussian_blur(_cuda(vol), sigma, fp64_accumulate=False).cpu().numpy()
+    np.testing.assert_allclose(got32, want, rtol=3e-6, atol=0)
+
+
+@pytest.mark.parametrize("shape", [(12, 96, 112), (7, 53, 67)])
+def test_gaussian_blur_u16_truncates_like_scipy(nat, shape):
+    rng = np.random.default_rng(3)
+    vol = rng.integers(0, 65535, size=shape).astype(np.uint16)
+    got = nat.gaussian_blur(_cuda(vol), orc.SIGMA_M).cpu().numpy()
+    assert np.array_equal(got, orc.blur_image(vol, orc.SIGMA_M))
+
+
+def _np_p95(vol, airyscan):
+    img = vol.astype(np.float32)
+    if airyscan:
+        img -= 10000
+        img[img < 0] = 0
+    nz = img[img > 0]
+    return (None if nz.size == 0 else np.percentile(nz, 95)), nz.size
+
+
+@pytest.mark.parametrize("kind", ["structured", "white", "sparse", "two_valued", "single", "zeros", "airyscan",
+                                  "odd_offset"])
+def test_percentile_matches_numpy(nat, kind):
+    rng = np.random.default_rng(11)
+    airy = kind == "airyscan"
+    if kind == "structured":
+        vol = synth.synth_stack(16, 200, 210, seed=3)[0]
+    elif kind == "white":
+        vol = rng.integers(0, 65536, size=(8, 128, 130)).astype(np.uint16)
+    elif kind == "sparse":
+        vol = synth.sparse_spike_stack(8, 100, 100, seed=2)[0]
+    elif kind == "two_valued":
+        vol = np.where(rng.random((4, 64, 64)) < 0.949, 100, 60000).astype(np.uint16)
+    elif kind == "single":
+        vol = np.zeros((2, 8, 8), dtype=np.uint16)
+        vol[1, 3, 3] = 777
+    elif kind == "zeros":
+        vol = np.zeros((3, 16, 16), dtype=np.uint16)
+    elif kind == "airyscan":
+        vol = synth.synth_stack(8, 96, 96, seed=4, airyscan=True)[0]
+    else:
+        vol = rng.integers(0, 5000, size=(3, 37, 41)).astype(np.uint16)
+    if kind == "odd_offset":
+        flat = _cuda(np.concatenate([[0], vol.ravel()]).astype(np.uint16))[1:]      # 2-byte aligned start
+        st = nat.percentile95_nonzero(flat.contiguous() if False else flat, airyscan=airy)
+    else:
+        st = nat.percentile95_nonzero(_cuda(vol), airyscan=airy)
+    want, n = _np_p95(vol, airy)
+    assert st["nonzero_count"] == n
+    assert st["has_nonzero"] == (n > 0)
+    if n:
+        assert np.float32(st["percentile95"]) == np.float32(want)
+
+
+def test_percentile_float32_rank_beyond_2_24(nat):
+    """SURVEY trap T1 at n > 2**24: numpy quantises the rank in float32."""
+    n = 20_000_003
+    vol = np.full(n, 7, dtype=np.uint16)
+    vol[19_000_002:] = 9            # float64 rank 19000001.9 would interpolate, float32 rank does not
+    rng = np.random.default_rng(0)
+    rng.shuffle(vol)
+    st = nat.percentile95_nonzero(_cuda(vol))
+    want = np.percentile(vol.astype(np.float32), 95)
+    assert np.float32(st["percentile95"]) == np.float32(want) == np.float32(9.0)
+
+
+def test_argmax_first_maximum_wins(nat):
+    rng = np.random.default_rng(2)
+    score = rng.integers(0, 4, size=(9, 40, 50)).astype(np.float32)       # many exact ties
+    got = nat.argmax_z(_cuda(score), z_offset=3).cpu().numpy()
+    assert np.array_equal(got, 3 + np.argmax(score, axis=0))
+
+
+@pytest.mark.parametrize("shift,ref", [(0, 0), (2, 1), (-3, 0)])
+def test_band_projection_from_oracle_height_map(nat, shift, ref):
+    Z, Y, X, C = 14, 75, 99, 2
+    img = synth.synth_stack(Z, Y, X, C=C, seed=8)
+    rng = np.random.default_rng(4)
+    zmap = np.clip((synth.height_field(Z, Y, X) + rng.integers(-1, 2, size=(Y, X))).astype(np.int64), 0, Z - 1)
+    zmap[:6, :] = 0
+    zmap[-6:, :] = Z - 1 - max(shift, 0)
+    zmap = np.clip(zmap, 0, Z - 1 - max(shift, 0))
+    image = img.astype(np.float32)
+    z_other = zmap if shift == 0 else np.clip(zmap + shift, 0, Z)
+    want = orc.project_channels(image, ref, orc.band_mask(zmap, Z), orc.band_mask(z_other, Z))
+    got = nat.band_project(_cuda(img), _cuda(zmap.astype(np.int32)), reference_channel=ref, atoh_shift=shift)
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-5, atol=0)
+
+
+def test_band_projection_index_error(nat):
+    img = synth.synth_stack(6, 20, 20, seed=1)
+    zmap = np.full((20, 20), 6, dtype=np.int32)
+    with pytest.raises(IndexError):
+        nat.band_project(_cuda(img), _cuda(zmap))
+
+
+def test_host_c_abi_call_matches_device_call(nat):
+    import torch
+    img = synth.synth_stack(10, 64, 96, C=2, seed=6)
+    proj, zmap, st = nat.project_frame_host(img, 0, mode="exact")
+    p = nat.DeviceProjector(2, 10, 64, 96, mode="exact")
+    dproj, dzmap = p.run(_cuda(img))
+    torch.cuda.synchronize()
+    assert np.array_equal(proj, dproj.cpu().numpy().astype(np.float64))
+    assert np.array_equal(zmap, dzmap.cpu().numpy().astype(np.int64))
+    assert st["has_nonzero"] and not st["band_index_error"]
+    assert p.status()["percentile95"] == st["percentile95"]

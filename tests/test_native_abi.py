@@ -1,0 +1,60 @@
+"""CPU-side checks of the C ABI: the library loads without a GPU and exports every symbol that
+include/tsp_b200.h declares; struct layouts agree with the header."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def native():
+    import __graft_entry__ as entry
+    entry.build()
+    from tissue_image_processing_b200 import _native
+    return _native
+
+
+def _header_functions():
+    text = open(os.path.join(ROOT, "include", "tsp_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(tsp_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported(native):
+    lib = native.load_library()
+    declared = _header_functions()
+    assert "tsp_project_frame_host" in declared and len(declared) >= 15
+    for name in declared:
+        assert hasattr(lib, name), "libtsp_b200.so does not export " + name
+    assert sorted(native.EXPORTS) == declared, "python binding table and header disagree"
+
+
+def test_abi_version_and_struct_sizes(native):
+    lib = native.load_library()
+    assert lib.tsp_abi_version() == 1
+    assert ctypes.sizeof(native.FrameDesc) == 16 * 4
+    assert ctypes.sizeof(native.FrameStatus) == 5 * 4 + 4 + 8 + 4 + 5 * 4   # with alignment padding
+    assert native.FrameStatus.nonzero_count.offset == 24
+
+
+def test_workspace_query_needs_no_gpu(native):
+    lib = native.load_library()
+    d = native.make_desc(1, 32, 512, 512, mode="exact")
+    n = lib.tsp_project_workspace_bytes(ctypes.byref(d))
+    assert n >= 2 * 32 * 512 * 512 * 4
+    bad = native.make_desc(1, 32, 512, 512, reference_channel=3, mode="exact")
+    assert lib.tsp_project_workspace_bytes(ctypes.byref(bad)) == 0
+    assert b"reference_channel" in lib.tsp_last_error()
+
+
+def test_no_cpu_fallback_without_gpu(native):
+    import numpy as np
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import tissue_image_processing_b200 as pkg
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pkg.time_point_surface_projection(np.zeros((1, 1, 4, 8, 8), np.uint16), "TCZYX", 0)

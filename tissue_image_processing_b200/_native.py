@@ -1,0 +1,323 @@
+"""ctypes binding of libtsp_b200.so (C ABI in include/tsp_b200.h).
+
+There is no CPU fallback: if the shared library is missing or no B200 is visible the calls raise.
+PyTorch is used only for device buffers, pinned host buffers and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtsp_b200.so")
+
+MODE_FAST, MODE_EXACT, MODE_BITEXACT = 0, 1, 2
+MODES = {"fast": MODE_FAST, "exact": MODE_EXACT, "bitexact": MODE_BITEXACT}
+
+ERR_INVALID, ERR_CUDA, ERR_WORKSPACE, ERR_BAND_INDEX, ERR_CHOOSE_LIMIT = -1, -2, -3, -4, -5
+
+
+class FrameDesc(C.Structure):
+    _fields_ = [("channels", C.c_int32), ("planes", C.c_int32), ("rows", C.c_int32), ("cols", C.c_int32),
+                ("reference_channel", C.c_int32), ("min_z", C.c_int32), ("max_z", C.c_int32),
+                ("airyscan", C.c_int32), ("atoh_shift", C.c_int32), ("mode", C.c_int32),
+                ("reserved", C.c_int32 * 6)]
+
+
+class FrameStatus(C.Structure):
+    _fields_ = [("band_index_error", C.c_int32), ("has_nonzero", C.c_int32), ("percentile95", C.c_float),
+                ("zmap_min", C.c_int32), ("zmap_max", C.c_int32), ("nonzero_count", C.c_int64),
+                ("near_tie_pixels", C.c_int32), ("reserved", C.c_int32 * 5)]
+
+
+EXPORTS = {
+    # name: (restype, argtypes)
+    "tsp_abi_version": (C.c_int, []),
+    "tsp_last_error": (C.c_char_p, []),
+    "tsp_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "tsp_destroy": (C.c_int, [C.c_void_p]),
+    "tsp_project_workspace_bytes": (C.c_size_t, [C.POINTER(FrameDesc)]),
+    "tsp_project_frame": (C.c_int, [C.c_void_p, C.POINTER(FrameDesc), C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_size_t, C.c_void_p]),
+    "tsp_get_frame_status": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(FrameStatus)]),
+    "tsp_project_frame_host": (C.c_int, [C.c_void_p, C.POINTER(FrameDesc), C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.POINTER(FrameStatus)]),
+    "tsp_gaussian_blur_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                        C.c_int, C.POINTER(C.c_double), C.c_int, C.c_void_p]),
+    "tsp_gaussian_blur_u16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                        C.c_int, C.POINTER(C.c_double), C.c_void_p]),
+    "tsp_percentile95_nonzero_u16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p,
+                                               C.POINTER(FrameStatus)]),
+    "tsp_focus_score_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                      C.c_int, C.c_int, C.c_void_p]),
+    "tsp_argmax_z_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.c_void_p]),
+    "tsp_band_project": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "tsp_band_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "tsp_project_m_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "tsp_project_m": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                C.c_void_p, C.c_size_t, C.c_void_p]),
+    "tsp_debug_coarse_taps": (C.c_int, [C.POINTER(C.c_double), C.c_int]),
+    "tsp_launch_count": (C.c_int64, [C.c_void_p]),
+}
+
+_lib = None
+_lib_lock = threading.Lock()
+_handles = {}
+
+
+class NativeLibraryMissing(ImportError):
+    pass
+
+
+def load_library():
+    """dlopen libtsp_b200.so and declare every symbol of include/tsp_b200.h.  Loading needs no GPU."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.isfile(LIB_PATH):
+            raise NativeLibraryMissing(
+                "%s is missing - run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)" % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in EXPORTS.items():
+            fn = getattr(lib, name)          # AttributeError here = header and library disagree
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = lib
+        return lib
+
+
+def last_error():
+    return load_library().tsp_last_error().decode("utf-8", "replace")
+
+
+class TspError(RuntimeError):
+    def __init__(self, code, where):
+        self.code = code
+        super().__init__("%s failed (%d): %s" % (where, code, last_error()))
+
+
+def check(code, where):
+    """Map C status codes onto the exceptions the reference raises."""
+    if code == 0:
+        return
+    if code == ERR_BAND_INDEX:
+        raise IndexError("index out of bounds for the cropped z axis (reference surface_projection.py:68-69): "
+                         + last_error())
+    if code == ERR_CHOOSE_LIMIT:
+        raise ValueError("Need at least 0 and at most 64 array objects.")
+    raise TspError(code, where)
+
+
+def handle(device=None):
+    """One tsp_handle per (process, GPU)."""
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("tissue_image_processing_b200 needs a B200 GPU (there is no CPU fallback)")
+    if device is None:
+        device = torch.cuda.current_device()
+    device = int(device)
+    lib = load_library()
+    with _lib_lock:
+        h = _handles.get(device)
+        if h is None:
+            out = C.c_void_p()
+            rc = lib.tsp_create(device, C.byref(out))
+            if rc != 0:
+                raise TspError(rc, "tsp_create")
+            h = _handles[device] = out
+        return h
+
+
+def launch_count(device=None):
+    return int(load_library().tsp_launch_count(handle(device)))
+
+
+def make_desc(C_, Z, Y, X, reference_channel=0, min_z=0, max_z=0, airyscan=False, atoh_shift=0, mode="fast"):
+    d = FrameDesc()
+    d.channels, d.planes, d.rows, d.cols = int(C_), int(Z), int(Y), int(X)
+    d.reference_channel = int(reference_channel)
+    d.min_z, d.max_z = int(min_z), int(max_z)
+    d.airyscan = 1 if airyscan else 0
+    d.atoh_shift = int(atoh_shift)
+    d.mode = MODES[mode] if isinstance(mode, str) else int(mode)
+    return d
+
+
+def _stream_ptr(stream=None):
+    import torch
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return C.c_void_p(s.cuda_stream)
+
+
+def status_dict(st):
+    return {"band_index_error": bool(st.band_index_error), "has_nonzero": bool(st.has_nonzero),
+            "percentile95": float(st.percentile95), "zmap_min": int(st.zmap_min), "zmap_max": int(st.zmap_max),
+            "nonzero_count": int(st.nonzero_count), "near_tie_pixels": int(st.near_tie_pixels)}
+
+
+# --------------------------------------------------------------------------------------------------
+# host-buffer operator (the plugin boundary)
+# --------------------------------------------------------------------------------------------------
+def pinned_empty(shape, dtype):
+    """numpy array backed by pinned host memory (DMA-able), kept alive by its torch tensor."""
+    import torch
+    tdtype = {np.dtype("float64"): torch.float64, np.dtype("int64"): torch.int64,
+              np.dtype("uint16"): torch.uint16, np.dtype("float32"): torch.float32,
+              np.dtype("int32"): torch.int32}[np.dtype(dtype)]
+    return torch.empty(tuple(int(s) for s in shape), dtype=tdtype, pin_memory=True).numpy()
+
+
+def project_frame_host(stack, reference_channel, min_z=0, max_z=0, airyscan=False, atoh_shift=0, mode="fast",
+                       device=None, out_proj=None, out_zmap=None):
+    """stack: C-contiguous uint16 ndarray (C,Z,Y,X) in host memory.  Returns (projection float64 (C,Y,X),
+    zmap int64 (Y,X), status dict)."""
+    lib = load_library()
+    h = handle(device)
+    assert stack.dtype == np.uint16 and stack.ndim == 4 and stack.flags.c_contiguous
+    Cn, Z, Y, X = stack.shape
+    desc = make_desc(Cn, Z, Y, X, reference_channel, min_z, max_z, airyscan, atoh_shift, mode)
+    proj = out_proj if out_proj is not None else pinned_empty((Cn, Y, X), np.float64)
+    zmap = out_zmap if out_zmap is not None else pinned_empty((Y, X), np.int64)
+    st = FrameStatus()
+    rc = lib.tsp_project_frame_host(h, C.byref(desc), C.c_void_p(stack.ctypes.data), C.c_void_p(proj.ctypes.data),
+                                    C.c_void_p(zmap.ctypes.data), C.byref(st))
+    check(rc, "tsp_project_frame_host")
+    return proj, zmap, status_dict(st)
+
+
+# --------------------------------------------------------------------------------------------------
+# device-resident operator
+# --------------------------------------------------------------------------------------------------
+class DeviceProjector:
+    """Reusable device-side buffers for one frame shape; everything stays on the current stream."""
+
+    def __init__(self, Cn, Z, Y, X, reference_channel=0, min_z=0, max_z=0, airyscan=False, atoh_shift=0,
+                 mode="fast", device=None):
+        import torch
+        self.lib = load_library()
+        self.h = handle(device)
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
+        self.desc = make_desc(Cn, Z, Y, X, reference_channel, min_z, max_z, airyscan, atoh_shift, mode)
+        self.ws_bytes = int(self.lib.tsp_project_workspace_bytes(C.byref(self.desc)))
+        if self.ws_bytes == 0:
+            raise TspError(ERR_INVALID, "tsp_project_workspace_bytes")
+        self.workspace = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
+        self.proj = torch.empty((Cn, Y, X), dtype=torch.float32, device=self.device)
+        self.zmap = torch.empty((Y, X), dtype=torch.int32, device=self.device)
+
+    def run(self, d_stack, stream=None):
+        """d_stack: CUDA uint16 tensor (C,Z,Y,X), contiguous.  Asynchronous."""
+        assert d_stack.is_cuda and d_stack.is_contiguous() and d_stack.element_size() == 2
+        rc = self.lib.tsp_project_frame(self.h, C.byref(self.desc), C.c_void_p(d_stack.data_ptr()),
+                                        C.c_void_p(self.proj.data_ptr()), C.c_void_p(self.zmap.data_ptr()),
+                                        C.c_void_p(self.workspace.data_ptr()), self.ws_bytes, _stream_ptr(stream))
+        check(rc, "tsp_project_frame")
+        return self.proj, self.zmap
+
+    def status(self, stream=None):
+        st = FrameStatus()
+        rc = self.lib.tsp_get_frame_status(self.h, C.c_void_p(self.workspace.data_ptr()), _stream_ptr(stream),
+                                           C.byref(st))
+        check(rc, "tsp_get_frame_status")
+        return status_dict(st)
+
+
+# --------------------------------------------------------------------------------------------------
+# building blocks (device tensors in, device tensors out)
+# --------------------------------------------------------------------------------------------------
+def _sig3(sigma):
+    return (C.c_double * 3)(*[float(s) for s in sigma])
+
+
+def gaussian_blur(d_vol, sigma, fp64_accumulate=True, stream=None):
+    """scipy.ndimage.gaussian_filter(mode='nearest') of a 3-D CUDA tensor (float32 or uint16)."""
+    import torch
+    lib, h = load_library(), handle(d_vol.device.index)
+    assert d_vol.is_cuda and d_vol.dim() == 3 and d_vol.is_contiguous()
+    Z, Y, X = d_vol.shape
+    out, tmp = torch.empty_like(d_vol), torch.empty_like(d_vol)
+    if d_vol.dtype == torch.float32:
+        rc = lib.tsp_gaussian_blur_f32(h, C.c_void_p(d_vol.data_ptr()), C.c_void_p(out.data_ptr()),
+                                       C.c_void_p(tmp.data_ptr()), Z, Y, X, _sig3(sigma),
+                                       1 if fp64_accumulate else 0, _stream_ptr(stream))
+    elif d_vol.dtype == torch.uint16:
+        rc = lib.tsp_gaussian_blur_u16(h, C.c_void_p(d_vol.data_ptr()), C.c_void_p(out.data_ptr()),
+                                       C.c_void_p(tmp.data_ptr()), Z, Y, X, _sig3(sigma), _stream_ptr(stream))
+    else:
+        raise TypeError("gaussian_blur supports float32 and uint16 volumes, got %s" % d_vol.dtype)
+    check(rc, "tsp_gaussian_blur")
+    return out
+
+
+def percentile95_nonzero(d_vol, airyscan=False, stream=None):
+    lib, h = load_library(), handle(d_vol.device.index)
+    assert d_vol.is_cuda and d_vol.is_contiguous() and d_vol.element_size() == 2
+    st = FrameStatus()
+    rc = lib.tsp_percentile95_nonzero_u16(h, C.c_void_p(d_vol.data_ptr()), d_vol.numel(), 1 if airyscan else 0,
+                                          _stream_ptr(stream), C.byref(st))
+    check(rc, "tsp_percentile95_nonzero_u16")
+    return status_dict(st)
+
+
+def focus_score(d_channel, airyscan=False, fp64_accumulate=False, stream=None):
+    import torch
+    lib, h = load_library(), handle(d_channel.device.index)
+    assert d_channel.is_cuda and d_channel.dim() == 3 and d_channel.is_contiguous()
+    Z, Y, X = d_channel.shape
+    score = torch.empty((Z, Y, X), dtype=torch.float32, device=d_channel.device)
+    tmp = torch.empty_like(score)
+    rc = lib.tsp_focus_score_f32(h, C.c_void_p(d_channel.data_ptr()), C.c_void_p(score.data_ptr()),
+                                 C.c_void_p(tmp.data_ptr()), Z, Y, X, 1 if airyscan else 0,
+                                 1 if fp64_accumulate else 0, _stream_ptr(stream))
+    check(rc, "tsp_focus_score_f32")
+    return score
+
+
+def argmax_z(d_score, z_offset=0, stream=None):
+    import torch
+    lib, h = load_library(), handle(d_score.device.index)
+    Z, Y, X = d_score.shape
+    zmap = torch.empty((Y, X), dtype=torch.int32, device=d_score.device)
+    rc = lib.tsp_argmax_z_f32(h, C.c_void_p(d_score.data_ptr()), C.c_void_p(zmap.data_ptr()), Z, Y, X,
+                              int(z_offset), _stream_ptr(stream))
+    check(rc, "tsp_argmax_z_f32")
+    return zmap
+
+
+def band_project(d_stack, d_zmap, reference_channel=0, atoh_shift=0, airyscan=False, stream=None):
+    """SP:62-81 from a given height map.  d_stack (C,Z,Y,X) uint16, d_zmap (Y,X) int32."""
+    import torch
+    lib, h = load_library(), handle(d_stack.device.index)
+    Cn, Z, Y, X = d_stack.shape
+    proj = torch.empty((Cn, Y, X), dtype=torch.float32, device=d_stack.device)
+    nws = int(lib.tsp_band_workspace_bytes(Cn, Z, Y, X))
+    ws = torch.empty(nws, dtype=torch.uint8, device=d_stack.device)
+    rc = lib.tsp_band_project(h, C.c_void_p(d_stack.data_ptr()), C.c_void_p(d_zmap.data_ptr()),
+                              C.c_void_p(proj.data_ptr()), Cn, Z, Y, X, int(reference_channel), int(atoh_shift),
+                              1 if airyscan else 0, C.c_void_p(ws.data_ptr()), nws, _stream_ptr(stream))
+    check(rc, "tsp_band_project")
+    st = FrameStatus()
+    rc = lib.tsp_get_frame_status(h, C.c_void_p(ws.data_ptr()), _stream_ptr(stream), C.byref(st))
+    check(rc, "tsp_band_project")
+    return proj
+
+
+def project_m(d_channel, method, bin_size, stream=None):
+    """SPM:14-35 on a (Z,Y,X) uint16 CUDA tensor (already channel-selected and z-cropped)."""
+    import torch
+    lib, h = load_library(), handle(d_channel.device.index)
+    Z, Y, X = d_channel.shape
+    out = torch.empty((Y, X), dtype=torch.uint16, device=d_channel.device)
+    nws = int(lib.tsp_project_m_workspace_bytes(Z, Y, X, int(bin_size)))
+    ws = torch.empty(max(nws, 256), dtype=torch.uint8, device=d_channel.device)
+    rc = lib.tsp_project_m(h, C.c_void_p(d_channel.data_ptr()), C.c_void_p(out.data_ptr()), Z, Y, X,
+                           int(method), int(bin_size), C.c_void_p(ws.data_ptr()), nws, _stream_ptr(stream))
+    check(rc, "tsp_project_m")
+    return out

@@ -1,0 +1,393 @@
+// C ABI of libtsp_b200 (see include/tsp_b200.h for the reference interfaces each entry replaces).
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace tsp {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof g_error, fmt, ap);
+    va_end(ap);
+}
+
+struct Crop {
+    int z0;        // first plane of the cropped stack inside the full stack
+    int zc;        // planes after SP:30-31
+    int z_offset;  // added to the argmax (SP:61 adds min_z even when max_z == 0)
+};
+
+static int resolve_crop(const tsp_frame_desc* d, Crop* c) {
+    if (d->channels < 1 || d->planes < 1 || d->rows < 1 || d->cols < 1) {
+        set_error("invalid shape C=%d Z=%d Y=%d X=%d", d->channels, d->planes, d->rows, d->cols);
+        return TSP_ERR_INVALID;
+    }
+    if (d->reference_channel < 0 || d->reference_channel >= d->channels) {
+        set_error("reference_channel %d out of range for %d channels", d->reference_channel, d->channels);
+        return TSP_ERR_INVALID;
+    }
+    if (d->min_z < 0 || d->max_z < 0) {
+        set_error("negative min_z/max_z are not supported");
+        return TSP_ERR_INVALID;
+    }
+    if (d->mode < TSP_MODE_FAST || d->mode > TSP_MODE_BITEXACT) {
+        set_error("unknown mode %d", d->mode);
+        return TSP_ERR_INVALID;
+    }
+    c->z_offset = d->min_z;
+    if (d->max_z > 0) {
+        const int hi = d->max_z < d->planes ? d->max_z : d->planes;
+        c->z0 = d->min_z;
+        c->zc = hi - d->min_z;
+        if (c->zc < 1) {
+            set_error("empty z crop [%d:%d) of %d planes", d->min_z, d->max_z, d->planes);
+            return TSP_ERR_INVALID;
+        }
+    } else {
+        c->z0 = 0;
+        c->zc = d->planes;
+    }
+    return TSP_OK;
+}
+
+struct Workspace {
+    int32_t* status;
+    uint32_t* hist;
+    float* volA;
+    float* volB;
+    void* fast;
+    size_t total;
+};
+
+static Workspace carve(const tsp_frame_desc* d, const Crop& c, void* base) {
+    Workspace w{};
+    char* p = (char*)base;
+    size_t off = 0;
+    w.status = (int32_t*)(p + off);
+    off += align_up(kStatusWords * sizeof(int32_t), 256);
+    w.hist = (uint32_t*)(p + off);
+    off += align_up(kHistBins * sizeof(uint32_t), 256);
+    const size_t vol = align_up((size_t)c.zc * d->rows * d->cols * sizeof(float), 256);
+    if (d->mode == TSP_MODE_FAST) {
+        w.fast = p + off;
+        off += fast_workspace_bytes(c.zc, d->rows, d->cols);
+    } else {
+        w.volA = (float*)(p + off);
+        off += vol;
+        w.volB = (float*)(p + off);
+        off += vol;
+    }
+    w.total = off;
+    return w;
+}
+
+}  // namespace tsp
+
+using namespace tsp;
+
+extern "C" {
+
+int tsp_abi_version(void) { return TSP_ABI_VERSION; }
+
+const char* tsp_last_error(void) { return g_error; }
+
+int tsp_create(int device, tsp_handle** out) {
+    if (!out) return TSP_ERR_INVALID;
+    int count = 0;
+    TSP_CUDA(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) {
+        set_error("device %d not present (%d visible)", device, count);
+        return TSP_ERR_INVALID;
+    }
+    TSP_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    TSP_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("libtsp_b200 is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+        return TSP_ERR_INVALID;
+    }
+    tsp_handle* h = new tsp_handle();
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    TSP_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    TSP_CUDA(cudaMallocHost((void**)&h->h_status, kStatusWords * sizeof(int32_t)));
+    *out = h;
+    return TSP_OK;
+}
+
+int tsp_destroy(tsp_handle* h) {
+    if (!h) return TSP_OK;
+    cudaSetDevice(h->device);
+    for (auto& kv : h->taps) {
+        cudaFree((void*)kv.second.w64);
+        cudaFree((void*)(kv.second.w32 - kTapPad));
+    }
+    for (auto& kv : h->tables) cudaFree(kv.second);
+    if (h->d_scratch) cudaFree(h->d_scratch);
+    if (h->h_status) cudaFreeHost(h->h_status);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return TSP_OK;
+}
+
+int64_t tsp_launch_count(const tsp_handle* h) { return h ? h->launches : 0; }
+
+size_t tsp_project_workspace_bytes(const tsp_frame_desc* desc) {
+    Crop c;
+    if (!desc || resolve_crop(desc, &c)) return 0;
+    return carve(desc, c, nullptr).total;
+}
+
+int tsp_project_frame(tsp_handle* h, const tsp_frame_desc* desc, const uint16_t* d_stack, float* d_proj,
+                      int32_t* d_zmap, void* d_workspace, size_t workspace_bytes, void* cuda_stream) {
+    if (!h || !desc || !d_stack || !d_proj || !d_zmap || !d_workspace) {
+        set_error("null argument");
+        return TSP_ERR_INVALID;
+    }
+    Crop c;
+    int rc = resolve_crop(desc, &c);
+    if (rc) return rc;
+    Workspace w = carve(desc, c, d_workspace);
+    if (workspace_bytes < w.total) {
+        set_error("workspace %zu bytes < required %zu", workspace_bytes, w.total);
+        return TSP_ERR_WORKSPACE;
+    }
+    TSP_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    const int Y = desc->rows, X = desc->cols, C = desc->channels;
+    const size_t plane = (size_t)Y * X;
+    const size_t chan_stride = (size_t)desc->planes * plane;
+    const size_t z0_off = (size_t)c.z0 * plane;
+    const size_t nvox = (size_t)c.zc * plane;
+    const int ped = desc->airyscan ? kAiryscanPedestal : 0;
+    const uint16_t* ref = d_stack + (size_t)desc->reference_channel * chan_stride + z0_off;
+
+    TSP_CUDA(cudaMemsetAsync(w.status, 0, kStatusWords * sizeof(int32_t), s));
+    rc = launch_histogram(h, ref, nvox, w.hist, s);
+    if (rc) return rc;
+    rc = launch_percentile_finalize(h, w.hist, ped, w.status, s);
+    if (rc) return rc;
+
+    if (desc->mode == TSP_MODE_FAST) {
+        rc = launch_fast_score_argmax(h, ref, d_zmap, c.zc, Y, X, ped, c.z_offset, w.status, w.fast, s);
+        if (rc) return rc;
+        return launch_band_project_ex(h, d_stack, chan_stride, z0_off, d_zmap, d_proj, C, c.zc, Y, X,
+                                      desc->reference_channel, desc->atoh_shift, ped, w.status, s);
+    }
+    const bool fp64 = desc->mode == TSP_MODE_BITEXACT;
+    const double sig_pre[3] = {0.5, 1.0, 1.0};       // SP:37
+    const double sig_score[3] = {0.5, 30.0, 30.0};   // SP:55
+    rc = launch_prepare(h, ref, w.volA, nvox, ped, w.status, s);
+    if (rc) return rc;
+    rc = gaussian_blur<float>(h, w.volA, w.volB, w.volA, c.zc, Y, X, sig_pre, fp64, s);
+    if (rc) return rc;
+    rc = gaussian_blur<float>(h, w.volB, w.volA, w.volB, c.zc, Y, X, sig_score, fp64, s);
+    if (rc) return rc;
+    rc = launch_argmax(h, w.volA, d_zmap, c.zc, Y, X, c.z_offset, w.status, s);
+    if (rc) return rc;
+    if (fp64)
+        return launch_band_project_bitexact_ex(h, d_stack, chan_stride, z0_off, d_zmap, d_proj, C, c.zc, Y, X,
+                                               desc->reference_channel, desc->atoh_shift, ped, w.volA, w.volB,
+                                               w.status, s);
+    return launch_band_project_ex(h, d_stack, chan_stride, z0_off, d_zmap, d_proj, C, c.zc, Y, X,
+                                  desc->reference_channel, desc->atoh_shift, ped, w.status, s);
+}
+
+static void fill_status(const int32_t* st, tsp_frame_status* out) {
+    memset(out, 0, sizeof *out);
+    out->band_index_error = st[ST_BAND_ERR];
+    out->has_nonzero = st[ST_HAS_NONZERO];
+    memcpy(&out->percentile95, &st[ST_P95_BITS], sizeof(float));
+    out->zmap_min = st[ST_ZMIN];
+    out->zmap_max = st[ST_ZMAX];
+    out->nonzero_count = (int64_t)(((uint64_t)(uint32_t)st[ST_NZ_HI] << 32) | (uint32_t)st[ST_NZ_LO]);
+    out->near_tie_pixels = st[ST_NEAR_TIE];
+}
+
+int tsp_get_frame_status(tsp_handle* h, const void* d_workspace, void* cuda_stream, tsp_frame_status* out) {
+    if (!h || !d_workspace || !out) return TSP_ERR_INVALID;
+    TSP_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    int32_t st[kStatusWords];
+    TSP_CUDA(cudaMemcpyAsync(st, d_workspace, sizeof st, cudaMemcpyDeviceToHost, s));
+    TSP_CUDA(cudaStreamSynchronize(s));
+    fill_status(st, out);
+    if (out->band_index_error) {
+        set_error("height map indexes past the cropped stack (reference raises IndexError)");
+        return TSP_ERR_BAND_INDEX;
+    }
+    return TSP_OK;
+}
+
+static int ensure_scratch(tsp_handle* h, size_t bytes) {
+    if (h->d_scratch_bytes >= bytes) return TSP_OK;
+    if (h->d_scratch) TSP_CUDA(cudaFree(h->d_scratch));
+    h->d_scratch = nullptr;
+    h->d_scratch_bytes = 0;
+    TSP_CUDA(cudaMalloc(&h->d_scratch, bytes));
+    h->d_scratch_bytes = bytes;
+    return TSP_OK;
+}
+
+int tsp_project_frame_host(tsp_handle* h, const tsp_frame_desc* desc, const uint16_t* h_stack, double* h_proj,
+                           int64_t* h_zmap, tsp_frame_status* status) {
+    if (!h || !desc || !h_stack || !h_proj || !h_zmap) {
+        set_error("null argument");
+        return TSP_ERR_INVALID;
+    }
+    Crop c;
+    int rc = resolve_crop(desc, &c);
+    if (rc) return rc;
+    TSP_CUDA(cudaSetDevice(h->device));
+    std::lock_guard<std::mutex> lock(h->host_mu);
+    const size_t plane = (size_t)desc->rows * desc->cols;
+    const size_t nstack = (size_t)desc->channels * desc->planes * plane;
+    const size_t nproj = (size_t)desc->channels * plane;
+    const size_t ws = tsp_project_workspace_bytes(desc);
+    size_t off = 0;
+    const size_t o_stack = off;  off += align_up(nstack * sizeof(uint16_t), 256);
+    const size_t o_proj = off;   off += align_up(nproj * sizeof(float), 256);
+    const size_t o_zmap = off;   off += align_up(plane * sizeof(int32_t), 256);
+    const size_t o_proj64 = off; off += align_up(nproj * sizeof(double), 256);
+    const size_t o_zmap64 = off; off += align_up(plane * sizeof(int64_t), 256);
+    const size_t o_ws = off;     off += ws;
+    rc = ensure_scratch(h, off);
+    if (rc) return rc;
+    char* base = (char*)h->d_scratch;
+    cudaStream_t s = h->stream;
+    TSP_CUDA(cudaMemcpyAsync(base + o_stack, h_stack, nstack * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
+    rc = tsp_project_frame(h, desc, (const uint16_t*)(base + o_stack), (float*)(base + o_proj),
+                           (int32_t*)(base + o_zmap), base + o_ws, ws, s);
+    if (rc) return rc;
+    rc = launch_widen_outputs(h, (const float*)(base + o_proj), (const int32_t*)(base + o_zmap),
+                              (double*)(base + o_proj64), (int64_t*)(base + o_zmap64), nproj, plane, s);
+    if (rc) return rc;
+    TSP_CUDA(cudaMemcpyAsync(h->h_status, base + o_ws, kStatusWords * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    TSP_CUDA(cudaMemcpyAsync(h_proj, base + o_proj64, nproj * sizeof(double), cudaMemcpyDeviceToHost, s));
+    TSP_CUDA(cudaMemcpyAsync(h_zmap, base + o_zmap64, plane * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    TSP_CUDA(cudaStreamSynchronize(s));
+    tsp_frame_status st;
+    fill_status(h->h_status, &st);
+    if (status) *status = st;
+    if (st.band_index_error) {
+        set_error("height map indexes past the cropped stack (reference raises IndexError)");
+        return TSP_ERR_BAND_INDEX;
+    }
+    return TSP_OK;
+}
+
+int tsp_gaussian_blur_f32(tsp_handle* h, const float* d_in, float* d_out, float* d_tmp, int planes, int rows,
+                          int cols, const double sigma[3], int fp64_accumulate, void* cuda_stream) {
+    if (!h || !d_in || !d_out || !d_tmp || !sigma || planes < 1 || rows < 1 || cols < 1) return TSP_ERR_INVALID;
+    TSP_CUDA(cudaSetDevice(h->device));
+    return gaussian_blur<float>(h, d_in, d_out, d_tmp, planes, rows, cols, sigma, fp64_accumulate != 0,
+                                (cudaStream_t)cuda_stream);
+}
+
+int tsp_gaussian_blur_u16(tsp_handle* h, const uint16_t* d_in, uint16_t* d_out, uint16_t* d_tmp, int planes,
+                          int rows, int cols, const double sigma[3], void* cuda_stream) {
+    if (!h || !d_in || !d_out || !d_tmp || !sigma || planes < 1 || rows < 1 || cols < 1) return TSP_ERR_INVALID;
+    TSP_CUDA(cudaSetDevice(h->device));
+    return gaussian_blur<uint16_t>(h, d_in, d_out, d_tmp, planes, rows, cols, sigma, true,
+                                   (cudaStream_t)cuda_stream);
+}
+
+int tsp_percentile95_nonzero_u16(tsp_handle* h, const uint16_t* d_volume, size_t count, int airyscan,
+                                 void* cuda_stream, tsp_frame_status* out) {
+    if (!h || !d_volume || !out) return TSP_ERR_INVALID;
+    TSP_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    const size_t bytes = align_up(kStatusWords * sizeof(int32_t), 256) + kHistBins * sizeof(uint32_t);
+    std::lock_guard<std::mutex> lock(h->host_mu);
+    int rc = ensure_scratch(h, bytes);
+    if (rc) return rc;
+    int32_t* st = (int32_t*)h->d_scratch;
+    uint32_t* hist = (uint32_t*)((char*)h->d_scratch + align_up(kStatusWords * sizeof(int32_t), 256));
+    TSP_CUDA(cudaMemsetAsync(st, 0, kStatusWords * sizeof(int32_t), s));
+    rc = launch_histogram(h, d_volume, count, hist, s);
+    if (rc) return rc;
+    rc = launch_percentile_finalize(h, hist, airyscan ? kAiryscanPedestal : 0, st, s);
+    if (rc) return rc;
+    TSP_CUDA(cudaMemcpyAsync(h->h_status, st, kStatusWords * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    TSP_CUDA(cudaStreamSynchronize(s));
+    fill_status(h->h_status, out);
+    return TSP_OK;
+}
+
+int tsp_focus_score_f32(tsp_handle* h, const uint16_t* d_channel, float* d_score, float* d_tmp, int planes,
+                        int rows, int cols, int airyscan, int fp64_accumulate, void* cuda_stream) {
+    if (!h || !d_channel || !d_score || !d_tmp || planes < 1 || rows < 1 || cols < 1) return TSP_ERR_INVALID;
+    TSP_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    const size_t bytes = align_up(kStatusWords * sizeof(int32_t), 256) + kHistBins * sizeof(uint32_t);
+    std::lock_guard<std::mutex> lock(h->host_mu);
+    int rc = ensure_scratch(h, bytes);
+    if (rc) return rc;
+    int32_t* st = (int32_t*)h->d_scratch;
+    uint32_t* hist = (uint32_t*)((char*)h->d_scratch + align_up(kStatusWords * sizeof(int32_t), 256));
+    const size_t nvox = (size_t)planes * rows * cols;
+    const int ped = airyscan ? kAiryscanPedestal : 0;
+    TSP_CUDA(cudaMemsetAsync(st, 0, kStatusWords * sizeof(int32_t), s));
+    rc = launch_histogram(h, d_channel, nvox, hist, s);
+    if (rc) return rc;
+    rc = launch_percentile_finalize(h, hist, ped, st, s);
+    if (rc) return rc;
+    rc = launch_prepare(h, d_channel, d_score, nvox, ped, st, s);
+    if (rc) return rc;
+    const double sig_pre[3] = {0.5, 1.0, 1.0}, sig_score[3] = {0.5, 30.0, 30.0};
+    const bool fp64 = fp64_accumulate != 0;
+    rc = gaussian_blur<float>(h, d_score, d_tmp, d_score, planes, rows, cols, sig_pre, fp64, s);
+    if (rc) return rc;
+    return gaussian_blur<float>(h, d_tmp, d_score, d_tmp, planes, rows, cols, sig_score, fp64, s);
+}
+
+int tsp_argmax_z_f32(tsp_handle* h, const float* d_score, int32_t* d_zmap, int planes, int rows, int cols,
+                     int z_offset, void* cuda_stream) {
+    if (!h || !d_score || !d_zmap || planes < 1 || rows < 1 || cols < 1) return TSP_ERR_INVALID;
+    TSP_CUDA(cudaSetDevice(h->device));
+    return launch_argmax(h, d_score, d_zmap, planes, rows, cols, z_offset, nullptr, (cudaStream_t)cuda_stream);
+}
+
+size_t tsp_band_workspace_bytes(int, int, int, int) { return align_up(kStatusWords * sizeof(int32_t), 256); }
+
+int tsp_band_project(tsp_handle* h, const uint16_t* d_stack, const int32_t* d_zmap, float* d_proj, int channels,
+                     int planes, int rows, int cols, int reference_channel, int atoh_shift, int airyscan,
+                     void* d_workspace, size_t workspace_bytes, void* cuda_stream) {
+    if (!h || !d_stack || !d_zmap || !d_proj || !d_workspace || channels < 1 || planes < 1 || rows < 1 || cols < 1)
+        return TSP_ERR_INVALID;
+    if (workspace_bytes < tsp_band_workspace_bytes(channels, planes, rows, cols)) return TSP_ERR_WORKSPACE;
+    TSP_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    TSP_CUDA(cudaMemsetAsync(d_workspace, 0, kStatusWords * sizeof(int32_t), s));
+    const size_t plane = (size_t)rows * cols;
+    return launch_band_project_ex(h, d_stack, (size_t)planes * plane, 0, d_zmap, d_proj, channels, planes, rows,
+                                  cols, reference_channel, atoh_shift, airyscan ? kAiryscanPedestal : 0,
+                                  (int32_t*)d_workspace, s);
+}
+
+size_t tsp_project_m_workspace_bytes(int planes, int rows, int cols, int bin_size) {
+    if (planes < 1 || rows < 1 || cols < 1 || bin_size < 1) return 0;
+    const size_t vox = align_up((size_t)planes * rows * cols, 128);
+    const size_t by = (rows + bin_size - 1) / bin_size, bx = (cols + bin_size - 1) / bin_size;
+    return 2 * vox * sizeof(uint16_t) + (size_t)planes * by * bx * sizeof(double) + 256;
+}
+
+int tsp_project_m(tsp_handle* h, const uint16_t* d_channel, uint16_t* d_out, int planes, int rows, int cols,
+                  int method, int bin_size, void* d_workspace, size_t workspace_bytes, void* cuda_stream) {
+    if (!h || !d_channel || !d_out || !d_workspace || planes < 1 || rows < 1 || cols < 1 || bin_size < 1 ||
+        method < 0 || method > 1)
+        return TSP_ERR_INVALID;
+    if (planes >= 64) {
+        set_error("np.choose accepts fewer than 64 planes (reference raises ValueError)");
+        return TSP_ERR_CHOOSE_LIMIT;
+    }
+    if (workspace_bytes < tsp_project_m_workspace_bytes(planes, rows, cols, bin_size)) return TSP_ERR_WORKSPACE;
+    TSP_CUDA(cudaSetDevice(h->device));
+    return launch_project_m(h, d_channel, d_out, planes, rows, cols, method, bin_size, d_workspace,
+                            (cudaStream_t)cuda_stream);
+}
+
+}  // extern "C"

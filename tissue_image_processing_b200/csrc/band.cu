@@ -1,0 +1,416 @@
+// Stages K4-K7: argmax over z (SP:61), band mask (SP:62-71) and weighted max projection (SP:72-81).
+//
+// The reference scatters a one-hot (Z, Y*X) volume at the height map, blurs it with sigma=(1,2,2)
+// and takes max_z(image * mask).  band_project_kernel never materialises either volume: for a
+// 32x64 pixel tile it walks only the planes near the tile's heights, builds the XY-blurred
+// one-hot plane A[z''] on the fly from the height-map tile (x pass into shared memory, y pass into
+// registers), keeps a 9-plane window of A per pixel and applies the z taps as the exact
+// edge-replicating 9-band matrix (SURVEY trap T9), multiplying the raw uint16 voxels as they
+// stream by.  Only planes inside the band are read from HBM.
+#include "common.cuh"
+
+namespace tsp {
+
+__constant__ float c_w2[17];      // sigma = 2 taps (SP:70, axes y and x)
+
+// ---- K4 ----------------------------------------------------------------------------------------
+__global__ void argmax_z_kernel(const float* __restrict__ score, int32_t* __restrict__ zmap, int Z,
+                                size_t plane, int z_offset) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < plane; p += stride) {
+        float best = score[p];
+        int bz = 0;
+        for (int z = 1; z < Z; ++z) {
+            const float v = score[(size_t)z * plane + p];
+            if (v > best) {          // strict: first maximum wins, like np.argmax
+                best = v;
+                bz = z;
+            }
+        }
+        zmap[p] = bz + z_offset;
+    }
+}
+
+int launch_argmax(tsp_handle* h, const float* d_score, int32_t* d_zmap, int Z, int Y, int X,
+                  int z_offset, int32_t* d_status, cudaStream_t s) {
+    (void)d_status;
+    const size_t plane = (size_t)Y * X;
+    const int threads = 256;
+    size_t blocks = (plane + threads - 1) / threads;
+    if (blocks > (size_t)h->sm_count * 32) blocks = (size_t)h->sm_count * 32;
+    argmax_z_kernel<<<(int)blocks, threads, 0, s>>>(d_score, d_zmap, Z, plane, z_offset);
+    TSP_LAUNCH_CHECK(h);
+    return TSP_OK;
+}
+
+// ---- height-map range + IndexError condition (SP:62, SP:68-69) -------------------------------
+__global__ void zmap_range_kernel(const int32_t* __restrict__ zmap, size_t n, int32_t* __restrict__ status) {
+    int lo = INT32_MAX, hi = INT32_MIN;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int v = zmap[i];
+        lo = min(lo, v);
+        hi = max(hi, v);
+    }
+    for (int o = 16; o; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&status[ST_ZMIN], lo);
+        atomicMax(&status[ST_ZMAX], hi);
+    }
+}
+
+__global__ void zmap_range_init_kernel(int32_t* status) {
+    status[ST_ZMIN] = INT32_MAX;
+    status[ST_ZMAX] = INT32_MIN;
+}
+
+// the reference indexes the cropped stack with chosen_z (and clip(chosen_z+shift, 0, Z), upper bound
+// inclusive): any index >= Z raises IndexError; negative indices cannot occur.
+__global__ void band_check_kernel(int32_t* status, int Z, int shift) {
+    const int hi = status[ST_ZMAX];
+    int err = hi >= Z;
+    if (shift != 0) {
+        int hs = hi + shift;
+        hs = hs < 0 ? 0 : (hs > Z ? Z : hs);
+        err |= hs >= Z;
+    }
+    if (status[ST_ZMIN] < 0) err = 1;
+    status[ST_BAND_ERR] = err;
+}
+
+// ---- K5-K7 fused -------------------------------------------------------------------------------
+constexpr int kBandTY = 32, kBandTX = 64, kBandHalo = 8;
+constexpr int kBandThreads = 256;
+constexpr int kBandPix = 8;                 // pixels (consecutive rows) per thread
+constexpr int kBandMaxCh = 2;               // channels per CTA
+constexpr int kBandMaxPlanes = 4096;
+
+struct BandArgs {
+    const uint16_t* stack;      // (C, Zfull, Y, X)
+    size_t channel_stride;      // Zfull*Y*X
+    size_t z0_offset;           // min_z*Y*X : first plane of the cropped stack
+    const int32_t* zmap;        // (Y, X) indices into the cropped stack (before shift)
+    float* proj;                // (C, Y, X)
+    const float* wz;            // (Z, 9) edge-replicating z taps, wz[z*9+i] multiplies A[z-4+i]
+    const int32_t* status;
+    int Z, Y, X;
+    int shift;
+    int pedestal;
+    int nch;
+    int ch[16];
+};
+
+__global__ void __launch_bounds__(kBandThreads, 2) band_project_kernel(const BandArgs a) {
+    constexpr int CW = kBandTX + 2 * kBandHalo;      // 80
+    constexpr int CH = kBandTY + 2 * kBandHalo;      // 48
+    __shared__ __align__(16) int cz_s[CH][CW];
+    __shared__ __align__(16) float b_s[CH][kBandTX];
+    __shared__ uint32_t present[kBandMaxPlanes / 32];
+    __shared__ int zlo_s, zhi_s;
+
+    if (a.status[ST_BAND_ERR]) return;          // the reference raises before projecting
+
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * kBandTX, y0 = blockIdx.y * kBandTY;
+    if (tid == 0) {
+        zlo_s = INT32_MAX;
+        zhi_s = INT32_MIN;
+    }
+    for (int i = tid; i < kBandMaxPlanes / 32; i += kBandThreads) present[i] = 0;
+    __syncthreads();
+    {
+        int lo = INT32_MAX, hi = INT32_MIN;
+        for (int i = tid; i < CH * CW; i += kBandThreads) {
+            const int yy = min(max(y0 - kBandHalo + i / CW, 0), a.Y - 1);
+            const int xx = min(max(x0 - kBandHalo + i % CW, 0), a.X - 1);
+            int v = a.zmap[(size_t)yy * a.X + xx];
+            if (a.shift != 0) v = min(max(v + a.shift, 0), a.Z);
+            cz_s[i / CW][i % CW] = v;
+            lo = min(lo, v);
+            hi = max(hi, v);
+            atomicOr(&present[v >> 5], 1u << (v & 31));
+        }
+        atomicMin(&zlo_s, lo);
+        atomicMax(&zhi_s, hi);
+    }
+    __syncthreads();
+    const int zlo = zlo_s, zhi = zhi_s;
+
+    const int tx = tid % kBandTX, ty = tid / kBandTX;          // ty in 0..3 -> rows ty*8 .. ty*8+7
+    const int x = x0 + tx;
+    const int ybase = ty * kBandPix;
+    const int c0 = blockIdx.z * kBandMaxCh;
+    const int nc = min(kBandMaxCh, a.nch - c0);
+
+    float win[kBandPix][9];
+    float best[kBandMaxCh][kBandPix];
+#pragma unroll
+    for (int p = 0; p < kBandPix; ++p) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) win[p][i] = 0.f;
+#pragma unroll
+        for (int c = 0; c < kBandMaxCh; ++c) best[c][p] = 0.f;
+    }
+
+    for (int t = zlo; t <= zhi + 8; ++t) {
+        float a_new[kBandPix];
+#pragma unroll
+        for (int p = 0; p < kBandPix; ++p) a_new[p] = 0.f;
+        const bool have = t <= zhi && ((present[t >> 5] >> (t & 31)) & 1u);
+        if (have) {                                   // block-uniform
+            // x pass: b_s[row][x] = sum_dx w2[dx] * [cz(row, x+dx) == t], 4 outputs per task
+            for (int task = tid; task < CH * (kBandTX / 4); task += kBandThreads) {
+                const int row = task / (kBandTX / 4), xq = (task % (kBandTX / 4)) * 4;
+                float oh[20];
+                const int4* src = reinterpret_cast<const int4*>(&cz_s[row][xq]);
+#pragma unroll
+                for (int q = 0; q < 5; ++q) {
+                    const int4 v = src[q];
+                    oh[4 * q + 0] = v.x == t ? 1.f : 0.f;
+                    oh[4 * q + 1] = v.y == t ? 1.f : 0.f;
+                    oh[4 * q + 2] = v.z == t ? 1.f : 0.f;
+                    oh[4 * q + 3] = v.w == t ? 1.f : 0.f;
+                }
+                float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int k = 0; k < 17; ++k)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) o[j] = fmaf(c_w2[k], oh[j + k], o[j]);
+                *reinterpret_cast<float4*>(&b_s[row][xq]) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+            __syncthreads();
+            // y pass into registers: a_new[p] = sum_dy w2[dy] * b_s[ybase + p + dy][tx]
+#pragma unroll
+            for (int i = 0; i < kBandPix + 16; ++i) {
+                const float v = b_s[ybase + i][tx];
+#pragma unroll
+                for (int p = 0; p < kBandPix; ++p) {
+                    const int k = i - p;
+                    if (k >= 0 && k < 17) a_new[p] = fmaf(c_w2[k], v, a_new[p]);
+                }
+            }
+            __syncthreads();
+        }
+        const int z = t - 4;
+        const bool zvalid = z >= 0 && z < a.Z;
+        float wzr[9];
+        if (zvalid) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) wzr[i] = a.wz[z * 9 + i];
+        }
+#pragma unroll
+        for (int p = 0; p < kBandPix; ++p) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) win[p][i] = win[p][i + 1];
+            win[p][8] = a_new[p];
+        }
+        if (zvalid) {
+#pragma unroll
+            for (int p = 0; p < kBandPix; ++p) {
+                const int y = y0 + ybase + p;
+                float m = 0.f;
+#pragma unroll
+                for (int i = 0; i < 9; ++i) m = fmaf(wzr[i], win[p][i], m);
+                if (y < a.Y && x < a.X && m != 0.f) {
+                    const size_t off = a.z0_offset + ((size_t)z * a.Y + y) * a.X + x;
+#pragma unroll
+                    for (int c = 0; c < kBandMaxCh; ++c) {
+                        if (c < nc) {
+                            int v = (int)a.stack[(size_t)a.ch[c0 + c] * a.channel_stride + off] - a.pedestal;
+                            const float f = (float)(v > 0 ? v : 0);
+                            best[c][p] = fmaxf(best[c][p], __fmul_rn(f, m));
+                        }
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < kBandPix; ++p) {
+        const int y = y0 + ybase + p;
+        if (y < a.Y && x < a.X) {
+#pragma unroll
+            for (int c = 0; c < kBandMaxCh; ++c)
+                if (c < nc) a.proj[((size_t)a.ch[c0 + c] * a.Y + y) * a.X + x] = best[c][p];
+        }
+    }
+}
+
+static int get_wz_table(tsp_handle* h, int Z, const float** out) {
+    char key[32];
+    snprintf(key, sizeof key, "wz%d", Z);
+    std::lock_guard<std::mutex> lock(h->mu);
+    auto it = h->tables.find(key);
+    if (it != h->tables.end()) {
+        *out = (const float*)it->second;
+        return TSP_OK;
+    }
+    static bool w2_uploaded = false;
+    if (!w2_uploaded) {
+        std::vector<double> w2 = gaussian_taps(2.0);
+        float w2f[17];
+        for (int i = 0; i < 17; ++i) w2f[i] = (float)w2[i];
+        TSP_CUDA(cudaMemcpyToSymbol(c_w2, w2f, sizeof w2f));
+        w2_uploaded = true;
+    }
+    std::vector<double> wz = gaussian_taps(1.0);       // radius 4
+    std::vector<float> tab((size_t)Z * 9, 0.f);
+    for (int z = 0; z < Z; ++z) {
+        std::vector<double> row(9, 0.0);
+        for (int k = -4; k <= 4; ++k) {
+            int zz = z + k;
+            zz = zz < 0 ? 0 : (zz > Z - 1 ? Z - 1 : zz);
+            row[zz - z + 4] += wz[k + 4];
+        }
+        for (int i = 0; i < 9; ++i) tab[(size_t)z * 9 + i] = (float)row[i];
+    }
+    float* d = nullptr;
+    TSP_CUDA(cudaMalloc(&d, tab.size() * sizeof(float)));
+    TSP_CUDA(cudaMemcpy(d, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice));
+    h->tables[key] = d;
+    *out = d;
+    return TSP_OK;
+}
+
+static int launch_band_range(tsp_handle* h, const int32_t* d_zmap, int Z, int Y, int X, int shift,
+                             int32_t* d_status, cudaStream_t s) {
+    zmap_range_init_kernel<<<1, 1, 0, s>>>(d_status);
+    TSP_LAUNCH_CHECK(h);
+    const size_t n = (size_t)Y * X;
+    size_t blocks = (n + 255) / 256;
+    if (blocks > (size_t)h->sm_count * 8) blocks = (size_t)h->sm_count * 8;
+    zmap_range_kernel<<<(int)blocks, 256, 0, s>>>(d_zmap, n, d_status);
+    TSP_LAUNCH_CHECK(h);
+    band_check_kernel<<<1, 1, 0, s>>>(d_status, Z, shift);
+    TSP_LAUNCH_CHECK(h);
+    return TSP_OK;
+}
+
+int launch_band_project_ex(tsp_handle* h, const uint16_t* d_stack, size_t channel_stride, size_t z0_offset,
+                           const int32_t* d_zmap, float* d_proj, int C, int Z, int Y, int X, int ref_c,
+                           int shift, int pedestal, int32_t* d_status, cudaStream_t s) {
+    if (Z > kBandMaxPlanes) {
+        set_error("band projection supports at most %d planes", kBandMaxPlanes);
+        return TSP_ERR_INVALID;
+    }
+    if (C > 17) {
+        set_error("band projection supports at most 17 channels");
+        return TSP_ERR_INVALID;
+    }
+    const float* wz = nullptr;
+    int rc = get_wz_table(h, Z, &wz);
+    if (rc) return rc;
+    rc = launch_band_range(h, d_zmap, Z, Y, X, shift, d_status, s);
+    if (rc) return rc;
+    BandArgs a;
+    a.stack = d_stack;
+    a.channel_stride = channel_stride;
+    a.z0_offset = z0_offset;
+    a.zmap = d_zmap;
+    a.proj = d_proj;
+    a.wz = wz;
+    a.status = d_status;
+    a.Z = Z;
+    a.Y = Y;
+    a.X = X;
+    a.pedestal = pedestal;
+    dim3 grid((X + kBandTX - 1) / kBandTX, (Y + kBandTY - 1) / kBandTY, 1);
+    // pass 1: every channel that uses the un-shifted mask (all of them when shift == 0)
+    a.shift = 0;
+    a.nch = 0;
+    for (int c = 0; c < C; ++c)
+        if (shift == 0 || c == ref_c) a.ch[a.nch++] = c;
+    grid.z = (a.nch + kBandMaxCh - 1) / kBandMaxCh;
+    band_project_kernel<<<grid, kBandThreads, 0, s>>>(a);
+    TSP_LAUNCH_CHECK(h);
+    if (shift != 0 && C > 1) {
+        a.shift = shift;
+        a.nch = 0;
+        for (int c = 0; c < C; ++c)
+            if (c != ref_c) a.ch[a.nch++] = c;
+        grid.z = (a.nch + kBandMaxCh - 1) / kBandMaxCh;
+        band_project_kernel<<<grid, kBandThreads, 0, s>>>(a);
+        TSP_LAUNCH_CHECK(h);
+    }
+    return TSP_OK;
+}
+
+// ---- bit-exact variant: materialise the one-hot volume and run the scipy-order passes ----------
+__global__ void onehot_kernel(const int32_t* __restrict__ zmap, float* __restrict__ vol, int Z, size_t plane,
+                              int shift, const int32_t* __restrict__ status) {
+    if (status[ST_BAND_ERR]) return;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < plane; p += stride) {
+        int v = zmap[p];
+        if (shift != 0) v = min(max(v + shift, 0), Z);
+        for (int z = 0; z < Z; ++z) vol[(size_t)z * plane + p] = z == v ? 1.f : 0.f;
+    }
+}
+
+__global__ void mulmax_kernel(const uint16_t* __restrict__ chan, const float* __restrict__ mask,
+                              float* __restrict__ proj, int Z, size_t plane, int pedestal,
+                              const int32_t* __restrict__ status) {
+    if (status[ST_BAND_ERR]) return;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < plane; p += stride) {
+        float best = -INFINITY;
+        for (int z = 0; z < Z; ++z) {
+            int v = (int)chan[(size_t)z * plane + p] - pedestal;
+            const float f = (float)(v > 0 ? v : 0);
+            best = fmaxf(best, __fmul_rn(f, mask[(size_t)z * plane + p]));
+        }
+        proj[p] = best;
+    }
+}
+
+int launch_band_project_bitexact_ex(tsp_handle* h, const uint16_t* d_stack, size_t channel_stride,
+                                    size_t z0_offset, const int32_t* d_zmap, float* d_proj, int C, int Z,
+                                    int Y, int X, int ref_c, int shift, int pedestal, float* d_volA,
+                                    float* d_volB, int32_t* d_status, cudaStream_t s) {
+    int rc = launch_band_range(h, d_zmap, Z, Y, X, shift, d_status, s);
+    if (rc) return rc;
+    const size_t plane = (size_t)Y * X;
+    size_t blocks = (plane + 255) / 256;
+    if (blocks > (size_t)h->sm_count * 32) blocks = (size_t)h->sm_count * 32;
+    const double sig[3] = {1.0, 2.0, 2.0};
+    for (int pass = 0; pass < 2; ++pass) {
+        const int sh = pass == 0 ? 0 : shift;
+        if (pass == 1 && (shift == 0 || C == 1)) break;
+        onehot_kernel<<<(int)blocks, 256, 0, s>>>(d_zmap, d_volA, Z, plane, sh, d_status);
+        TSP_LAUNCH_CHECK(h);
+        rc = gaussian_blur<float>(h, d_volA, d_volB, d_volA, Z, Y, X, sig, true, s);
+        if (rc) return rc;
+        for (int c = 0; c < C; ++c) {
+            const bool uses = (shift == 0) ? (pass == 0) : ((c == ref_c) == (pass == 0));
+            if (!uses) continue;
+            mulmax_kernel<<<(int)blocks, 256, 0, s>>>(d_stack + (size_t)c * channel_stride + z0_offset, d_volB,
+                                                      d_proj + (size_t)c * plane, Z, plane, pedestal, d_status);
+            TSP_LAUNCH_CHECK(h);
+        }
+    }
+    return TSP_OK;
+}
+
+// ---- output widening (the reference returns float64 / int64) ---------------------------------
+__global__ void widen_kernel(const float* __restrict__ p32, const int32_t* __restrict__ z32,
+                             double* __restrict__ p64, long long* __restrict__ z64, size_t np, size_t nz) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < np; i += stride) p64[i] = (double)p32[i];
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nz; i += stride) z64[i] = (long long)z32[i];
+}
+
+int launch_widen_outputs(tsp_handle* h, const float* d_proj, const int32_t* d_zmap, double* d_proj64,
+                         int64_t* d_zmap64, size_t nproj, size_t nz, cudaStream_t s) {
+    size_t n = nproj > nz ? nproj : nz;
+    size_t blocks = (n + 255) / 256;
+    if (blocks > (size_t)h->sm_count * 16) blocks = (size_t)h->sm_count * 16;
+    if (blocks == 0) blocks = 1;
+    widen_kernel<<<(int)blocks, 256, 0, s>>>(d_proj, d_zmap, d_proj64, (long long*)d_zmap64, nproj, nz);
+    TSP_LAUNCH_CHECK(h);
+    return TSP_OK;
+}
+
+}  // namespace tsp

@@ -1,0 +1,127 @@
+// Shared declarations of libtsp_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/tsp_b200.h"
+
+namespace tsp {
+
+constexpr int kAiryscanPedestal = 10000;   // SP:28
+constexpr int kHistBins = 65536;
+constexpr int kStatusWords = 64;           // device status block (int32 words) at workspace start
+
+// indices into the device status block
+enum StatusWord {
+    ST_BAND_ERR = 0,
+    ST_HAS_NONZERO = 1,
+    ST_P95_BITS = 2,
+    ST_ZMIN = 3,
+    ST_ZMAX = 4,
+    ST_NZ_LO = 5,
+    ST_NZ_HI = 6,
+    ST_NEAR_TIE = 7,
+    ST_TICKET = 8,       // scratch counters for "last block finishes" patterns
+    ST_TICKET2 = 9,
+};
+
+void set_error(const char* fmt, ...);
+
+#define TSP_CUDA(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            tsp::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                           __LINE__);                                                        \
+            return TSP_ERR_CUDA;                                                             \
+        }                                                                                    \
+    } while (0)
+
+#define TSP_LAUNCH_CHECK(h)                                                                    \
+    do {                                                                                       \
+        (h)->launches++;                                                                       \
+        cudaError_t _e = cudaGetLastError();                                                   \
+        if (_e != cudaSuccess) {                                                               \
+            tsp::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, \
+                           __LINE__);                                                          \
+            return TSP_ERR_CUDA;                                                               \
+        }                                                                                      \
+    } while (0)
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// scipy.ndimage Gaussian weights: radius int(4*sigma+0.5), exp(-k^2/(2 sigma^2)) / sum, float64
+std::vector<double> gaussian_taps(double sigma);
+
+struct DeviceTaps {          // one uploaded FIR: w64[0..2r], w32 padded with `pad` zeros each side
+    int radius = 0;
+    const double* w64 = nullptr;
+    const float* w32 = nullptr;    // points at the first real tap; w32[-pad..-1] and [2r+1..2r+pad] are 0
+};
+constexpr int kTapPad = 8;
+
+}  // namespace tsp
+
+struct tsp_handle {
+    int device = 0;
+    int sm_count = 148;
+    int64_t launches = 0;
+    std::mutex mu;        // guards taps / tables
+    std::mutex host_mu;   // serialises the host-buffer entry points (they share d_scratch)
+    // small device arena for FIR taps and fast-mode tables, keyed by a text key
+    std::map<std::string, tsp::DeviceTaps> taps;
+    std::map<std::string, void*> tables;
+    // host-buffer path state (owned scratch, grows on demand)
+    cudaStream_t stream = nullptr;
+    void* d_scratch = nullptr;
+    size_t d_scratch_bytes = 0;
+    int32_t* h_status = nullptr;   // pinned copy of the status block
+};
+
+namespace tsp {
+
+int get_taps(tsp_handle* h, double sigma, DeviceTaps* out);
+
+// stage launchers (each returns TSP_OK or an error code)
+int launch_histogram(tsp_handle* h, const uint16_t* d_vol, size_t count, uint32_t* d_hist,
+                     cudaStream_t s);
+int launch_percentile_finalize(tsp_handle* h, const uint32_t* d_hist, int pedestal, int32_t* d_status,
+                               cudaStream_t s);
+int launch_prepare(tsp_handle* h, const uint16_t* d_in, float* d_out, size_t count, int pedestal,
+                   const int32_t* d_status, cudaStream_t s);
+int launch_convert_u16_f32(tsp_handle* h, const uint16_t* d_in, float* d_out, size_t count,
+                           cudaStream_t s);
+template <typename T>
+int launch_fir_axis(tsp_handle* h, const T* d_in, T* d_out, int Z, int Y, int X, int axis,
+                    const DeviceTaps& taps, bool fp64, cudaStream_t s);
+template <typename T>
+int gaussian_blur(tsp_handle* h, const T* d_in, T* d_out, T* d_tmp, int Z, int Y, int X,
+                  const double sigma[3], bool fp64, cudaStream_t s);
+int launch_argmax(tsp_handle* h, const float* d_score, int32_t* d_zmap, int Z, int Y, int X,
+                  int z_offset, int32_t* d_status, cudaStream_t s);
+int launch_band_project_ex(tsp_handle* h, const uint16_t* d_stack, size_t channel_stride, size_t z0_offset,
+                           const int32_t* d_zmap, float* d_proj, int C, int Z, int Y, int X, int ref_c,
+                           int shift, int pedestal, int32_t* d_status, cudaStream_t s);
+int launch_band_project_bitexact_ex(tsp_handle* h, const uint16_t* d_stack, size_t channel_stride,
+                                    size_t z0_offset, const int32_t* d_zmap, float* d_proj, int C, int Z,
+                                    int Y, int X, int ref_c, int shift, int pedestal, float* d_volA,
+                                    float* d_volB, int32_t* d_status, cudaStream_t s);
+int launch_project_m(tsp_handle* h, const uint16_t* d_channel, uint16_t* d_out, int Z, int Y, int X,
+                     int method, int bin, void* d_ws, cudaStream_t s);
+int launch_widen_outputs(tsp_handle* h, const float* d_proj, const int32_t* d_zmap, double* d_proj64,
+                         int64_t* d_zmap64, size_t nproj, size_t nz, cudaStream_t s);
+
+// fast (multirate) score stage
+size_t fast_workspace_bytes(int Z, int Y, int X);
+int launch_fast_score_argmax(tsp_handle* h, const uint16_t* d_channel, int32_t* d_zmap, int Z, int Y,
+                             int X, int pedestal, int z_offset, int32_t* d_status, void* d_ws,
+                             cudaStream_t s);
+
+}  // namespace tsp
