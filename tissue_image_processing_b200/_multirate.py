@@ -67,19 +67,6 @@ def coarse_taps(sigma_score=30.0, order_d=ORDER_D, order_u=ORDER_U, rc=RC):
     rd, ru = (len(d) - 1) // 2, (len(u) - 1) // 2
     span = STRIDE * rc + rd + ru + STRIDE
     n = 2 * span + 1                       # fine offsets s in [-span, span]
-    cols = []
-    for i in range(rc + 1):
-        cz = np.zeros(2 * STRIDE * i + 1)
-        cz[0] = cz[-1] = 1.0 if i else 0.5
-        if i == 0:
-            cz = np.ones(1)
-        full = np.convolve(np.convolve(d, cz), u)          # centred, length rd+ru+8i both sides
-        rf = (len(full) - 1) // 2
-        col = np.zeros((STRIDE, n))
-        # output phase p at fine x = p; input offset s: response full[(s) + rf] only when the coarse
-        # grid is aligned, i.e. the zero-stuffed chain sees coarse positions at multiples of 8.
-        # Enumerate explicitly: out[x] = sum_m u[x-8m] * sum_i c_i * sum_t d[t] P[8(m+i)+t]
-        cols.append(col)
     # explicit enumeration (tiny problem): weight of P[x+s] in out[x], x = p
     A = np.zeros((STRIDE, n, rc + 1))
     for p in range(STRIDE):
@@ -97,12 +84,17 @@ def coarse_taps(sigma_score=30.0, order_d=ORDER_D, order_u=ORDER_U, rc=RC):
     b[:, span - r_h: span + r_h + 1] = h
     c, *_ = np.linalg.lstsq(A.reshape(-1, rc + 1), b.reshape(-1), rcond=None)
     resid = (A.reshape(-1, rc + 1) @ c - b.reshape(-1)).reshape(STRIDE, n)
+    c = c / (c[0] + 2.0 * c[1:].sum())                 # unit DC gain (B-splines are a partition of unity)
     return c, float(np.abs(resid).sum(axis=1).max())
 
 
 def coarse_len(n):
-    """Stored coarse samples for a fine axis of length n: m = -PAD_LO .. ceil((n-1)/8)+PAD_LO."""
-    return (n - 1 + STRIDE - 1) // STRIDE + 1 + 2 * PAD_LO
+    """Stored coarse samples for a fine axis of length n.  Index mi < coarse_len-1 is the prefiltered
+    sample at fine position 8*(mi - PAD_LO): mi = 0 lies fully before the line (it equals the
+    replicated value P[0]), the last true sample is the last one whose B-spline support still
+    touches the line.  Index coarse_len-1 is a stand-alone sample holding the replicated value
+    P[n-1]; the coarse FIR clamps its reads to [0, coarse_len-1]."""
+    return (n + 29) // STRIDE + 2
 
 
 def decimation_matrix(n, sigma_pre=1.0, order_d=ORDER_D):
@@ -112,10 +104,12 @@ def decimation_matrix(n, sigma_pre=1.0, order_d=ORDER_D):
     rd = (len(d) - 1) // 2
     mc = coarse_len(n)
     out = np.zeros((mc, n))
-    for mi in range(mc):
+    for mi in range(mc - 1):
         centre = STRIDE * (mi - PAD_LO)
         for t in range(-rd, rd + 1):
             out[mi] += d[t + rd] * h1[min(max(centre + t, 0), n - 1)]
+    assert STRIDE * (mc - 1 - PAD_LO) - rd > n - 1        # the next regular sample would be fully outside
+    out[mc - 1] = h1[n - 1]
     return out
 
 

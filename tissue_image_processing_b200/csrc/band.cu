@@ -243,18 +243,17 @@ static int get_wz_table(tsp_handle* h, int Z, const float** out) {
     char key[32];
     snprintf(key, sizeof key, "wz%d", Z);
     std::lock_guard<std::mutex> lock(h->mu);
-    auto it = h->tables.find(key);
-    if (it != h->tables.end()) {
-        *out = (const float*)it->second;
-        return TSP_OK;
-    }
-    static bool w2_uploaded = false;
-    if (!w2_uploaded) {
+    if (!h->band_consts) {
         std::vector<double> w2 = gaussian_taps(2.0);
         float w2f[17];
         for (int i = 0; i < 17; ++i) w2f[i] = (float)w2[i];
         TSP_CUDA(cudaMemcpyToSymbol(c_w2, w2f, sizeof w2f));
-        w2_uploaded = true;
+        h->band_consts = true;
+    }
+    auto it = h->tables.find(key);
+    if (it != h->tables.end()) {
+        *out = (const float*)it->second;
+        return TSP_OK;
     }
     std::vector<double> wz = gaussian_taps(1.0);       // radius 4
     std::vector<float> tab((size_t)Z * 9, 0.f);

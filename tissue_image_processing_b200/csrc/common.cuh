@@ -83,6 +83,8 @@ struct tsp_handle {
     void* d_scratch = nullptr;
     size_t d_scratch_bytes = 0;
     int32_t* h_status = nullptr;   // pinned copy of the status block
+    // per-device one-time setup done (constant memory, function attributes)
+    bool fast_consts = false, band_consts = false, hist_attr = false;
 };
 
 namespace tsp {

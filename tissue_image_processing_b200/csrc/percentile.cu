@@ -12,7 +12,7 @@ namespace tsp {
 // counter can overflow; a flush adds the non-zero counters to the global histogram.
 constexpr int kHistThreads = 1024;
 constexpr int kVecPerThread = 7;                                      // uint4 loads per thread per chunk
-constexpr int kChunk = kHistThreads * kVecPerThread * 8;              // 57344 voxels
+static_assert(kHistThreads * kVecPerThread * 8 + 16 < 65536, "16-bit counters must not overflow between flushes");
 constexpr int kHistSmemBytes = kHistBins / 2 * 4;                     // 131072
 
 __device__ __forceinline__ void hist_add(uint32_t* sh, uint32_t v) {
@@ -81,8 +81,8 @@ hist16_kernel(const uint16_t* __restrict__ vol, size_t count, uint32_t* __restri
         }
         __syncthreads();
     }
-    // head/tail voxels handled by block 0 when there was no chunk to flush them with
-    if (blockIdx.x == 0 && (nchunks == 0 || true)) {
+    // head/tail voxels of block 0 when there was no chunk to flush them with
+    if (blockIdx.x == 0) {
         __syncthreads();
         for (int i = threadIdx.x; i < kHistBins / 2; i += kHistThreads) {
             const uint32_t w = sh[i];
@@ -96,11 +96,10 @@ hist16_kernel(const uint16_t* __restrict__ vol, size_t count, uint32_t* __restri
 
 int launch_histogram(tsp_handle* h, const uint16_t* d_vol, size_t count, uint32_t* d_hist,
                      cudaStream_t s) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!h->hist_attr) {
         TSP_CUDA(cudaFuncSetAttribute(hist16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       kHistSmemBytes));
-        attr_set = true;
+        h->hist_attr = true;
     }
     TSP_CUDA(cudaMemsetAsync(d_hist, 0, kHistBins * sizeof(uint32_t), s));
     const size_t nchunks = (count / 8 + (size_t)kHistThreads * kVecPerThread - 1) /
