@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""Benchmark of the surface-projection hot path (contract in the task statement / SURVEY.md section 8d).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--mode fast|exact|bitexact] [--impl reference]
+
+A step = the whole operator (reference surface_projection.py:17-85) on one synthetic
+2048x2048x64 uint16 single-channel frame (BASELINE.json configs[1]) per GPU; frames are independent, so
+N GPUs = a movie partitioned by frame, no collective on the data path (scaling "weak").
+  value  device-resident voxels/s (CUDA events around exactly K steps, max over ranks)
+  e2e    the same through the public host-buffer API time_point_surface_projection(): pinned host frame in,
+         float64 projection + int64 height map out, H2D and D2H inside the timed region
+  roofline      dominant kernel: algorithmic bytes / CUDA-event duration vs the measured HBM copy peak
+  cpu_baseline  the CPU oracle (port of the reference path, same scipy calls) on a bounded crop, host cores
+`--impl reference` times only that CPU path (the reference is pure numpy/scipy; /root/reference is not on
+the GPU box, the oracle restates it bit for bit - tests/test_oracle_golden.py).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+Z, Y, X = 64, 2048, 2048
+WORKLOAD = "single 2048x2048x64 uint16 stack, one channel (BASELINE configs[1]); one frame per step per GPU"
+METRIC = "projected voxels/s"
+UNIT = "voxels/s"
+
+
+def algorithmic_bytes(C, z, y, x):
+    """reference channel read 3x as uint16 (percentile, score, projection), other channels once,
+    int32 height map + float32 projection written."""
+    v = z * y * x
+    return 2 * v * (C + 2) + y * x * (4 + 4 * C)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def synth_frame_device(torch, seed, device):
+    """Same construction as oracle/synth.py (bright sheet on a smooth surface, sparse texture, noise),
+    generated on the device because the numpy generator needs minutes at this size."""
+    g = torch.Generator(device=device).manual_seed(1000 + seed)
+    zz = torch.arange(Z, device=device, dtype=torch.float32)[:, None, None]
+    yy = torch.arange(Y, device=device, dtype=torch.float32)[None, :, None]
+    xx = torch.arange(X, device=device, dtype=torch.float32)[None, None, :]
+    h = Z / 2 + 0.15 * Z * torch.sin(2 * np.pi * 1.5 * yy / Y + 0.1 * seed) + 0.10 * Z * torch.cos(2 * np.pi * xx / X)
+    tex = 0.5 + 0.5 * (torch.rand((1, Y, X), device=device, generator=g) < 0.15)
+    sig = 300.0 + 2500.0 * torch.exp(-(zz - h) ** 2 / 8.0) * tex
+    sig += torch.sqrt(8.0 * sig) * torch.randn(sig.shape, device=device, generator=g)      # ~ 8*Poisson(sig/8)
+    sig += 20.0 * torch.randn(sig.shape, device=device, generator=g)
+    return sig.clamp_(0, 65535).round_().to(torch.uint16)[None].contiguous()               # (1, Z, Y, X)
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, reasons, smax = [], set(), None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.tmp.read().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax = float(parts[1])
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        self.tmp.close()
+        os.unlink(self.tmp.name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=smax, reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm
+# --------------------------------------------------------------------------------------------------
+def _cpu_crop(seed, shape):
+    from oracle import synth
+    return synth.synth_stack(shape[0], shape[1], shape[2], C=1, seed=seed)[None]
+
+
+def _cpu_one(args):
+    seed, shape = args
+    from oracle import surface_projection_oracle as orc
+    img = _cpu_crop(seed, shape)
+    t0 = time.perf_counter()
+    orc.time_point_surface_projection(img, "TCZYX", 0, airyscan=False, z_map=True)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(shape=(48, 640, 640), procs=1, rounds=1):
+    """Oracle (bit-exact port of the reference operator) on crops of the workload frame.  Returns voxels/s
+    over all processes (the reference path is single-threaded; parallelism = independent frames)."""
+    vox = shape[0] * shape[1] * shape[2]
+    jobs = [(100 + i, shape) for i in range(procs * rounds)]
+    t0 = time.perf_counter()
+    if procs == 1:
+        for j in jobs:
+            _cpu_one(j)
+    else:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(procs) as pool:
+            pool.map(_cpu_one, jobs)
+    wall = time.perf_counter() - t0
+    return vox * len(jobs) / wall, wall
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0))
+    procs = max(1, min(cores, 16))
+    shape = (48, 640, 640)
+    per_step = []
+    for i in range(args.warmup + args.steps):
+        v, wall = cpu_baseline(shape, procs=procs)
+        if i >= args.warmup:
+            per_step.append((v, wall))
+    value = float(np.mean([v for v, _ in per_step]))
+    ms = float(np.mean([w for _, w in per_step]) * 1e3)
+    sample = "%d independent %dx%dx%d crops of the workload frame per step, one process each" % (
+        procs, shape[1], shape[2], shape[0])
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 data / f64 accumulate (scipy)",
+            "data": "synthetic", "config": {"workload": WORKLOAD},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
+def run_gpu(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200 (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    import tissue_image_processing_b200 as tsp
+    from tissue_image_processing_b200 import _native as nat
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    nframes = 2
+    frames = [synth_frame_device(torch, 10 * rank + i, device) for i in range(nframes)]
+    vox = Z * Y * X
+    proj = nat.DeviceProjector(1, Z, Y, X, reference_channel=0, airyscan=False, mode=args.mode, device=local_rank)
+
+    # ---- device-resident ---------------------------------------------------------------------------
+    for i in range(args.warmup):
+        proj.run(frames[i % nframes])
+    barrier()
+    nat.set_profiling(True, local_rank)
+    nat.stage_times(reset=True, device=local_rank)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = nat.launch_count(local_rank)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        proj.run(frames[i % nframes])
+    ev1.record()
+    barrier()
+    dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = nat.launch_count(local_rank) - launches0
+    stages = nat.stage_times(reset=True, device=local_rank)
+    nat.set_profiling(False, local_rank)
+    status = proj.status()
+
+    # ---- end to end through the public API ----------------------------------------------------------
+    host_frames = []
+    for f in frames:
+        h = nat.pinned_empty((1, 1, Z, Y, X), np.uint16)
+        torch.from_numpy(h).copy_(f.view(1, 1, Z, Y, X))
+        host_frames.append(h)
+    torch.cuda.synchronize()
+    kw = dict(reference_channel=0, airyscan=False, z_map=True, mode=args.mode, device=local_rank)
+    for i in range(min(args.warmup, 3)):
+        tsp.time_point_surface_projection(host_frames[i % nframes], "TCZYX", **kw)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        p64, z64 = tsp.time_point_surface_projection(host_frames[i % nframes], "TCZYX", **kw)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    clocks = sampler.stop() if sampler else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peaks()
+    value = world * args.steps * vox / (dev_ms * 1e-3)
+    frame_bytes = algorithmic_bytes(1, Z, Y, X)
+    frame_gbs = frame_bytes * args.steps / (dev_ms * 1e-3) / 1e9
+    # dominant kernel = the stage with the largest share of device time
+    stage_ms = {k: v[0] / max(v[1], 1) for k, v in stages.items()}
+    dom = max(stage_ms, key=stage_ms.get)
+    # algorithmic bytes of each stage of the fast path (per frame): every score-path stage is charged the one
+    # uint16 read of the reference channel it exists for; band = one uint16 read + both outputs
+    stage_bytes = {"percentile": 2 * vox, "decimate": 2 * vox, "blur_score": 2 * vox, "blur_pre": 2 * vox,
+                   "prepare": 2 * vox, "band": 2 * vox + Y * X * 8, "interp_argmax": 2 * vox, "coarse": 2 * vox,
+                   "argmax": 2 * vox}
+    achieved = stage_bytes.get(dom, 2 * vox) / (stage_ms[dom] * 1e-3) / 1e9
+    cpu_v, cpu_wall = cpu_baseline((48, 640, 640), procs=1)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 (u16 in)", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "mode": args.mode, "frames_per_step_per_gpu": 1,
+                   "l2": "inputs (512 MiB per frame, 2 alternating) larger than the 126 MB L2",
+                   "algorithmic_bytes_per_frame": frame_bytes},
+        "e2e": {"value": world * args.steps * vox / e2e_s, "unit": UNIT,
+                "h2d_bytes_per_step": int(vox * 2), "d2h_bytes_per_step": int(Y * X * 16 + 256),
+                "ms_per_step": e2e_s * 1e3 / args.steps,
+                "api": "time_point_surface_projection(pinned host uint16 frame) -> float64 projection, int64 zmap"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "kernel_ms": stage_ms[dom]},
+        "frame_roofline": {"achieved": frame_gbs, "peak": peak, "unit": "GB/s", "frac": frame_gbs / peak,
+                           "frac_of_nominal_8TBs": frame_gbs / 8000.0,
+                           "note": "whole operator, SURVEY 8(d) algorithmic bytes / device time"},
+        "stage_ms": stage_ms,
+        "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": "one 640x640x48 crop of the workload frame, %.1f s" % cpu_wall},
+        "clocks": clocks,
+        "frame_status": status,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--mode", default="fast", choices=["fast", "exact", "bitexact"])
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_gpu(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -154,6 +154,15 @@ int tsp_debug_coarse_taps(double* out, int capacity);
 /* Number of CUDA kernels launched through this handle so far (bench.py reports it). */
 int64_t tsp_launch_count(const tsp_handle* h);
 
+/* Optional per-stage device timing: when enabled, tsp_project_frame records CUDA events on the
+ * launching stream between its stages.  tsp_get_stage_times synchronises the device, folds the
+ * recorded intervals into per-stage totals (milliseconds, number of intervals) for
+ * tsp_stage_count() stages named by tsp_stage_name(), and resets the totals when reset != 0. */
+int tsp_set_profiling(tsp_handle* h, int enable);
+int tsp_stage_count(void);
+const char* tsp_stage_name(int stage);
+int tsp_get_stage_times(tsp_handle* h, double* ms_out, int64_t* count_out, int reset);
+
 #ifdef __cplusplus
 }
 #endif

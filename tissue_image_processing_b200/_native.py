@@ -63,6 +63,10 @@ EXPORTS = {
                                 C.c_void_p, C.c_size_t, C.c_void_p]),
     "tsp_debug_coarse_taps": (C.c_int, [C.POINTER(C.c_double), C.c_int]),
     "tsp_launch_count": (C.c_int64, [C.c_void_p]),
+    "tsp_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
+    "tsp_stage_count": (C.c_int, []),
+    "tsp_stage_name": (C.c_char_p, [C.c_int]),
+    "tsp_get_stage_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int]),
 }
 
 _lib = None
@@ -137,6 +141,19 @@ def handle(device=None):
 
 def launch_count(device=None):
     return int(load_library().tsp_launch_count(handle(device)))
+
+
+def set_profiling(enable, device=None):
+    check(load_library().tsp_set_profiling(handle(device), 1 if enable else 0), "tsp_set_profiling")
+
+
+def stage_times(reset=True, device=None):
+    """{stage name: (total ms, intervals)} recorded since the last reset (synchronises the device)."""
+    lib = load_library()
+    n = lib.tsp_stage_count()
+    ms, cnt = (C.c_double * n)(), (C.c_int64 * n)()
+    check(lib.tsp_get_stage_times(handle(device), ms, cnt, 1 if reset else 0), "tsp_get_stage_times")
+    return {lib.tsp_stage_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n) if cnt[i]}
 
 
 def make_desc(C_, Z, Y, X, reference_channel=0, min_z=0, max_z=0, airyscan=False, atoh_shift=0, mode="fast"):

@@ -14,6 +14,23 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+void prof_mark(tsp_handle* h, cudaStream_t s, int stage) {
+    if (!h->profiling) return;
+    cudaEvent_t ev;
+    if (!h->prof_pool.empty()) {
+        ev = h->prof_pool.back();
+        h->prof_pool.pop_back();
+    } else if (cudaEventCreate(&ev) != cudaSuccess) {
+        return;
+    }
+    cudaEventRecord(ev, s);
+    h->prof_events.push_back(ev);
+    h->prof_stage.push_back(stage);
+}
+
+static const char* kStageNames[STG_COUNT] = {"percentile", "decimate", "coarse", "interp_argmax", "prepare",
+                                             "blur_pre", "blur_score", "argmax", "band", "widen"};
+
 struct Crop {
     int z0;        // first plane of the cropped stack inside the full stack
     int zc;        // planes after SP:30-31
@@ -69,7 +86,7 @@ static Workspace carve(const tsp_frame_desc* d, const Crop& c, void* base) {
     w.status = (int32_t*)(p + off);
     off += align_up(kStatusWords * sizeof(int32_t), 256);
     w.hist = (uint32_t*)(p + off);
-    off += align_up(kHistBins * sizeof(uint32_t), 256);
+    off += align_up(percentile_scratch_bytes(), 256);
     const size_t vol = align_up((size_t)c.zc * d->rows * d->cols * sizeof(float), 256);
     if (d->mode == TSP_MODE_FAST) {
         w.fast = p + off;
@@ -129,6 +146,8 @@ int tsp_destroy(tsp_handle* h) {
     if (h->d_scratch) cudaFree(h->d_scratch);
     if (h->h_status) cudaFreeHost(h->h_status);
     if (h->stream) cudaStreamDestroy(h->stream);
+    for (cudaEvent_t ev : h->prof_events) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : h->prof_pool) cudaEventDestroy(ev);
     delete h;
     return TSP_OK;
 }
@@ -165,35 +184,84 @@ int tsp_project_frame(tsp_handle* h, const tsp_frame_desc* desc, const uint16_t*
     const int ped = desc->airyscan ? kAiryscanPedestal : 0;
     const uint16_t* ref = d_stack + (size_t)desc->reference_channel * chan_stride + z0_off;
 
+    prof_mark(h, s, -1);
     TSP_CUDA(cudaMemsetAsync(w.status, 0, kStatusWords * sizeof(int32_t), s));
-    rc = launch_histogram(h, ref, nvox, w.hist, s);
+    rc = launch_percentile(h, ref, nvox, ped, w.status, w.hist, s);
     if (rc) return rc;
-    rc = launch_percentile_finalize(h, w.hist, ped, w.status, s);
-    if (rc) return rc;
+    prof_mark(h, s, STG_PERCENTILE);
 
     if (desc->mode == TSP_MODE_FAST) {
         rc = launch_fast_score_argmax(h, ref, d_zmap, c.zc, Y, X, ped, c.z_offset, w.status, w.fast, s);
         if (rc) return rc;
-        return launch_band_project_ex(h, d_stack, chan_stride, z0_off, d_zmap, d_proj, C, c.zc, Y, X,
-                                      desc->reference_channel, desc->atoh_shift, ped, w.status, s);
+        rc = launch_band_project_ex(h, d_stack, chan_stride, z0_off, d_zmap, d_proj, C, c.zc, Y, X,
+                                    desc->reference_channel, desc->atoh_shift, ped, w.status, true, s);
+        prof_mark(h, s, STG_BAND);
+        return rc;
     }
     const bool fp64 = desc->mode == TSP_MODE_BITEXACT;
     const double sig_pre[3] = {0.5, 1.0, 1.0};       // SP:37
     const double sig_score[3] = {0.5, 30.0, 30.0};   // SP:55
     rc = launch_prepare(h, ref, w.volA, nvox, ped, w.status, s);
     if (rc) return rc;
+    prof_mark(h, s, STG_PREPARE);
     rc = gaussian_blur<float>(h, w.volA, w.volB, w.volA, c.zc, Y, X, sig_pre, fp64, s);
     if (rc) return rc;
+    prof_mark(h, s, STG_BLUR_PRE);
     rc = gaussian_blur<float>(h, w.volB, w.volA, w.volB, c.zc, Y, X, sig_score, fp64, s);
     if (rc) return rc;
+    prof_mark(h, s, STG_BLUR_SCORE);
     rc = launch_argmax(h, w.volA, d_zmap, c.zc, Y, X, c.z_offset, w.status, s);
     if (rc) return rc;
+    prof_mark(h, s, STG_ARGMAX);
     if (fp64)
-        return launch_band_project_bitexact_ex(h, d_stack, chan_stride, z0_off, d_zmap, d_proj, C, c.zc, Y, X,
-                                               desc->reference_channel, desc->atoh_shift, ped, w.volA, w.volB,
-                                               w.status, s);
-    return launch_band_project_ex(h, d_stack, chan_stride, z0_off, d_zmap, d_proj, C, c.zc, Y, X,
-                                  desc->reference_channel, desc->atoh_shift, ped, w.status, s);
+        rc = launch_band_project_bitexact_ex(h, d_stack, chan_stride, z0_off, d_zmap, d_proj, C, c.zc, Y, X,
+                                             desc->reference_channel, desc->atoh_shift, ped, w.volA, w.volB,
+                                             w.status, true, s);
+    else
+        rc = launch_band_project_ex(h, d_stack, chan_stride, z0_off, d_zmap, d_proj, C, c.zc, Y, X,
+                                    desc->reference_channel, desc->atoh_shift, ped, w.status, true, s);
+    prof_mark(h, s, STG_BAND);
+    return rc;
+}
+
+int tsp_set_profiling(tsp_handle* h, int enable) {
+    if (!h) return TSP_ERR_INVALID;
+    h->profiling = enable != 0;
+    return TSP_OK;
+}
+
+int tsp_stage_count(void) { return STG_COUNT; }
+
+const char* tsp_stage_name(int stage) { return stage >= 0 && stage < STG_COUNT ? kStageNames[stage] : ""; }
+
+// Folds every recorded mark into per-stage totals (synchronises the device), returns them and optionally
+// resets.  ms_out / count_out hold tsp_stage_count() entries.
+int tsp_get_stage_times(tsp_handle* h, double* ms_out, int64_t* count_out, int reset) {
+    if (!h || !ms_out || !count_out) return TSP_ERR_INVALID;
+    TSP_CUDA(cudaSetDevice(h->device));
+    TSP_CUDA(cudaDeviceSynchronize());
+    for (size_t i = 0; i < h->prof_events.size(); ++i) {
+        const int st = h->prof_stage[i];
+        if (st >= 0 && i > 0) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, h->prof_events[i - 1], h->prof_events[i]) == cudaSuccess) {
+                h->prof_ms[st] += ms;
+                h->prof_count[st] += 1;
+            }
+        }
+    }
+    for (cudaEvent_t ev : h->prof_events) h->prof_pool.push_back(ev);
+    h->prof_events.clear();
+    h->prof_stage.clear();
+    for (int i = 0; i < STG_COUNT; ++i) {
+        ms_out[i] = h->prof_ms[i];
+        count_out[i] = h->prof_count[i];
+        if (reset) {
+            h->prof_ms[i] = 0;
+            h->prof_count[i] = 0;
+        }
+    }
+    return TSP_OK;
 }
 
 static void fill_status(const int32_t* st, tsp_frame_status* out) {
@@ -300,16 +368,14 @@ int tsp_percentile95_nonzero_u16(tsp_handle* h, const uint16_t* d_volume, size_t
     if (!h || !d_volume || !out) return TSP_ERR_INVALID;
     TSP_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = (cudaStream_t)cuda_stream;
-    const size_t bytes = align_up(kStatusWords * sizeof(int32_t), 256) + kHistBins * sizeof(uint32_t);
+    const size_t bytes = align_up(kStatusWords * sizeof(int32_t), 256) + percentile_scratch_bytes();
     std::lock_guard<std::mutex> lock(h->host_mu);
     int rc = ensure_scratch(h, bytes);
     if (rc) return rc;
     int32_t* st = (int32_t*)h->d_scratch;
     uint32_t* hist = (uint32_t*)((char*)h->d_scratch + align_up(kStatusWords * sizeof(int32_t), 256));
     TSP_CUDA(cudaMemsetAsync(st, 0, kStatusWords * sizeof(int32_t), s));
-    rc = launch_histogram(h, d_volume, count, hist, s);
-    if (rc) return rc;
-    rc = launch_percentile_finalize(h, hist, airyscan ? kAiryscanPedestal : 0, st, s);
+    rc = launch_percentile(h, d_volume, count, airyscan ? kAiryscanPedestal : 0, st, hist, s);
     if (rc) return rc;
     TSP_CUDA(cudaMemcpyAsync(h->h_status, st, kStatusWords * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     TSP_CUDA(cudaStreamSynchronize(s));
@@ -322,7 +388,7 @@ int tsp_focus_score_f32(tsp_handle* h, const uint16_t* d_channel, float* d_score
     if (!h || !d_channel || !d_score || !d_tmp || planes < 1 || rows < 1 || cols < 1) return TSP_ERR_INVALID;
     TSP_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = (cudaStream_t)cuda_stream;
-    const size_t bytes = align_up(kStatusWords * sizeof(int32_t), 256) + kHistBins * sizeof(uint32_t);
+    const size_t bytes = align_up(kStatusWords * sizeof(int32_t), 256) + percentile_scratch_bytes();
     std::lock_guard<std::mutex> lock(h->host_mu);
     int rc = ensure_scratch(h, bytes);
     if (rc) return rc;
@@ -331,9 +397,7 @@ int tsp_focus_score_f32(tsp_handle* h, const uint16_t* d_channel, float* d_score
     const size_t nvox = (size_t)planes * rows * cols;
     const int ped = airyscan ? kAiryscanPedestal : 0;
     TSP_CUDA(cudaMemsetAsync(st, 0, kStatusWords * sizeof(int32_t), s));
-    rc = launch_histogram(h, d_channel, nvox, hist, s);
-    if (rc) return rc;
-    rc = launch_percentile_finalize(h, hist, ped, st, s);
+    rc = launch_percentile(h, d_channel, nvox, ped, st, hist, s);
     if (rc) return rc;
     rc = launch_prepare(h, d_channel, d_score, nvox, ped, st, s);
     if (rc) return rc;
@@ -365,7 +429,7 @@ int tsp_band_project(tsp_handle* h, const uint16_t* d_stack, const int32_t* d_zm
     const size_t plane = (size_t)rows * cols;
     return launch_band_project_ex(h, d_stack, (size_t)planes * plane, 0, d_zmap, d_proj, channels, planes, rows,
                                   cols, reference_channel, atoh_shift, airyscan ? kAiryscanPedestal : 0,
-                                  (int32_t*)d_workspace, s);
+                                  (int32_t*)d_workspace, false, s);
 }
 
 size_t tsp_project_m_workspace_bytes(int planes, int rows, int cols, int bin_size) {

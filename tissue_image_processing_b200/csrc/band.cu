@@ -15,8 +15,9 @@ __constant__ float c_w2[17];      // sigma = 2 taps (SP:70, axes y and x)
 
 // ---- K4 ----------------------------------------------------------------------------------------
 __global__ void argmax_z_kernel(const float* __restrict__ score, int32_t* __restrict__ zmap, int Z,
-                                size_t plane, int z_offset) {
+                                size_t plane, int z_offset, int32_t* __restrict__ status) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
+    int zmin = INT32_MAX, zmax = INT32_MIN;
     for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < plane; p += stride) {
         float best = score[p];
         int bz = 0;
@@ -28,17 +29,28 @@ __global__ void argmax_z_kernel(const float* __restrict__ score, int32_t* __rest
             }
         }
         zmap[p] = bz + z_offset;
+        zmin = min(zmin, bz + z_offset);
+        zmax = max(zmax, bz + z_offset);
+    }
+    if (status) {
+        for (int o = 16; o; o >>= 1) {
+            zmin = min(zmin, __shfl_xor_sync(0xffffffffu, zmin, o));
+            zmax = max(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
+        }
+        if ((threadIdx.x & 31) == 0 && zmax >= zmin) {
+            atomicMax(&status[ST_ZMAX], zmax);
+            atomicMax(&status[ST_ZMIN_INV], INT32_MAX - zmin);
+        }
     }
 }
 
 int launch_argmax(tsp_handle* h, const float* d_score, int32_t* d_zmap, int Z, int Y, int X,
                   int z_offset, int32_t* d_status, cudaStream_t s) {
-    (void)d_status;
     const size_t plane = (size_t)Y * X;
     const int threads = 256;
     size_t blocks = (plane + threads - 1) / threads;
     if (blocks > (size_t)h->sm_count * 32) blocks = (size_t)h->sm_count * 32;
-    argmax_z_kernel<<<(int)blocks, threads, 0, s>>>(d_score, d_zmap, Z, plane, z_offset);
+    argmax_z_kernel<<<(int)blocks, threads, 0, s>>>(d_score, d_zmap, Z, plane, z_offset, d_status);
     TSP_LAUNCH_CHECK(h);
     return TSP_OK;
 }
@@ -69,7 +81,8 @@ __global__ void zmap_range_init_kernel(int32_t* status) {
 
 // the reference indexes the cropped stack with chosen_z (and clip(chosen_z+shift, 0, Z), upper bound
 // inclusive): any index >= Z raises IndexError; negative indices cannot occur.
-__global__ void band_check_kernel(int32_t* status, int Z, int shift) {
+__global__ void band_check_kernel(int32_t* status, int Z, int shift, int decode) {
+    if (decode) status[ST_ZMIN] = INT32_MAX - status[ST_ZMIN_INV];     // argmax kernels keep max(INT_MAX - z)
     const int hi = status[ST_ZMAX];
     int err = hi >= Z;
     if (shift != 0) {
@@ -83,10 +96,12 @@ __global__ void band_check_kernel(int32_t* status, int Z, int shift) {
 
 // ---- K5-K7 fused -------------------------------------------------------------------------------
 constexpr int kBandTY = 32, kBandTX = 64, kBandHalo = 8;
-constexpr int kBandThreads = 256;
-constexpr int kBandPix = 8;                 // pixels (consecutive rows) per thread
+constexpr int kBandThreads = 256;           // thread = 8 consecutive pixels of one row
+constexpr int kBandPix = 8;
 constexpr int kBandMaxCh = 2;               // channels per CTA
 constexpr int kBandMaxPlanes = 4096;
+
+__constant__ float c_w1[9];       // sigma = 1 taps (z axis, interior planes)
 
 struct BandArgs {
     const uint16_t* stack;      // (C, Zfull, Y, X)
@@ -100,8 +115,22 @@ struct BandArgs {
     int shift;
     int pedestal;
     int nch;
+    int vec;                    // rows are 16-byte aligned: uint4 loads
     int ch[16];
 };
+
+// b_s column permutation: the two float4 halves of every 8-pixel group live in separate 32-float
+// halves of the row, so that the y pass reads conflict-free 16-byte vectors
+__device__ __forceinline__ int band_col(int xq) { return ((xq >> 2) & 1) * 32 + (xq >> 3) * 4; }
+
+__device__ __forceinline__ uint4 band_load8(const uint16_t* __restrict__ src, int x, int X, bool vec) {
+    if (vec && x + 7 < X) return __ldg(reinterpret_cast<const uint4*>(src));
+    uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        if (x + c < X) w[c >> 1] |= (uint32_t)__ldg(src + c) << (16 * (c & 1));
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
 
 __global__ void __launch_bounds__(kBandThreads, 2) band_project_kernel(const BandArgs a) {
     constexpr int CW = kBandTX + 2 * kBandHalo;      // 80
@@ -126,115 +155,166 @@ __global__ void __launch_bounds__(kBandThreads, 2) band_project_kernel(const Ban
         for (int i = tid; i < CH * CW; i += kBandThreads) {
             const int yy = min(max(y0 - kBandHalo + i / CW, 0), a.Y - 1);
             const int xx = min(max(x0 - kBandHalo + i % CW, 0), a.X - 1);
-            int v = a.zmap[(size_t)yy * a.X + xx];
+            int v = __ldg(a.zmap + (size_t)yy * a.X + xx);
             if (a.shift != 0) v = min(max(v + a.shift, 0), a.Z);
             cz_s[i / CW][i % CW] = v;
             lo = min(lo, v);
             hi = max(hi, v);
             atomicOr(&present[v >> 5], 1u << (v & 31));
         }
-        atomicMin(&zlo_s, lo);
-        atomicMax(&zhi_s, hi);
+        for (int o = 16; o; o >>= 1) {
+            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        if ((tid & 31) == 0) {
+            atomicMin(&zlo_s, lo);
+            atomicMax(&zhi_s, hi);
+        }
     }
     __syncthreads();
     const int zlo = zlo_s, zhi = zhi_s;
 
-    const int tx = tid % kBandTX, ty = tid / kBandTX;          // ty in 0..3 -> rows ty*8 .. ty*8+7
-    const int x = x0 + tx;
-    const int ybase = ty * kBandPix;
+    const int g = tid & 7, row = tid >> 3;                     // 8 pixels x0+8g .. +7 of row y0+row
+    const int x = x0 + g * kBandPix, y = y0 + row;
+    const bool inside = y < a.Y && x < a.X;
     const int c0 = blockIdx.z * kBandMaxCh;
     const int nc = min(kBandMaxCh, a.nch - c0);
+    const size_t plane = (size_t)a.Y * a.X;
+    const uint16_t* src0 = a.stack + (size_t)a.ch[c0] * a.channel_stride + a.z0_offset + (size_t)y * a.X + x;
+    const uint16_t* src1 = a.stack + (size_t)a.ch[c0 + (nc > 1 ? 1 : 0)] * a.channel_stride + a.z0_offset +
+                           (size_t)y * a.X + x;
+    const float ped = (float)a.pedestal + 8388608.0f;
 
-    float win[kBandPix][9];
+    // pending masks of planes t-4 .. t+4(+2): unrolled by 3 so the window shifts by 3 every 3 steps
+    float win[kBandPix][11];
     float best[kBandMaxCh][kBandPix];
 #pragma unroll
     for (int p = 0; p < kBandPix; ++p) {
 #pragma unroll
-        for (int i = 0; i < 9; ++i) win[p][i] = 0.f;
+        for (int i = 0; i < 11; ++i) win[p][i] = 0.f;
 #pragma unroll
         for (int c = 0; c < kBandMaxCh; ++c) best[c][p] = 0.f;
     }
+    int live = 0;                                   // steps during which this thread's window may be non-zero
 
-    for (int t = zlo; t <= zhi + 8; ++t) {
-        float a_new[kBandPix];
+    uint4 nxt0 = make_uint4(0, 0, 0, 0), nxt1 = nxt0;
+    {
+        const int z = zlo - 4;
+        if (inside && z >= 0 && z < a.Z) {
+            nxt0 = band_load8(src0 + (size_t)z * plane, x, a.X, a.vec != 0);
+            if (nc > 1) nxt1 = band_load8(src1 + (size_t)z * plane, x, a.X, a.vec != 0);
+        }
+    }
+
+    for (int tb = zlo; tb <= zhi + 8; tb += 3) {
 #pragma unroll
-        for (int p = 0; p < kBandPix; ++p) a_new[p] = 0.f;
-        const bool have = t <= zhi && ((present[t >> 5] >> (t & 31)) & 1u);
-        if (have) {                                   // block-uniform
-            // x pass: b_s[row][x] = sum_dx w2[dx] * [cz(row, x+dx) == t], 4 outputs per task
-            for (int task = tid; task < CH * (kBandTX / 4); task += kBandThreads) {
-                const int row = task / (kBandTX / 4), xq = (task % (kBandTX / 4)) * 4;
-                float oh[20];
-                const int4* src = reinterpret_cast<const int4*>(&cz_s[row][xq]);
-#pragma unroll
-                for (int q = 0; q < 5; ++q) {
-                    const int4 v = src[q];
-                    oh[4 * q + 0] = v.x == t ? 1.f : 0.f;
-                    oh[4 * q + 1] = v.y == t ? 1.f : 0.f;
-                    oh[4 * q + 2] = v.z == t ? 1.f : 0.f;
-                    oh[4 * q + 3] = v.w == t ? 1.f : 0.f;
-                }
-                float o[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                for (int k = 0; k < 17; ++k)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) o[j] = fmaf(c_w2[k], oh[j + k], o[j]);
-                *reinterpret_cast<float4*>(&b_s[row][xq]) = make_float4(o[0], o[1], o[2], o[3]);
-            }
-            __syncthreads();
-            // y pass into registers: a_new[p] = sum_dy w2[dy] * b_s[ybase + p + dy][tx]
-#pragma unroll
-            for (int i = 0; i < kBandPix + 16; ++i) {
-                const float v = b_s[ybase + i][tx];
-#pragma unroll
-                for (int p = 0; p < kBandPix; ++p) {
-                    const int k = i - p;
-                    if (k >= 0 && k < 17) a_new[p] = fmaf(c_w2[k], v, a_new[p]);
+        for (int u = 0; u < 3; ++u) {
+            const int t = tb + u;
+            if (t > zhi + 8) break;                                    // block-uniform
+            const uint4 cur0 = nxt0, cur1 = nxt1;
+            {   // prefetch the voxels of the next output plane while this one is processed
+                const int zn = t - 3;
+                if (inside && zn >= 0 && zn < a.Z && t + 1 <= zhi + 8) {
+                    nxt0 = band_load8(src0 + (size_t)zn * plane, x, a.X, a.vec != 0);
+                    if (nc > 1) nxt1 = band_load8(src1 + (size_t)zn * plane, x, a.X, a.vec != 0);
                 }
             }
-            __syncthreads();
-        }
-        const int z = t - 4;
-        const bool zvalid = z >= 0 && z < a.Z;
-        float wzr[9];
-        if (zvalid) {
+            const bool have = t <= zhi && ((present[t >> 5] >> (t & 31)) & 1u);
+            if (have) {                                                // block-uniform
+                // x pass: b_s[r][x] = sum_dx w2[dx] * [cz(r, x+dx) == t], 4 outputs per task
+                for (int task = tid; task < CH * (kBandTX / 4); task += kBandThreads) {
+                    const int r = task / (kBandTX / 4), xq = (task % (kBandTX / 4)) * 4;
+                    float oh[20];
+                    const int4* src = reinterpret_cast<const int4*>(&cz_s[r][xq]);
+                    bool any = false;
 #pragma unroll
-            for (int i = 0; i < 9; ++i) wzr[i] = a.wz[z * 9 + i];
-        }
+                    for (int q = 0; q < 5; ++q) {
+                        const int4 v = src[q];
+                        oh[4 * q + 0] = v.x == t ? 1.f : 0.f;
+                        oh[4 * q + 1] = v.y == t ? 1.f : 0.f;
+                        oh[4 * q + 2] = v.z == t ? 1.f : 0.f;
+                        oh[4 * q + 3] = v.w == t ? 1.f : 0.f;
+                        any |= (v.x == t) | (v.y == t) | (v.z == t) | (v.w == t);
+                    }
+                    float o[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (any) {
 #pragma unroll
-        for (int p = 0; p < kBandPix; ++p) {
+                        for (int k = 0; k < 17; ++k)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) win[p][i] = win[p][i + 1];
-            win[p][8] = a_new[p];
-        }
-        if (zvalid) {
+                            for (int j = 0; j < 4; ++j) o[j] = fmaf(c_w2[k], oh[j + k], o[j]);
+                    }
+                    *reinterpret_cast<float4*>(&b_s[r][band_col(xq)]) = make_float4(o[0], o[1], o[2], o[3]);
+                }
+                __syncthreads();
+                // y pass: a_new[p] = sum_dy w2[dy] * b_s[row + dy][x + p]
+                float a_new[kBandPix];
 #pragma unroll
-            for (int p = 0; p < kBandPix; ++p) {
-                const int y = y0 + ybase + p;
-                float m = 0.f;
+                for (int p = 0; p < kBandPix; ++p) a_new[p] = 0.f;
 #pragma unroll
-                for (int i = 0; i < 9; ++i) m = fmaf(wzr[i], win[p][i], m);
-                if (y < a.Y && x < a.X && m != 0.f) {
-                    const size_t off = a.z0_offset + ((size_t)z * a.Y + y) * a.X + x;
+                for (int dy = 0; dy < 17; ++dy) {
+                    const float4 lo4 = *reinterpret_cast<const float4*>(&b_s[row + dy][g * 4]);
+                    const float4 hi4 = *reinterpret_cast<const float4*>(&b_s[row + dy][32 + g * 4]);
+                    const float w = c_w2[dy];
+                    a_new[0] = fmaf(w, lo4.x, a_new[0]); a_new[1] = fmaf(w, lo4.y, a_new[1]);
+                    a_new[2] = fmaf(w, lo4.z, a_new[2]); a_new[3] = fmaf(w, lo4.w, a_new[3]);
+                    a_new[4] = fmaf(w, hi4.x, a_new[4]); a_new[5] = fmaf(w, hi4.y, a_new[5]);
+                    a_new[6] = fmaf(w, hi4.z, a_new[6]); a_new[7] = fmaf(w, hi4.w, a_new[7]);
+                }
+                __syncthreads();
+                bool nzero = false;
 #pragma unroll
-                    for (int c = 0; c < kBandMaxCh; ++c) {
-                        if (c < nc) {
-                            int v = (int)a.stack[(size_t)a.ch[c0 + c] * a.channel_stride + off] - a.pedestal;
-                            const float f = (float)(v > 0 ? v : 0);
-                            best[c][p] = fmaxf(best[c][p], __fmul_rn(f, m));
-                        }
+                for (int p = 0; p < kBandPix; ++p) nzero |= a_new[p] != 0.f;
+                if (nzero) {
+                    live = 9;
+                    // plane t feeds the masks of z = t-4+k (window slot u+k) with the (z, t) entry of the
+                    // edge-replicating z matrix: interior rows are the plain sigma=1 taps
+                    const bool edge = t - 4 < 4 || t + 4 > a.Z - 5;
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) {
+                        const int z = t - 4 + k;
+                        float w = c_w1[8 - k];
+                        if (edge) w = (z >= 0 && z < a.Z) ? __ldg(a.wz + z * 9 + (8 - k)) : 0.f;
+#pragma unroll
+                        for (int p = 0; p < kBandPix; ++p) win[p][u + k] = fmaf(w, a_new[p], win[p][u + k]);
                     }
                 }
             }
+            const int z = t - 4;
+            if (live > 0 && inside && z >= 0 && z < a.Z) {
+                const uint32_t w0[4] = {cur0.x, cur0.y, cur0.z, cur0.w};
+                const uint32_t w1[4] = {cur1.x, cur1.y, cur1.z, cur1.w};
+#pragma unroll
+                for (int p = 0; p < kBandPix; ++p) {
+                    const float m = win[p][u];
+                    const uint32_t v0 = (p & 1) ? (w0[p >> 1] >> 16) : (w0[p >> 1] & 0xffffu);
+                    const float f0 = fmaxf(__uint_as_float(0x4B000000u | v0) - ped, 0.f);
+                    best[0][p] = fmaxf(best[0][p], __fmul_rn(f0, m));
+                    if (nc > 1) {
+                        const uint32_t v1 = (p & 1) ? (w1[p >> 1] >> 16) : (w1[p >> 1] & 0xffffu);
+                        const float f1 = fmaxf(__uint_as_float(0x4B000000u | v1) - ped, 0.f);
+                        best[1][p] = fmaxf(best[1][p], __fmul_rn(f1, m));
+                    }
+                }
+            }
+            live -= live > 0;
+        }
+        // slide the window by 3 planes
+#pragma unroll
+        for (int p = 0; p < kBandPix; ++p) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) win[p][i] = win[p][i + 3];
+            win[p][8] = win[p][9] = win[p][10] = 0.f;
         }
     }
+    if (inside) {
 #pragma unroll
-    for (int p = 0; p < kBandPix; ++p) {
-        const int y = y0 + ybase + p;
-        if (y < a.Y && x < a.X) {
+        for (int c = 0; c < kBandMaxCh; ++c) {
+            if (c < nc) {
+                float* dst = a.proj + ((size_t)a.ch[c0 + c] * a.Y + y) * a.X + x;
 #pragma unroll
-            for (int c = 0; c < kBandMaxCh; ++c)
-                if (c < nc) a.proj[((size_t)a.ch[c0 + c] * a.Y + y) * a.X + x] = best[c][p];
+                for (int p = 0; p < kBandPix; ++p)
+                    if (x + p < a.X) dst[p] = best[c][p];
+            }
         }
     }
 }
@@ -248,6 +328,10 @@ static int get_wz_table(tsp_handle* h, int Z, const float** out) {
         float w2f[17];
         for (int i = 0; i < 17; ++i) w2f[i] = (float)w2[i];
         TSP_CUDA(cudaMemcpyToSymbol(c_w2, w2f, sizeof w2f));
+        std::vector<double> w1 = gaussian_taps(1.0);
+        float w1f[9];
+        for (int i = 0; i < 9; ++i) w1f[i] = (float)w1[i];
+        TSP_CUDA(cudaMemcpyToSymbol(c_w1, w1f, sizeof w1f));
         h->band_consts = true;
     }
     auto it = h->tables.find(key);
@@ -275,7 +359,12 @@ static int get_wz_table(tsp_handle* h, int Z, const float** out) {
 }
 
 static int launch_band_range(tsp_handle* h, const int32_t* d_zmap, int Z, int Y, int X, int shift,
-                             int32_t* d_status, cudaStream_t s) {
+                             int32_t* d_status, bool range_known, cudaStream_t s) {
+    if (range_known) {
+        band_check_kernel<<<1, 1, 0, s>>>(d_status, Z, shift, 1);
+        TSP_LAUNCH_CHECK(h);
+        return TSP_OK;
+    }
     zmap_range_init_kernel<<<1, 1, 0, s>>>(d_status);
     TSP_LAUNCH_CHECK(h);
     const size_t n = (size_t)Y * X;
@@ -283,14 +372,14 @@ static int launch_band_range(tsp_handle* h, const int32_t* d_zmap, int Z, int Y,
     if (blocks > (size_t)h->sm_count * 8) blocks = (size_t)h->sm_count * 8;
     zmap_range_kernel<<<(int)blocks, 256, 0, s>>>(d_zmap, n, d_status);
     TSP_LAUNCH_CHECK(h);
-    band_check_kernel<<<1, 1, 0, s>>>(d_status, Z, shift);
+    band_check_kernel<<<1, 1, 0, s>>>(d_status, Z, shift, 0);
     TSP_LAUNCH_CHECK(h);
     return TSP_OK;
 }
 
 int launch_band_project_ex(tsp_handle* h, const uint16_t* d_stack, size_t channel_stride, size_t z0_offset,
                            const int32_t* d_zmap, float* d_proj, int C, int Z, int Y, int X, int ref_c,
-                           int shift, int pedestal, int32_t* d_status, cudaStream_t s) {
+                           int shift, int pedestal, int32_t* d_status, bool range_known, cudaStream_t s) {
     if (Z > kBandMaxPlanes) {
         set_error("band projection supports at most %d planes", kBandMaxPlanes);
         return TSP_ERR_INVALID;
@@ -302,7 +391,7 @@ int launch_band_project_ex(tsp_handle* h, const uint16_t* d_stack, size_t channe
     const float* wz = nullptr;
     int rc = get_wz_table(h, Z, &wz);
     if (rc) return rc;
-    rc = launch_band_range(h, d_zmap, Z, Y, X, shift, d_status, s);
+    rc = launch_band_range(h, d_zmap, Z, Y, X, shift, d_status, range_known, s);
     if (rc) return rc;
     BandArgs a;
     a.stack = d_stack;
@@ -316,6 +405,7 @@ int launch_band_project_ex(tsp_handle* h, const uint16_t* d_stack, size_t channe
     a.Y = Y;
     a.X = X;
     a.pedestal = pedestal;
+    a.vec = (X % 8 == 0) && ((reinterpret_cast<uintptr_t>(d_stack) & 15) == 0) ? 1 : 0;
     dim3 grid((X + kBandTX - 1) / kBandTX, (Y + kBandTY - 1) / kBandTY, 1);
     // pass 1: every channel that uses the un-shifted mask (all of them when shift == 0)
     a.shift = 0;
@@ -368,8 +458,8 @@ __global__ void mulmax_kernel(const uint16_t* __restrict__ chan, const float* __
 int launch_band_project_bitexact_ex(tsp_handle* h, const uint16_t* d_stack, size_t channel_stride,
                                     size_t z0_offset, const int32_t* d_zmap, float* d_proj, int C, int Z,
                                     int Y, int X, int ref_c, int shift, int pedestal, float* d_volA,
-                                    float* d_volB, int32_t* d_status, cudaStream_t s) {
-    int rc = launch_band_range(h, d_zmap, Z, Y, X, shift, d_status, s);
+                                    float* d_volB, int32_t* d_status, bool range_known, cudaStream_t s) {
+    int rc = launch_band_range(h, d_zmap, Z, Y, X, shift, d_status, range_known, s);
     if (rc) return rc;
     const size_t plane = (size_t)Y * X;
     size_t blocks = (plane + 255) / 256;

@@ -28,11 +28,19 @@ enum StatusWord {
     ST_NZ_LO = 5,
     ST_NZ_HI = 6,
     ST_NEAR_TIE = 7,
-    ST_TICKET = 8,       // scratch counters for "last block finishes" patterns
-    ST_TICKET2 = 9,
+    ST_WIN_LO = 8,       // percentile: first raw value of the counted window
+    ST_WIN_N = 9,        //             window width in values
+    ST_WIN_OK = 10,      //             1 when the sample produced a usable window
+    ST_NEED_FULL = 11,   //             1 arms the full-histogram fallback
+    ST_ZMIN_INV = 12,    // max over pixels of INT_MAX - z (so that a zeroed block is the identity)
 };
 
 void set_error(const char* fmt, ...);
+
+enum Stage {
+    STG_PERCENTILE = 0, STG_DECIMATE, STG_COARSE, STG_INTERP_ARGMAX, STG_PREPARE, STG_BLUR_PRE, STG_BLUR_SCORE,
+    STG_ARGMAX, STG_BAND, STG_WIDEN, STG_COUNT
+};
 
 #define TSP_CUDA(expr)                                                                       \
     do {                                                                                     \
@@ -85,17 +93,24 @@ struct tsp_handle {
     int32_t* h_status = nullptr;   // pinned copy of the status block
     // per-device one-time setup done (constant memory, function attributes)
     bool fast_consts = false, band_consts = false, hist_attr = false;
+    // optional per-stage timing (tsp_set_profiling): CUDA events recorded on the launching stream
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;       // marks of calls not yet folded into the totals
+    std::vector<int> prof_stage;                // stage id attributed to the interval ending at the mark (-1 = start)
+    std::vector<cudaEvent_t> prof_pool;
+    double prof_ms[16] = {0};
+    int64_t prof_count[16] = {0};
 };
 
 namespace tsp {
 
 int get_taps(tsp_handle* h, double sigma, DeviceTaps* out);
+void prof_mark(tsp_handle* h, cudaStream_t s, int stage);   // stage -1 opens a timed sequence
 
 // stage launchers (each returns TSP_OK or an error code)
-int launch_histogram(tsp_handle* h, const uint16_t* d_vol, size_t count, uint32_t* d_hist,
-                     cudaStream_t s);
-int launch_percentile_finalize(tsp_handle* h, const uint32_t* d_hist, int pedestal, int32_t* d_status,
-                               cudaStream_t s);
+size_t percentile_scratch_bytes();
+int launch_percentile(tsp_handle* h, const uint16_t* d_vol, size_t count, int pedestal, int32_t* d_status,
+                      void* d_scratch, cudaStream_t s);
 int launch_prepare(tsp_handle* h, const uint16_t* d_in, float* d_out, size_t count, int pedestal,
                    const int32_t* d_status, cudaStream_t s);
 int launch_convert_u16_f32(tsp_handle* h, const uint16_t* d_in, float* d_out, size_t count,
@@ -110,11 +125,11 @@ int launch_argmax(tsp_handle* h, const float* d_score, int32_t* d_zmap, int Z, i
                   int z_offset, int32_t* d_status, cudaStream_t s);
 int launch_band_project_ex(tsp_handle* h, const uint16_t* d_stack, size_t channel_stride, size_t z0_offset,
                            const int32_t* d_zmap, float* d_proj, int C, int Z, int Y, int X, int ref_c,
-                           int shift, int pedestal, int32_t* d_status, cudaStream_t s);
+                           int shift, int pedestal, int32_t* d_status, bool range_known, cudaStream_t s);
 int launch_band_project_bitexact_ex(tsp_handle* h, const uint16_t* d_stack, size_t channel_stride,
                                     size_t z0_offset, const int32_t* d_zmap, float* d_proj, int C, int Z,
                                     int Y, int X, int ref_c, int shift, int pedestal, float* d_volA,
-                                    float* d_volB, int32_t* d_status, cudaStream_t s);
+                                    float* d_volB, int32_t* d_status, bool range_known, cudaStream_t s);
 int launch_project_m(tsp_handle* h, const uint16_t* d_channel, uint16_t* d_out, int Z, int Y, int X,
                      int method, int bin, void* d_ws, cudaStream_t s);
 int launch_widen_outputs(tsp_handle* h, const float* d_proj, const int32_t* d_zmap, double* d_proj64,

@@ -1,20 +1,30 @@
-// Stage K1 - 95th percentile of the non-zero voxels (reference surface_projection.py:32-36),
-// exact: a full 65536-bin histogram of the raw uint16 values, then numpy's 'linear' percentile
-// index arithmetic replayed in float32 (numpy/lib/_function_base_impl.py: virtual index
-// (n-1)*q, floor, +1, gamma, _lerp - all float32 for float32 input; SURVEY trap T1).
+// Stage K1 - 95th percentile of the non-zero voxels (reference surface_projection.py:32-36), exact.
+//
+// numpy's 'linear' percentile needs the values at two adjacent sorted ranks; its index arithmetic
+// is replayed in float32 (numpy/lib/_function_base_impl.py: virtual index (n-1)*q, floor, +1,
+// gamma, _lerp - all float32 for float32 input; SURVEY trap T1).
+//
+// A full 65536-bin histogram costs one shared-memory atomic per voxel (~0.45 ms for 268 M voxels).
+// Large volumes therefore take the order statistics in three steps, all exact:
+//   1. hist16_kernel on a pseudo-random 1/stride subsample of 16-byte vectors -> a value window
+//      [lo, lo+W) that contains the wanted ranks with overwhelming probability
+//   2. window_count_kernel: one streaming pass that only COUNTS (voxels > pedestal, voxels < lo)
+//      and histograms the few voxels inside the window
+//   3. window_finalize_kernel: the ranks are resolved inside the window, or - if the window missed
+//      or was too wide - a flag arms the full-histogram fallback (step 1's kernel over everything).
+// Small volumes (stride 1) use the full histogram directly.
 #include "common.cuh"
 
 namespace tsp {
 
-// ---- histogram --------------------------------------------------------------------------------
-// Per-CTA privatised histogram in shared memory with two 16-bit counters per 32-bit word
-// (65536 bins = 128 KB).  A CTA adds at most kChunk < 65536 voxels between flushes, so no
-// counter can overflow; a flush adds the non-zero counters to the global histogram.
 constexpr int kHistThreads = 1024;
 constexpr int kVecPerThread = 7;                                      // uint4 loads per thread per chunk
 static_assert(kHistThreads * kVecPerThread * 8 + 16 < 65536, "16-bit counters must not overflow between flushes");
 constexpr int kHistSmemBytes = kHistBins / 2 * 4;                     // 131072
+constexpr int kWinBins = 4096;                                        // widest value window counted in one pass
+constexpr size_t kSampleTarget = (size_t)1 << 22;                     // ~4 M sampled voxels
 
+// ---- per-CTA privatised histogram: two 16-bit counters per 32-bit shared word --------------------
 __device__ __forceinline__ void hist_add(uint32_t* sh, uint32_t v) {
     atomicAdd(&sh[v >> 1], (v & 1u) ? 0x10000u : 1u);
 }
@@ -24,21 +34,31 @@ __device__ __forceinline__ void hist_add_word(uint32_t* sh, uint32_t w) {
     hist_add(sh, w >> 16);
 }
 
+__device__ __forceinline__ uint32_t hash32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+
+// stride == 1: exact histogram of all `count` voxels.  stride = 2^k > 1: one 16-byte vector out of
+// every `stride`, at a hashed position inside its group (head/tail voxels are skipped).
+// `gate`: when non-null the kernel only runs if *gate != 0 (full-histogram fallback).
 __global__ void __launch_bounds__(kHistThreads, 1)
-hist16_kernel(const uint16_t* __restrict__ vol, size_t count, uint32_t* __restrict__ ghist) {
+hist16_kernel(const uint16_t* __restrict__ vol, size_t count, uint32_t* __restrict__ ghist, uint32_t stride,
+              const int32_t* __restrict__ gate) {
+    if (gate && *gate == 0) return;
     extern __shared__ uint32_t sh[];
     for (int i = threadIdx.x; i < kHistBins / 2; i += kHistThreads) sh[i] = 0;
     __syncthreads();
 
-    // split [0,count) into a scalar head up to 16-byte alignment, a vector body, a scalar tail
     const uintptr_t addr = reinterpret_cast<uintptr_t>(vol);
     size_t head = ((16 - (addr & 15)) & 15) / 2;
     if (head > count) head = count;
-    const size_t nvec = (count - head) / 8;
-    const size_t tail0 = head + nvec * 8;
+    const size_t nvec_all = (count - head) / 8;
+    const size_t tail0 = head + nvec_all * 8;
     const uint4* body = reinterpret_cast<const uint4*>(vol + head);
+    const size_t nvec = nvec_all / stride;                    // sampled vectors
 
-    if (blockIdx.x == 0) {
+    if (blockIdx.x == 0 && stride == 1) {
         for (size_t i = threadIdx.x; i < head; i += kHistThreads) hist_add(sh, vol[i]);
         for (size_t i = tail0 + threadIdx.x; i < count; i += kHistThreads) hist_add(sh, vol[i]);
     }
@@ -51,7 +71,9 @@ hist16_kernel(const uint16_t* __restrict__ vol, size_t count, uint32_t* __restri
 #pragma unroll
         for (int j = 0; j < kVecPerThread; ++j) {
             const size_t idx = base + (size_t)j * kHistThreads + threadIdx.x;
-            v[j] = idx < nvec ? __ldg(body + idx) : make_uint4(0, 0, 0, 0);
+            size_t src = idx;
+            if (stride > 1) src = idx * stride + (hash32((uint32_t)idx) & (stride - 1));
+            v[j] = idx < nvec ? __ldg(body + src) : make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
         for (int j = 0; j < kVecPerThread; ++j) {
@@ -64,7 +86,6 @@ hist16_kernel(const uint16_t* __restrict__ vol, size_t count, uint32_t* __restri
             }
         }
         __syncthreads();
-        // flush: 32 words per thread, vectorised
         uint4* sh4 = reinterpret_cast<uint4*>(sh);
         for (int i = threadIdx.x; i < kHistBins / 8; i += kHistThreads) {
             uint4 w = sh4[i];
@@ -81,9 +102,7 @@ hist16_kernel(const uint16_t* __restrict__ vol, size_t count, uint32_t* __restri
         }
         __syncthreads();
     }
-    // head/tail voxels of block 0 when there was no chunk to flush them with
-    if (blockIdx.x == 0) {
-        __syncthreads();
+    if (blockIdx.x == 0) {      // head/tail voxels when block 0 had no chunk to flush them with
         for (int i = threadIdx.x; i < kHistBins / 2; i += kHistThreads) {
             const uint32_t w = sh[i];
             if (w) {
@@ -94,106 +113,324 @@ hist16_kernel(const uint16_t* __restrict__ vol, size_t count, uint32_t* __restri
     }
 }
 
-int launch_histogram(tsp_handle* h, const uint16_t* d_vol, size_t count, uint32_t* d_hist,
-                     cudaStream_t s) {
-    if (!h->hist_attr) {
-        TSP_CUDA(cudaFuncSetAttribute(hist16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      kHistSmemBytes));
-        h->hist_attr = true;
+// ---- block-wide rank lookup in a table of counts --------------------------------------------------
+// 1024 threads.  counts[0..L), L a multiple of 4096; bins below `first_bin` are ignored.  Returns the
+// total of the counted bins and, for each of the two ranks (0-based, after `base` earlier elements),
+// the smallest bin whose cumulative count exceeds it (-1 when the rank is outside the table).
+struct RankLookup {
+    unsigned long long total;
+    int bin[2];
+};
+
+__device__ RankLookup block_rank_lookup(const uint32_t* __restrict__ counts, int L, int first_bin,
+                                        unsigned long long base, unsigned long long r0, unsigned long long r1) {
+    __shared__ unsigned long long warp_tot[32];
+    __shared__ unsigned long long warp_off[33];
+    __shared__ int found[2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int seg = L / 32;                                   // bins per warp, multiple of 128
+    const uint4* c4 = reinterpret_cast<const uint4*>(counts);
+    if (threadIdx.x < 2) found[threadIdx.x] = -1;
+    auto masked = [&](int b0, uint4 v) {
+        if (b0 + 0 < first_bin) v.x = 0;
+        if (b0 + 1 < first_bin) v.y = 0;
+        if (b0 + 2 < first_bin) v.z = 0;
+        if (b0 + 3 < first_bin) v.w = 0;
+        return v;
+    };
+    unsigned long long mine = 0;
+    for (int c = 0; c < seg / 128; ++c) {
+        const int b0 = warp * seg + c * 128 + lane * 4;
+        const uint4 v = masked(b0, c4[b0 / 4]);
+        mine += (unsigned long long)v.x + v.y + v.z + v.w;
     }
-    TSP_CUDA(cudaMemsetAsync(d_hist, 0, kHistBins * sizeof(uint32_t), s));
-    const size_t nchunks = (count / 8 + (size_t)kHistThreads * kVecPerThread - 1) /
-                           ((size_t)kHistThreads * kVecPerThread);
-    int grid = (int)(nchunks < (size_t)h->sm_count ? (nchunks ? nchunks : 1) : (size_t)h->sm_count);
-    hist16_kernel<<<grid, kHistThreads, kHistSmemBytes, s>>>(d_vol, count, d_hist);
-    TSP_LAUNCH_CHECK(h);
-    return TSP_OK;
+    for (int o = 16; o; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if (lane == 0) warp_tot[warp] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long acc = base;
+        for (int w = 0; w < 32; ++w) {
+            warp_off[w] = acc;
+            acc += warp_tot[w];
+        }
+        warp_off[32] = acc;
+    }
+    __syncthreads();
+    const unsigned long long ranks[2] = {r0, r1};
+    const unsigned long long wlo = warp_off[warp], whi = warp_off[warp + 1];
+    if ((r0 >= wlo && r0 < whi) || (r1 >= wlo && r1 < whi)) {           // warp-uniform
+        unsigned long long run = wlo;
+        for (int c = 0; c < seg / 128; ++c) {
+            const int b0 = warp * seg + c * 128 + lane * 4;
+            const uint4 v = masked(b0, c4[b0 / 4]);
+            const unsigned long long s4 = (unsigned long long)v.x + v.y + v.z + v.w;
+            unsigned long long incl = s4;
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += up;
+            }
+            const unsigned long long excl = run + incl - s4;
+            for (int k = 0; k < 2; ++k) {
+                const unsigned long long r = ranks[k];
+                if (r >= excl && r < excl + s4) {
+                    unsigned long long cum = excl;
+                    const uint32_t vs[4] = {v.x, v.y, v.z, v.w};
+                    for (int i = 0; i < 4; ++i) {
+                        cum += vs[i];
+                        if (cum > r) {
+                            found[k] = b0 + i;
+                            break;
+                        }
+                    }
+                }
+            }
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    }
+    __syncthreads();
+    RankLookup out;
+    out.total = warp_off[32] - base;
+    out.bin[0] = found[0];
+    out.bin[1] = found[1];
+    __syncthreads();
+    return out;
 }
 
-// ---- percentile from the histogram ----------------------------------------------------------------
-// One CTA.  Bin b holds raw value b; after the optional pedestal the voxel value is b - pedestal,
-// non-zero when b > pedestal.
-__global__ void __launch_bounds__(1024, 1)
-percentile_finalize_kernel(const uint32_t* __restrict__ ghist, int pedestal, int32_t* __restrict__ status) {
-    __shared__ unsigned long long part[1024];
-    __shared__ unsigned long long total_s;
-    __shared__ int val_s[2];
-    const int t = threadIdx.x;
-    const int b0 = t * 64;
-    unsigned long long mine = 0;
-    for (int i = 0; i < 64; ++i) {
-        const int b = b0 + i;
-        if (b > pedestal) mine += ghist[b];
-    }
-    part[t] = mine;
-    __syncthreads();
-    // inclusive scan (Hillis-Steele on 1024 entries)
-    for (int off = 1; off < 1024; off <<= 1) {
-        unsigned long long add = t >= off ? part[t - off] : 0ull;
-        __syncthreads();
-        part[t] += add;
-        __syncthreads();
-    }
-    if (t == 1023) total_s = part[1023];
-    __syncthreads();
-    const unsigned long long n = total_s;
-    if (n == 0) {
-        if (t == 0) {
-            status[ST_HAS_NONZERO] = 0;
-            status[ST_P95_BITS] = 0;
-            status[ST_NZ_LO] = 0;
-            status[ST_NZ_HI] = 0;
-        }
-        return;
-    }
-    // numpy: q = float32(95)/float32(100); vi = float32(n-1) * q   (all float32, round to nearest)
+// numpy 'linear' rank arithmetic in float32 for n values: ranks of the two neighbours and gamma
+struct RankPair {
+    unsigned long long prev, next;
+    float gamma;
+};
+
+__device__ RankPair numpy_ranks(unsigned long long n) {
     const float q = __fdiv_rn(95.0f, 100.0f);
     const float nm1 = __ull2float_rn(n - 1);
     const float vi = __fmul_rn(nm1, q);
-    float prev_f = floorf(vi);
-    float next_f = __fadd_rn(prev_f, 1.0f);
-    long long prev_i, next_i;
-    if (vi >= nm1) {            // indexes_above_bounds -> index -1 = last element
-        prev_i = next_i = (long long)n - 1;
+    const float prev_f = floorf(vi);
+    const float next_f = __fadd_rn(prev_f, 1.0f);
+    RankPair r;
+    if (vi >= nm1) {                                   // indexes_above_bounds -> index -1 = last element
+        r.prev = r.next = n - 1;
     } else {
-        prev_i = (long long)prev_f;
-        next_i = (long long)next_f;
-        if (next_i > (long long)n - 1) next_i = (long long)n - 1;   // cannot happen for q<1; guard
+        r.prev = (unsigned long long)prev_f;
+        r.next = (unsigned long long)next_f;
+        if (r.next > n - 1) r.next = n - 1;            // cannot happen for q < 1; guard
     }
-    const float gamma = __fsub_rn(vi, prev_f);
-    // value at sorted rank r = smallest bin with cumulative count > r
-    const unsigned long long before = part[t] - mine;
-    const long long ranks[2] = {prev_i, next_i};
-    for (int k = 0; k < 2; ++k) {
-        const unsigned long long r = (unsigned long long)ranks[k];
-        if (r >= before && r < part[t]) {
-            unsigned long long cum = before;
-            for (int i = 0; i < 64; ++i) {
-                const int b = b0 + i;
-                if (b > pedestal) cum += ghist[b];
-                if (cum > r) {
-                    val_s[k] = b - pedestal;
-                    break;
+    r.gamma = __fsub_rn(vi, prev_f);
+    return r;
+}
+
+__device__ float numpy_lerp(float a, float b, float gamma) {
+    const float diff = __fsub_rn(b, a);
+    float res = __fadd_rn(a, __fmul_rn(diff, gamma));
+    if (gamma >= 0.5f) res = __fsub_rn(b, __fmul_rn(diff, __fsub_rn(1.0f, gamma)));
+    return res;
+}
+
+__device__ void write_result(int32_t* status, unsigned long long n, float p) {
+    status[ST_HAS_NONZERO] = n > 0 ? 1 : 0;
+    status[ST_P95_BITS] = __float_as_int(p);
+    status[ST_NZ_LO] = (int32_t)(n & 0xffffffffull);
+    status[ST_NZ_HI] = (int32_t)(n >> 32);
+}
+
+// ---- exact percentile from a full histogram (also the fallback) -----------------------------------
+__global__ void __launch_bounds__(1024, 1)
+percentile_finalize_kernel(const uint32_t* __restrict__ ghist, int pedestal, int32_t* __restrict__ status,
+                           const int32_t* __restrict__ gate) {
+    if (gate && *gate == 0) return;
+    // pass 1: total of the non-zero voxels, pass 2: the two ranks
+    RankLookup first = block_rank_lookup(ghist, kHistBins, pedestal + 1, 0, ~0ull, ~0ull);
+    const unsigned long long n = first.total;
+    if (n == 0) {
+        if (threadIdx.x == 0) write_result(status, 0, 0.f);
+        return;
+    }
+    const RankPair rp = numpy_ranks(n);
+    RankLookup look = block_rank_lookup(ghist, kHistBins, pedestal + 1, 0, rp.prev, rp.next);
+    if (threadIdx.x == 0)
+        write_result(status, n, numpy_lerp((float)(look.bin[0] - pedestal), (float)(look.bin[1] - pedestal), rp.gamma));
+}
+
+// ---- step 1b: value window from the sample histogram ----------------------------------------------
+__global__ void __launch_bounds__(1024, 1)
+window_select_kernel(const uint32_t* __restrict__ shist, int pedestal, int32_t* __restrict__ status) {
+    RankLookup first = block_rank_lookup(shist, kHistBins, pedestal + 1, 0, ~0ull, ~0ull);
+    const unsigned long long ns = first.total;
+    if (ns < 1024) {                  // sample too thin to trust: go straight to the full histogram
+        if (threadIdx.x == 0) {
+            status[ST_WIN_OK] = 0;
+            status[ST_NEED_FULL] = 1;
+        }
+        return;
+    }
+    const double centre = 0.95 * (double)(ns - 1);
+    const double margin = 4.0 + 24.0 * sqrt((double)ns * 0.0475);
+    const double lo_r = centre - margin, hi_r = centre + margin + 1.0;
+    const unsigned long long r_lo = lo_r < 0.0 ? 0ull : (unsigned long long)lo_r;
+    const unsigned long long r_hi = hi_r > (double)(ns - 1) ? ns - 1 : (unsigned long long)hi_r;
+    RankLookup look = block_rank_lookup(shist, kHistBins, pedestal + 1, 0, r_lo, r_hi);
+    if (threadIdx.x == 0) {
+        int lo = look.bin[0] - 1, hi = look.bin[1] + 1;          // raw-value bins, one spare on each side
+        if (lo < pedestal + 1) lo = pedestal + 1;
+        if (hi > kHistBins - 1) hi = kHistBins - 1;
+        const int w = hi - lo + 1;
+        const bool ok = w <= kWinBins;
+        status[ST_WIN_LO] = lo;
+        status[ST_WIN_N] = w;
+        status[ST_WIN_OK] = ok ? 1 : 0;
+        status[ST_NEED_FULL] = ok ? 0 : 1;
+    }
+}
+
+// ---- step 2: streaming count pass -----------------------------------------------------------------
+constexpr int kCountThreads = 512;
+constexpr int kCountUnroll = 4;
+
+__global__ void __launch_bounds__(kCountThreads)
+window_count_kernel(const uint16_t* __restrict__ vol, size_t count, int pedestal, int32_t* __restrict__ status,
+                    uint32_t* __restrict__ gwin, unsigned long long* __restrict__ gcounters) {
+    if (status[ST_WIN_OK] == 0) return;
+    __shared__ uint32_t win[kWinBins];
+    __shared__ unsigned long long blk[2];
+    const uint32_t lo = (uint32_t)status[ST_WIN_LO], wn = (uint32_t)status[ST_WIN_N];
+    const uint32_t ped = (uint32_t)pedestal;
+    for (int i = threadIdx.x; i < kWinBins; i += kCountThreads) win[i] = 0;
+    if (threadIdx.x < 2) blk[threadIdx.x] = 0;
+    __syncthreads();
+
+    uint32_t nz = 0, below = 0;              // per-thread counts (< 2^32 voxels per thread)
+    auto one = [&](uint32_t v) {
+        nz += v > ped;
+        below += v < lo;
+        const uint32_t d = v - lo;
+        if (d < wn) atomicAdd(&win[d], 1u);
+    };
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(vol);
+    size_t head = ((16 - (addr & 15)) & 15) / 2;
+    if (head > count) head = count;
+    const size_t nvec = (count - head) / 8;
+    const size_t tail0 = head + nvec * 8;
+    const uint4* body = reinterpret_cast<const uint4*>(vol + head);
+    if (blockIdx.x == 0) {
+        for (size_t i = threadIdx.x; i < head; i += kCountThreads) one(vol[i]);
+        for (size_t i = tail0 + threadIdx.x; i < count; i += kCountThreads) one(vol[i]);
+    }
+    const size_t step = (size_t)gridDim.x * kCountThreads;
+    for (size_t i0 = (size_t)blockIdx.x * kCountThreads + threadIdx.x; i0 < nvec; i0 += step * kCountUnroll) {
+        uint4 v[kCountUnroll];
+#pragma unroll
+        for (int j = 0; j < kCountUnroll; ++j) {
+            const size_t i = i0 + (size_t)j * step;
+            v[j] = i < nvec ? __ldg(body + i) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int j = 0; j < kCountUnroll; ++j) {
+            const size_t i = i0 + (size_t)j * step;
+            if (i < nvec) {
+                const uint32_t ws[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    one(ws[q] & 0xffffu);
+                    one(ws[q] >> 16);
                 }
             }
         }
     }
+    for (int o = 16; o; o >>= 1) {
+        nz += __shfl_xor_sync(0xffffffffu, nz, o);
+        below += __shfl_xor_sync(0xffffffffu, below, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&blk[0], (unsigned long long)nz);
+        atomicAdd(&blk[1], (unsigned long long)below);
+    }
     __syncthreads();
-    if (t == 0) {
-        const float a = (float)val_s[0], b = (float)val_s[1];
-        const float diff = __fsub_rn(b, a);
-        float res = __fadd_rn(a, __fmul_rn(diff, gamma));
-        if (gamma >= 0.5f) res = __fsub_rn(b, __fmul_rn(diff, __fsub_rn(1.0f, gamma)));
-        status[ST_HAS_NONZERO] = 1;
-        status[ST_P95_BITS] = __float_as_int(res);
-        status[ST_NZ_LO] = (int32_t)(n & 0xffffffffull);
-        status[ST_NZ_HI] = (int32_t)(n >> 32);
+    if (threadIdx.x == 0) {
+        atomicAdd(&gcounters[0], blk[0]);
+        atomicAdd(&gcounters[1], blk[1]);
+    }
+    for (int i = threadIdx.x; i < kWinBins; i += kCountThreads)
+        if (win[i]) atomicAdd(&gwin[i], win[i]);
+}
+
+// ---- step 3 ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024, 1)
+window_finalize_kernel(const uint32_t* __restrict__ gwin, const unsigned long long* __restrict__ gcounters,
+                       unsigned long long count, int pedestal, int32_t* __restrict__ status) {
+    if (status[ST_WIN_OK] == 0) return;            // NEED_FULL already set by window_select_kernel
+    const unsigned long long n = gcounters[0];      // voxels > pedestal
+    if (n == 0) {
+        if (threadIdx.x == 0) write_result(status, 0, 0.f);
+        return;
+    }
+    const unsigned long long zeros = count - n;     // voxels <= pedestal (they are all below the window)
+    const unsigned long long below_nz = gcounters[1] - zeros;
+    const RankPair rp = numpy_ranks(n);
+    RankLookup look = block_rank_lookup(gwin, kWinBins, 0, below_nz, rp.prev, rp.next);
+    if (threadIdx.x == 0) {
+        const int lo = status[ST_WIN_LO];
+        if (look.bin[0] < 0 || look.bin[1] < 0 || rp.prev < below_nz) {
+            status[ST_NEED_FULL] = 1;               // the sample window missed: exact fallback
+        } else {
+            write_result(status, n, numpy_lerp((float)(lo + look.bin[0] - pedestal),
+                                               (float)(lo + look.bin[1] - pedestal), rp.gamma));
+        }
     }
 }
 
-int launch_percentile_finalize(tsp_handle* h, const uint32_t* d_hist, int pedestal, int32_t* d_status,
-                               cudaStream_t s) {
-    percentile_finalize_kernel<<<1, 1024, 0, s>>>(d_hist, pedestal, d_status);
+// ---- launchers ------------------------------------------------------------------------------------
+size_t percentile_scratch_bytes() {
+    // [sample/full histogram 256 KB][fallback histogram 256 KB][window 16 KB][counters 64 B]
+    return 2 * kHistBins * sizeof(uint32_t) + kWinBins * sizeof(uint32_t) + 64;
+}
+
+static int ensure_hist_attr(tsp_handle* h) {
+    if (!h->hist_attr) {
+        TSP_CUDA(cudaFuncSetAttribute(hist16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmemBytes));
+        h->hist_attr = true;
+    }
+    return TSP_OK;
+}
+
+static int hist_grid(tsp_handle* h, size_t count, uint32_t stride) {
+    const size_t per_chunk = (size_t)kHistThreads * kVecPerThread * 8 * stride;
+    const size_t nchunks = (count + per_chunk - 1) / per_chunk;
+    return (int)(nchunks < (size_t)h->sm_count ? (nchunks ? nchunks : 1) : (size_t)h->sm_count);
+}
+
+// d_scratch: percentile_scratch_bytes() bytes.  Writes ST_HAS_NONZERO / ST_P95_BITS / ST_NZ_* into d_status.
+int launch_percentile(tsp_handle* h, const uint16_t* d_vol, size_t count, int pedestal, int32_t* d_status,
+                      void* d_scratch, cudaStream_t s) {
+    int rc = ensure_hist_attr(h);
+    if (rc) return rc;
+    uint32_t* hist_a = (uint32_t*)d_scratch;
+    uint32_t* hist_b = hist_a + kHistBins;
+    uint32_t* win = hist_b + kHistBins;
+    unsigned long long* counters = (unsigned long long*)(win + kWinBins);
+    TSP_CUDA(cudaMemsetAsync(d_scratch, 0, percentile_scratch_bytes(), s));
+    uint32_t stride = 1;
+    while ((count / stride) > 2 * kSampleTarget && stride < 1024) stride *= 2;
+    if (stride == 1) {
+        hist16_kernel<<<hist_grid(h, count, 1), kHistThreads, kHistSmemBytes, s>>>(d_vol, count, hist_a, 1, nullptr);
+        TSP_LAUNCH_CHECK(h);
+        percentile_finalize_kernel<<<1, 1024, 0, s>>>(hist_a, pedestal, d_status, nullptr);
+        TSP_LAUNCH_CHECK(h);
+        return TSP_OK;
+    }
+    hist16_kernel<<<hist_grid(h, count, stride), kHistThreads, kHistSmemBytes, s>>>(d_vol, count, hist_a, stride, nullptr);
+    TSP_LAUNCH_CHECK(h);
+    window_select_kernel<<<1, 1024, 0, s>>>(hist_a, pedestal, d_status);
+    TSP_LAUNCH_CHECK(h);
+    window_count_kernel<<<h->sm_count * 4, kCountThreads, 0, s>>>(d_vol, count, pedestal, d_status, win, counters);
+    TSP_LAUNCH_CHECK(h);
+    window_finalize_kernel<<<1, 1024, 0, s>>>(win, counters, (unsigned long long)count, pedestal, d_status);
+    TSP_LAUNCH_CHECK(h);
+    // exact fallback, armed by ST_NEED_FULL (both kernels return at once otherwise)
+    hist16_kernel<<<hist_grid(h, count, 1), kHistThreads, kHistSmemBytes, s>>>(d_vol, count, hist_b, 1,
+                                                                             d_status + ST_NEED_FULL);
+    TSP_LAUNCH_CHECK(h);
+    percentile_finalize_kernel<<<1, 1024, 0, s>>>(hist_b, pedestal, d_status, d_status + ST_NEED_FULL);
     TSP_LAUNCH_CHECK(h);
     return TSP_OK;
 }
