@@ -148,19 +148,31 @@ __global__ void __launch_bounds__(kBandThreads, 2) band_project_kernel(const Ban
         zlo_s = INT32_MAX;
         zhi_s = INT32_MIN;
     }
-    for (int i = tid; i < kBandMaxPlanes / 32; i += kBandThreads) present[i] = 0;
+    for (int i = tid; i < (a.Z >> 5) + 1 && i < kBandMaxPlanes / 32; i += kBandThreads) present[i] = 0;
     __syncthreads();
     {
-        int lo = INT32_MAX, hi = INT32_MIN;
-        for (int i = tid; i < CH * CW; i += kBandThreads) {
+        // all height-map loads of the thread are issued before any is used (tile + halo = 15 per thread)
+        constexpr int kPer = (CH * CW + kBandThreads - 1) / kBandThreads;
+        int vals[kPer];
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            const int i = tid + k * kBandThreads;
             const int yy = min(max(y0 - kBandHalo + i / CW, 0), a.Y - 1);
             const int xx = min(max(x0 - kBandHalo + i % CW, 0), a.X - 1);
-            int v = __ldg(a.zmap + (size_t)yy * a.X + xx);
-            if (a.shift != 0) v = min(max(v + a.shift, 0), a.Z);
-            cz_s[i / CW][i % CW] = v;
-            lo = min(lo, v);
-            hi = max(hi, v);
-            atomicOr(&present[v >> 5], 1u << (v & 31));
+            vals[k] = i < CH * CW ? __ldg(a.zmap + (size_t)yy * a.X + xx) : 0;
+        }
+        int lo = INT32_MAX, hi = INT32_MIN;
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            const int i = tid + k * kBandThreads;
+            if (i < CH * CW) {
+                int v = vals[k];
+                if (a.shift != 0) v = min(max(v + a.shift, 0), a.Z);
+                cz_s[i / CW][i % CW] = v;
+                lo = min(lo, v);
+                hi = max(hi, v);
+                atomicOr(&present[v >> 5], 1u << (v & 31));
+            }
         }
         for (int o = 16; o; o >>= 1) {
             lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));

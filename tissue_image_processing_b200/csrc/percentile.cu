@@ -265,7 +265,7 @@ window_select_kernel(const uint32_t* __restrict__ shist, int pedestal, int32_t* 
         return;
     }
     const double centre = 0.95 * (double)(ns - 1);
-    const double margin = 4.0 + 24.0 * sqrt((double)ns * 0.0475);
+    const double margin = 4.0 + 12.0 * sqrt((double)ns * 0.0475);
     const double lo_r = centre - margin, hi_r = centre + margin + 1.0;
     const unsigned long long r_lo = lo_r < 0.0 ? 0ull : (unsigned long long)lo_r;
     const unsigned long long r_hi = hi_r > (double)(ns - 1) ? ns - 1 : (unsigned long long)hi_r;
@@ -286,24 +286,30 @@ window_select_kernel(const uint32_t* __restrict__ shist, int pedestal, int32_t* 
 // ---- step 2: streaming count pass -----------------------------------------------------------------
 constexpr int kCountThreads = 512;
 constexpr int kCountUnroll = 4;
+constexpr int kQueueCap = 1536;              // parked 16-byte vectors per CTA (24 KB)
 
 __global__ void __launch_bounds__(kCountThreads)
 window_count_kernel(const uint16_t* __restrict__ vol, size_t count, int pedestal, int32_t* __restrict__ status,
                     uint32_t* __restrict__ gwin, unsigned long long* __restrict__ gcounters) {
     if (status[ST_WIN_OK] == 0) return;
     __shared__ uint32_t win[kWinBins];
+    __shared__ uint4 queue[kQueueCap];
+    __shared__ uint32_t qtail;
     __shared__ unsigned long long blk[2];
     const uint32_t lo = (uint32_t)status[ST_WIN_LO], wn = (uint32_t)status[ST_WIN_N];
     const uint32_t ped = (uint32_t)pedestal;
     for (int i = threadIdx.x; i < kWinBins; i += kCountThreads) win[i] = 0;
     if (threadIdx.x < 2) blk[threadIdx.x] = 0;
+    if (threadIdx.x == 0) qtail = 0;
     __syncthreads();
 
-    uint32_t nz = 0, below = 0;              // per-thread counts (< 2^32 voxels per thread)
+    // per-thread counts by sign bits: (v - lo) >> 31 is 1 when v < lo; (v - ped - 1) >> 31 is 1 when v <= ped
+    uint32_t below = 0, zeros = 0, seen = 0;
+    const uint32_t ped1 = ped + 1, wn1 = wn - 1;
     auto one = [&](uint32_t v) {
-        nz += v > ped;
-        below += v < lo;
         const uint32_t d = v - lo;
+        below += d >> 31;
+        zeros += (v - ped1) >> 31;
         if (d < wn) atomicAdd(&win[d], 1u);
     };
     const uintptr_t addr = reinterpret_cast<uintptr_t>(vol);
@@ -313,8 +319,8 @@ window_count_kernel(const uint16_t* __restrict__ vol, size_t count, int pedestal
     const size_t tail0 = head + nvec * 8;
     const uint4* body = reinterpret_cast<const uint4*>(vol + head);
     if (blockIdx.x == 0) {
-        for (size_t i = threadIdx.x; i < head; i += kCountThreads) one(vol[i]);
-        for (size_t i = tail0 + threadIdx.x; i < count; i += kCountThreads) one(vol[i]);
+        for (size_t i = threadIdx.x; i < head; i += kCountThreads) { one(vol[i]); ++seen; }
+        for (size_t i = tail0 + threadIdx.x; i < count; i += kCountThreads) { one(vol[i]); ++seen; }
     }
     const size_t step = (size_t)gridDim.x * kCountThreads;
     for (size_t i0 = (size_t)blockIdx.x * kCountThreads + threadIdx.x; i0 < nvec; i0 += step * kCountUnroll) {
@@ -322,21 +328,60 @@ window_count_kernel(const uint16_t* __restrict__ vol, size_t count, int pedestal
 #pragma unroll
         for (int j = 0; j < kCountUnroll; ++j) {
             const size_t i = i0 + (size_t)j * step;
-            v[j] = i < nvec ? __ldg(body + i) : make_uint4(0, 0, 0, 0);
+            v[j] = i < nvec ? __ldg(body + i) : make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
         }
 #pragma unroll
         for (int j = 0; j < kCountUnroll; ++j) {
             const size_t i = i0 + (size_t)j * step;
             if (i < nvec) {
                 const uint32_t ws[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+                // branch-free per voxel; "inside the window" (d < wn unsigned) is the sign bit of
+                // d | (wn-1-d) being clear, AND-reduced over the 8 voxels so the rare case branches once
+                uint32_t allout = 0x80000000u;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    one(ws[q] & 0xffffu);
-                    one(ws[q] >> 16);
+#pragma unroll
+                    for (int hlf = 0; hlf < 2; ++hlf) {
+                        const uint32_t val = hlf ? (ws[q] >> 16) : (ws[q] & 0xffffu);
+                        const uint32_t d = val - lo;
+                        below += d >> 31;
+                        zeros += (val - ped1) >> 31;
+                        allout &= d | (wn1 - d);
+                    }
                 }
+                if (!(allout >> 31)) {
+                    // rare: park the whole vector in the CTA queue; it is histogrammed after the stream
+                    const uint32_t slot = atomicAdd(&qtail, 1u);
+                    if (slot < kQueueCap) {
+                        queue[slot] = v[j];
+                    } else {
+#pragma unroll 1
+                        for (int q = 0; q < 8; ++q) {
+                            const uint32_t val = (q & 1) ? (ws[q >> 1] >> 16) : (ws[q >> 1] & 0xffffu);
+                            const uint32_t d = val - lo;
+                            if (d < wn) atomicAdd(&win[d], 1u);
+                        }
+                    }
+                }
+                seen += 8;
             }
         }
     }
+    __syncthreads();
+    {   // drain the queue: one parked vector per thread per round, every lane busy
+        const uint32_t nq = min(qtail, (uint32_t)kQueueCap);
+        for (uint32_t e = threadIdx.x; e < nq; e += kCountThreads) {
+            const uint4 qv = queue[e];
+            const uint32_t ws[4] = {qv.x, qv.y, qv.z, qv.w};
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const uint32_t val = (q & 1) ? (ws[q >> 1] >> 16) : (ws[q >> 1] & 0xffffu);
+                const uint32_t d = val - lo;
+                if (d < wn) atomicAdd(&win[d], 1u);
+            }
+        }
+    }
+    uint32_t nz = seen - zeros;
     for (int o = 16; o; o >>= 1) {
         nz += __shfl_xor_sync(0xffffffffu, nz, o);
         below += __shfl_xor_sync(0xffffffffu, below, o);
