@@ -99,6 +99,17 @@ int tsp_get_frame_status(tsp_handle* h, const void* d_workspace, void* cuda_stre
 int tsp_project_frame_host(tsp_handle* h, const tsp_frame_desc* desc, const uint16_t* h_stack,
                            double* h_proj, int64_t* h_zmap, tsp_frame_status* status);
 
+/* Pipelined form of the same call for movies (SP:205-212 projects the time points of a movie one by
+ * one; they are independent).  A handle owns TSP_MAX_SLOTS frame slots, each with its own stream
+ * and device memory: tsp_frame_submit enqueues copy-in, operator and copy-out of one frame and
+ * returns at once; tsp_frame_wait blocks until that slot's outputs are in h_proj / h_zmap.  With
+ * pinned host buffers the copy-in of frame t+1 overlaps the kernels of frame t.
+ * tsp_project_frame_host == submit + wait on slot 0. */
+#define TSP_MAX_SLOTS 4
+int tsp_frame_submit(tsp_handle* h, int slot, const tsp_frame_desc* desc, const uint16_t* h_stack,
+                     double* h_proj, int64_t* h_zmap);
+int tsp_frame_wait(tsp_handle* h, int slot, tsp_frame_status* status);
+
 /* ---- building blocks (also used one by one by the parity tests) --------------------------- */
 
 /* BIM:373-390 blur_image = scipy.ndimage.gaussian_filter(mode='nearest') on a 3-D float32

@@ -1,0 +1,119 @@
+"""Host-side logic of the drivers and of the frame partition, on CPU (no kernels run here)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import reference_runner, synth
+from oracle import surface_projection_oracle as orc
+from tests.fake_image import FakeAICSImage, install
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _toy_operator(chunk, scale=1.0, z_map=True):
+    """Cheap stand-in with the operator's return contract: (projection (C,Y,X) float64, zmap (Y,X) int64)."""
+    a = chunk.reshape(chunk.shape[1:]).astype(np.float64)
+    return (a.max(axis=1) * scale, a[0].argmax(axis=0).astype(np.int64))
+
+
+@pytest.mark.parametrize("dy,dx", [(0, 0), (16, 16), (10, 24)])
+def test_read_image_in_chunks_scatters_tiles_like_the_reference(monkeypatch, dy, dx):
+    from tissue_image_processing_b200 import basic_image_manipulations as bim
+    rng = np.random.default_rng(0)
+    movie = rng.integers(0, 1000, size=(3, 2, 5, 32, 48)).astype(np.uint16)
+    install(monkeypatch, {"f": FakeAICSImage([movie])})
+    proj = np.zeros((3, 2, 1, 32, 48))
+    zmap = np.zeros((3, 1, 1, 32, 48))
+    n = sum(1 for _ in bim.read_image_in_chunks("f", dt=1, dy=dy, dx=dx, apply_function=_toy_operator,
+                                               output=[proj, zmap], scale=2.0))
+    ty = 1 if dy == 0 else -(-32 // dy)
+    tx = 1 if dx == 0 else -(-48 // dx)
+    assert n == 3 * ty * tx
+    assert np.array_equal(proj[:, :, 0], movie.max(axis=2) * 2.0)
+    assert np.array_equal(zmap[:, 0, 0], movie[:, 0].argmax(axis=1))
+    if reference_runner.available():
+        # same walk through the unmodified reference generator (BIM:89-159) with its reader swapped out
+        reference_runner.load_surface_projection()
+        import basic_image_manipulations as ref_bim
+        monkeypatch.setattr(ref_bim, "AICSImage", lambda path, reader=None: FakeAICSImage([movie]))
+        monkeypatch.setattr(ref_bim, "bioformats_reader", type("R", (), {"BioformatsReader": None}))
+        rproj = np.zeros_like(proj)
+        rzmap = np.zeros_like(zmap)
+        rn = sum(1 for _ in ref_bim.read_image_in_chunks("f", dt=1, dy=dy, dx=dx, apply_function=_toy_operator,
+                                                        output=[rproj, rzmap], scale=2.0))
+        assert rn == n and np.array_equal(rproj, proj) and np.array_equal(rzmap, zmap)
+
+
+def test_put_channel_axis_first_matches_reference_quirk():
+    from tissue_image_processing_b200 import put_channel_axis_first
+    a = np.zeros((4, 2, 5, 6))                       # Z C Y X
+    out, order = put_channel_axis_first(a, "ZCYX")
+    assert out.shape == (2, 4, 6, 5) and tuple(order) == (1, 0, 3, 2)      # C, Z, X, Y (X before Y)
+    same, order = put_channel_axis_first(a, "CZYX")
+    assert same is a and tuple(order) == (0, 1, 2, 3)
+    o2, _ = orc.put_channel_axis_first(a, "ZCYX")
+    assert o2.shape == out.shape
+
+
+def test_concatenate_and_save_conventions(tmp_path):
+    from tissue_image_processing_b200 import surface_projection as sp
+    a = np.full((2, 2, 4, 4), 1000.7)
+    b = np.full((1, 1, 4, 4), 70000.0)                 # fewer channels -> padded in front; uint16 wraps
+    np.save(tmp_path / "a.npy", a)
+    np.save(tmp_path / "b.npy", b)
+    out = sp.concatenate_time_points([str(tmp_path / "a.npy"), str(tmp_path / "b.npy")])
+    assert out.dtype == np.uint16 and out.shape == (3, 2, 4, 4)
+    assert out[0, 0, 0, 0] == 1000 and out[2, 0, 0, 0] == 0 and out[2, 1, 0, 0] == np.float64(70000).astype("uint16")
+    seen = {}
+    sp.tiff_writer, old = (lambda path, image, axes, metadata: seen.update(path=path, image=image, axes=axes)), sp.tiff_writer
+    try:
+        sp.save_tiff("x.tif", np.array([[0.0, 0.5], [1.0, 2.0]]), axes="YX", data_type="uint16")
+    finally:
+        sp.tiff_writer = old
+    assert seen["image"].dtype == np.uint16 and seen["image"].max() == 65535 and seen["image"][0, 1] == 16384
+
+
+def test_frame_partition_is_a_partition():
+    from tissue_image_processing_b200.movie import frame_owner
+    for world in (1, 2, 3, 8):
+        owners = [frame_owner(t, world) for t in range(50)]
+        assert set(owners) == set(range(min(world, 50)))
+        counts = np.bincount(owners, minlength=world)
+        assert counts.max() - counts.min() <= 1
+
+
+def _gloo_worker(rank, world, port, tmp):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tests.fake_image import FakeAICSImage, install
+    from tissue_image_processing_b200 import basic_image_manipulations as bim
+    from tissue_image_processing_b200.movie import FramePipeline
+    movie = np.stack([synth.synth_stack(6, 24, 28, C=2, seed=3, t=t) for t in range(5)])      # (T,C,Z,Y,X)
+    install(bim, {"m": FakeAICSImage([movie])})
+    proj = np.zeros((5, 2, 1, 24, 28))
+    zmap = np.zeros((5, 1, 1, 24, 28))
+    pipe = FramePipeline(operator=orc.time_point_surface_projection)           # host-logic seam, no GPU here
+    pipe.project_movie("m", 0, proj, zmap, reference_channel=0, airyscan=False, atoh_shift=0, min_z=0, max_z=0)
+    np.save(os.path.join(tmp, "proj%d.npy" % rank), proj)
+    np.save(os.path.join(tmp, "zmap%d.npy" % rank), zmap)
+    dist.destroy_process_group()
+
+
+def test_movie_partition_world_size_2_gloo(tmp_path):
+    """Two ranks each project their own time points (t % 2 == rank); assembling the arrays is the only
+    exchange.  The operator is the oracle here - this checks the host logic, not the kernels."""
+    import torch.multiprocessing as mp
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    movie = np.stack([synth.synth_stack(6, 24, 28, C=2, seed=3, t=t) for t in range(5)])
+    for rank in range(2):
+        proj = np.load(tmp_path / ("proj%d.npy" % rank))
+        zmap = np.load(tmp_path / ("zmap%d.npy" % rank))
+        for t in range(5):
+            want_p, want_z = orc.time_point_surface_projection(movie[t:t + 1], "TCZYX", 0, airyscan=False, z_map=True)
+            assert np.array_equal(proj[t, :, 0], want_p), (rank, t)
+            assert np.array_equal(zmap[t, 0, 0], want_z), (rank, t)

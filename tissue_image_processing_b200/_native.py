@@ -45,6 +45,8 @@ EXPORTS = {
     "tsp_get_frame_status": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(FrameStatus)]),
     "tsp_project_frame_host": (C.c_int, [C.c_void_p, C.POINTER(FrameDesc), C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.POINTER(FrameStatus)]),
+    "tsp_frame_submit": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(FrameDesc), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tsp_frame_wait": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(FrameStatus)]),
     "tsp_gaussian_blur_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                         C.c_int, C.POINTER(C.c_double), C.c_int, C.c_void_p]),
     "tsp_gaussian_blur_u16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
@@ -207,6 +209,31 @@ def project_frame_host(stack, reference_channel, min_z=0, max_z=0, airyscan=Fals
                                     C.c_void_p(zmap.ctypes.data), C.byref(st))
     check(rc, "tsp_project_frame_host")
     return proj, zmap, status_dict(st)
+
+
+MAX_SLOTS = 4
+
+
+def frame_submit(slot, stack, proj, zmap, reference_channel, min_z=0, max_z=0, airyscan=False, atoh_shift=0,
+                 mode="fast", device=None):
+    """Enqueue one frame on a slot (asynchronous).  stack (C,Z,Y,X) uint16, proj (C,Y,X) float64 and zmap (Y,X)
+    int64 are host arrays that must stay alive (and untouched) until frame_wait(slot)."""
+    lib = load_library()
+    assert stack.dtype == np.uint16 and stack.ndim == 4 and stack.flags.c_contiguous
+    Cn, Z, Y, X = stack.shape
+    assert proj.dtype == np.float64 and proj.shape == (Cn, Y, X) and proj.flags.c_contiguous
+    assert zmap.dtype == np.int64 and zmap.shape == (Y, X) and zmap.flags.c_contiguous
+    desc = make_desc(Cn, Z, Y, X, reference_channel, min_z, max_z, airyscan, atoh_shift, mode)
+    rc = lib.tsp_frame_submit(handle(device), int(slot), C.byref(desc), C.c_void_p(stack.ctypes.data),
+                              C.c_void_p(proj.ctypes.data), C.c_void_p(zmap.ctypes.data))
+    check(rc, "tsp_frame_submit")
+
+
+def frame_wait(slot, device=None):
+    st = FrameStatus()
+    rc = load_library().tsp_frame_wait(handle(device), int(slot), C.byref(st))
+    check(rc, "tsp_frame_wait")
+    return status_dict(st)
 
 
 # --------------------------------------------------------------------------------------------------

@@ -144,6 +144,12 @@ int tsp_destroy(tsp_handle* h) {
     }
     for (auto& kv : h->tables) cudaFree(kv.second);
     if (h->d_scratch) cudaFree(h->d_scratch);
+    for (auto& sl : h->slots) {
+        if (sl.stream) cudaStreamSynchronize(sl.stream);
+        if (sl.d_mem) cudaFree(sl.d_mem);
+        if (sl.h_status) cudaFreeHost(sl.h_status);
+        if (sl.stream) cudaStreamDestroy(sl.stream);
+    }
     if (h->h_status) cudaFreeHost(h->h_status);
     if (h->stream) cudaStreamDestroy(h->stream);
     for (cudaEvent_t ev : h->prof_events) cudaEventDestroy(ev);
@@ -300,10 +306,27 @@ static int ensure_scratch(tsp_handle* h, size_t bytes) {
     return TSP_OK;
 }
 
-int tsp_project_frame_host(tsp_handle* h, const tsp_frame_desc* desc, const uint16_t* h_stack, double* h_proj,
-                           int64_t* h_zmap, tsp_frame_status* status) {
-    if (!h || !desc || !h_stack || !h_proj || !h_zmap) {
-        set_error("null argument");
+static int ensure_slot(tsp_handle* h, int slot, size_t bytes) {
+    tsp_handle::Slot& sl = h->slots[slot];
+    if (!sl.stream) TSP_CUDA(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+    if (!sl.h_status) TSP_CUDA(cudaMallocHost((void**)&sl.h_status, kStatusWords * sizeof(int32_t)));
+    if (sl.bytes < bytes) {
+        if (sl.d_mem) {
+            TSP_CUDA(cudaStreamSynchronize(sl.stream));
+            TSP_CUDA(cudaFree(sl.d_mem));
+        }
+        sl.d_mem = nullptr;
+        sl.bytes = 0;
+        TSP_CUDA(cudaMalloc(&sl.d_mem, bytes));
+        sl.bytes = bytes;
+    }
+    return TSP_OK;
+}
+
+int tsp_frame_submit(tsp_handle* h, int slot, const tsp_frame_desc* desc, const uint16_t* h_stack, double* h_proj,
+                     int64_t* h_zmap) {
+    if (!h || !desc || !h_stack || !h_proj || !h_zmap || slot < 0 || slot >= TSP_MAX_SLOTS) {
+        set_error("bad argument to tsp_frame_submit");
         return TSP_ERR_INVALID;
     }
     Crop c;
@@ -311,6 +334,10 @@ int tsp_project_frame_host(tsp_handle* h, const tsp_frame_desc* desc, const uint
     if (rc) return rc;
     TSP_CUDA(cudaSetDevice(h->device));
     std::lock_guard<std::mutex> lock(h->host_mu);
+    if (h->slots[slot].busy) {
+        set_error("slot %d still has a frame in flight: call tsp_frame_wait first", slot);
+        return TSP_ERR_INVALID;
+    }
     const size_t plane = (size_t)desc->rows * desc->cols;
     const size_t nstack = (size_t)desc->channels * desc->planes * plane;
     const size_t nproj = (size_t)desc->channels * plane;
@@ -322,10 +349,11 @@ int tsp_project_frame_host(tsp_handle* h, const tsp_frame_desc* desc, const uint
     const size_t o_proj64 = off; off += align_up(nproj * sizeof(double), 256);
     const size_t o_zmap64 = off; off += align_up(plane * sizeof(int64_t), 256);
     const size_t o_ws = off;     off += ws;
-    rc = ensure_scratch(h, off);
+    rc = ensure_slot(h, slot, off);
     if (rc) return rc;
-    char* base = (char*)h->d_scratch;
-    cudaStream_t s = h->stream;
+    tsp_handle::Slot& sl = h->slots[slot];
+    char* base = (char*)sl.d_mem;
+    cudaStream_t s = sl.stream;
     TSP_CUDA(cudaMemcpyAsync(base + o_stack, h_stack, nstack * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
     rc = tsp_project_frame(h, desc, (const uint16_t*)(base + o_stack), (float*)(base + o_proj),
                            (int32_t*)(base + o_zmap), base + o_ws, ws, s);
@@ -333,18 +361,42 @@ int tsp_project_frame_host(tsp_handle* h, const tsp_frame_desc* desc, const uint
     rc = launch_widen_outputs(h, (const float*)(base + o_proj), (const int32_t*)(base + o_zmap),
                               (double*)(base + o_proj64), (int64_t*)(base + o_zmap64), nproj, plane, s);
     if (rc) return rc;
-    TSP_CUDA(cudaMemcpyAsync(h->h_status, base + o_ws, kStatusWords * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    TSP_CUDA(cudaMemcpyAsync(sl.h_status, base + o_ws, kStatusWords * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     TSP_CUDA(cudaMemcpyAsync(h_proj, base + o_proj64, nproj * sizeof(double), cudaMemcpyDeviceToHost, s));
     TSP_CUDA(cudaMemcpyAsync(h_zmap, base + o_zmap64, plane * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-    TSP_CUDA(cudaStreamSynchronize(s));
+    sl.busy = true;
+    return TSP_OK;
+}
+
+int tsp_frame_wait(tsp_handle* h, int slot, tsp_frame_status* status) {
+    if (!h || slot < 0 || slot >= TSP_MAX_SLOTS) return TSP_ERR_INVALID;
+    tsp_handle::Slot& sl = h->slots[slot];
+    if (!sl.busy) {
+        set_error("slot %d has no frame in flight", slot);
+        return TSP_ERR_INVALID;
+    }
+    TSP_CUDA(cudaSetDevice(h->device));
+    cudaError_t e = cudaStreamSynchronize(sl.stream);
+    sl.busy = false;
+    if (e != cudaSuccess) {
+        set_error("cudaStreamSynchronize failed: %s", cudaGetErrorString(e));
+        return TSP_ERR_CUDA;
+    }
     tsp_frame_status st;
-    fill_status(h->h_status, &st);
+    fill_status(sl.h_status, &st);
     if (status) *status = st;
     if (st.band_index_error) {
         set_error("height map indexes past the cropped stack (reference raises IndexError)");
         return TSP_ERR_BAND_INDEX;
     }
     return TSP_OK;
+}
+
+int tsp_project_frame_host(tsp_handle* h, const tsp_frame_desc* desc, const uint16_t* h_stack, double* h_proj,
+                           int64_t* h_zmap, tsp_frame_status* status) {
+    int rc = tsp_frame_submit(h, 0, desc, h_stack, h_proj, h_zmap);
+    if (rc) return rc;
+    return tsp_frame_wait(h, 0, status);
 }
 
 int tsp_gaussian_blur_f32(tsp_handle* h, const float* d_in, float* d_out, float* d_tmp, int planes, int rows,

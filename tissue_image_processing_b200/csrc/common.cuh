@@ -91,6 +91,16 @@ struct tsp_handle {
     void* d_scratch = nullptr;
     size_t d_scratch_bytes = 0;
     int32_t* h_status = nullptr;   // pinned copy of the status block
+    // host-buffer frame slots (tsp_frame_submit / tsp_frame_wait): own stream + device memory each, so
+    // the H2D copy of one frame overlaps the kernels of another and the D2H copy of a third
+    struct Slot {
+        cudaStream_t stream = nullptr;
+        void* d_mem = nullptr;
+        size_t bytes = 0;
+        int32_t* h_status = nullptr;
+        bool busy = false;
+    };
+    Slot slots[TSP_MAX_SLOTS];
     // per-device one-time setup done (constant memory, function attributes)
     bool fast_consts = false, band_consts = false, hist_attr = false;
     // optional per-stage timing (tsp_set_profiling): CUDA events recorded on the launching stream
