@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -102,7 +103,7 @@ struct tsp_handle {
     };
     Slot slots[TSP_MAX_SLOTS];
     // per-device one-time setup done (constant memory, function attributes)
-    bool fast_consts = false, band_consts = false, hist_attr = false;
+    bool fast_consts = false, band_consts = false, hist_attr = false, ring_attr = false;
     // optional per-stage timing (tsp_set_profiling): CUDA events recorded on the launching stream
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;       // marks of calls not yet folded into the totals
