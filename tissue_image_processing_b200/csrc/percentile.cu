@@ -79,10 +79,17 @@ hist16_kernel(const uint16_t* __restrict__ vol, size_t count, uint32_t* __restri
         for (int j = 0; j < kVecPerThread; ++j) {
             const size_t idx = base + (size_t)j * kHistThreads + threadIdx.x;
             if (idx < nvec) {
-                hist_add_word(sh, v[j].x);
-                hist_add_word(sh, v[j].y);
-                hist_add_word(sh, v[j].z);
-                hist_add_word(sh, v[j].w);
+                if (stride > 1) {
+                    // sample: neighbouring voxels are correlated, two of the eight (4 apart) carry most of the
+                    // information at a quarter of the shared-memory atomics (the bound of this kernel)
+                    hist_add(sh, v[j].x & 0xffffu);
+                    hist_add(sh, v[j].z & 0xffffu);
+                } else {
+                    hist_add_word(sh, v[j].x);
+                    hist_add_word(sh, v[j].y);
+                    hist_add_word(sh, v[j].z);
+                    hist_add_word(sh, v[j].w);
+                }
             }
         }
         __syncthreads();
@@ -265,7 +272,7 @@ window_select_kernel(const uint32_t* __restrict__ shist, int pedestal, int32_t* 
         return;
     }
     const double centre = 0.95 * (double)(ns - 1);
-    const double margin = 4.0 + 12.0 * sqrt((double)ns * 0.0475);
+    const double margin = 4.0 + 9.0 * sqrt((double)ns * 0.0475);
     const double lo_r = centre - margin, hi_r = centre + margin + 1.0;
     const unsigned long long r_lo = lo_r < 0.0 ? 0ull : (unsigned long long)lo_r;
     const unsigned long long r_hi = hi_r > (double)(ns - 1) ? ns - 1 : (unsigned long long)hi_r;
@@ -284,11 +291,34 @@ window_select_kernel(const uint32_t* __restrict__ shist, int pedestal, int32_t* 
 }
 
 // ---- step 2: streaming count pass -----------------------------------------------------------------
+// One pass over the volume that only counts.  The integer pipe of an SMSP issues one warp instruction every
+// two cycles, so compare/shift/add per voxel cannot keep up with HBM; the counting is done on the FP32 pipe
+// instead.  PRMT turns a uint16 into the float 2^23 + v (exact), a saturating add against a threshold is the
+// flag [v >= t] as 0.0 or 1.0, and packed FADD2 adds the flags of two voxels at a time:
+//     nz  = #[v >= pedestal + 1]        a = #[v >= lo]        b = #[v >= lo + wn]
+// A 16-byte vector holds a voxel of the value window [lo, lo + wn) exactly when its a and b counts differ;
+// those rare vectors are parked in a shared queue and histogrammed after the stream.
 constexpr int kCountThreads = 512;
 constexpr int kCountUnroll = 4;
 constexpr int kQueueCap = 1536;              // parked 16-byte vectors per CTA (24 KB)
 
-__global__ void __launch_bounds__(kCountThreads)
+__device__ __forceinline__ float sat_add(float a, float b) {
+    float r;
+    asm("add.sat.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ float biased_lo(uint32_t w, uint32_t magic) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, 0x7410;" : "=r"(r) : "r"(w), "r"(magic));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ float biased_hi(uint32_t w, uint32_t magic) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, 0x7432;" : "=r"(r) : "r"(w), "r"(magic));
+    return __uint_as_float(r);
+}
+
+__global__ void __launch_bounds__(kCountThreads, 2)
 window_count_kernel(const uint16_t* __restrict__ vol, size_t count, int pedestal, int32_t* __restrict__ status,
                     uint32_t* __restrict__ gwin, unsigned long long* __restrict__ gcounters) {
     if (status[ST_WIN_OK] == 0) return;
@@ -303,13 +333,11 @@ window_count_kernel(const uint16_t* __restrict__ vol, size_t count, int pedestal
     if (threadIdx.x == 0) qtail = 0;
     __syncthreads();
 
-    // per-thread counts by sign bits: (v - lo) >> 31 is 1 when v < lo; (v - ped - 1) >> 31 is 1 when v <= ped
-    uint32_t below = 0, zeros = 0, seen = 0;
-    const uint32_t ped1 = ped + 1, wn1 = wn - 1;
+    unsigned long long nz_total = 0, below_total = 0;      // per-thread integer totals (scalar path + flushes)
     auto one = [&](uint32_t v) {
+        if (v > ped) ++nz_total;
+        if (v < lo) ++below_total;
         const uint32_t d = v - lo;
-        below += d >> 31;
-        zeros += (v - ped1) >> 31;
         if (d < wn) atomicAdd(&win[d], 1u);
     };
     const uintptr_t addr = reinterpret_cast<uintptr_t>(vol);
@@ -319,54 +347,76 @@ window_count_kernel(const uint16_t* __restrict__ vol, size_t count, int pedestal
     const size_t tail0 = head + nvec * 8;
     const uint4* body = reinterpret_cast<const uint4*>(vol + head);
     if (blockIdx.x == 0) {
-        for (size_t i = threadIdx.x; i < head; i += kCountThreads) { one(vol[i]); ++seen; }
-        for (size_t i = tail0 + threadIdx.x; i < count; i += kCountThreads) { one(vol[i]); ++seen; }
+        for (size_t i = threadIdx.x; i < head; i += kCountThreads) one(vol[i]);
+        for (size_t i = tail0 + threadIdx.x; i < count; i += kCountThreads) one(vol[i]);
     }
-    const size_t step = (size_t)gridDim.x * kCountThreads;
-    for (size_t i0 = (size_t)blockIdx.x * kCountThreads + threadIdx.x; i0 < nvec; i0 += step * kCountUnroll) {
-        uint4 v[kCountUnroll];
+
+    // thresholds in the biased domain: sat(f + c) with c = -(2^23 + t - 1) is [v >= t]; all values are exact
+    const float c_nz = -(8388608.0f + (float)ped);                 // t = ped + 1
+    const float c_a = -(8388608.0f + (float)lo - 1.0f);            // t = lo          (lo >= ped + 1 >= 1)
+    const float c_b = -(8388608.0f + (float)(lo + wn) - 1.0f);     // t = lo + wn
+    uint32_t magic = 0x4B000000u;
+    asm volatile("" : "+r"(magic));
+    float2 acc_nz = make_float2(0.f, 0.f), acc_a = acc_nz, acc_b = acc_nz;
+    uint32_t seen_vec = 0, rounds = 0;
+    auto flush = [&]() {
+        nz_total += (unsigned long long)(acc_nz.x + acc_nz.y);
+        below_total += (unsigned long long)seen_vec * 8ull - (unsigned long long)(acc_a.x + acc_a.y);
+        acc_nz = acc_a = acc_b = make_float2(0.f, 0.f);
+        seen_vec = 0;
+    };
+    const float2 zero2 = make_float2(0.f, 0.f);
+    auto park = [&](const uint4& vec) {      // rare: the vector goes to the CTA queue, histogrammed after the stream
+        const uint32_t slot = atomicAdd(&qtail, 1u);
+        if (slot < kQueueCap) {
+            queue[slot] = vec;
+        } else {
+            const uint32_t ws[4] = {vec.x, vec.y, vec.z, vec.w};
 #pragma unroll
-        for (int j = 0; j < kCountUnroll; ++j) {
-            const size_t i = i0 + (size_t)j * step;
-            v[j] = i < nvec ? __ldg(body + i) : make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-        }
-#pragma unroll
-        for (int j = 0; j < kCountUnroll; ++j) {
-            const size_t i = i0 + (size_t)j * step;
-            if (i < nvec) {
-                const uint32_t ws[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
-                // branch-free per voxel; "inside the window" (d < wn unsigned) is the sign bit of
-                // d | (wn-1-d) being clear, AND-reduced over the 8 voxels so the rare case branches once
-                uint32_t allout = 0x80000000u;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-#pragma unroll
-                    for (int hlf = 0; hlf < 2; ++hlf) {
-                        const uint32_t val = hlf ? (ws[q] >> 16) : (ws[q] & 0xffffu);
-                        const uint32_t d = val - lo;
-                        below += d >> 31;
-                        zeros += (val - ped1) >> 31;
-                        allout &= d | (wn1 - d);
-                    }
-                }
-                if (!(allout >> 31)) {
-                    // rare: park the whole vector in the CTA queue; it is histogrammed after the stream
-                    const uint32_t slot = atomicAdd(&qtail, 1u);
-                    if (slot < kQueueCap) {
-                        queue[slot] = v[j];
-                    } else {
-#pragma unroll 1
-                        for (int q = 0; q < 8; ++q) {
-                            const uint32_t val = (q & 1) ? (ws[q >> 1] >> 16) : (ws[q >> 1] & 0xffffu);
-                            const uint32_t d = val - lo;
-                            if (d < wn) atomicAdd(&win[d], 1u);
-                        }
-                    }
-                }
-                seen += 8;
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t d0 = (ws[q] & 0xffffu) - lo, d1 = (ws[q] >> 16) - lo;
+                if (d0 < wn) atomicAdd(&win[d0], 1u);
+                if (d1 < wn) atomicAdd(&win[d1], 1u);
             }
         }
+    };
+    // chunk c = vectors [c * T * U, (c + 1) * T * U): thread t takes c * T * U + j * T + t, j < U (no bounds checks)
+    constexpr size_t kChunkVec = (size_t)kCountThreads * kCountUnroll;
+    float2 inwin_prev = make_float2(0.f, 0.f);      // running a - b per half (exact small integers)
+    const size_t nfull = nvec / kChunkVec;
+    for (size_t chunk = blockIdx.x; chunk < nfull; chunk += gridDim.x) {
+        const uint4* src = body + chunk * kChunkVec + threadIdx.x;
+        uint4 v[kCountUnroll];
+#pragma unroll
+        for (int j = 0; j < kCountUnroll; ++j) v[j] = __ldg(src + j * kCountThreads);
+#pragma unroll
+        for (int j = 0; j < kCountUnroll; ++j) {
+            const uint32_t ws[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float f0 = biased_lo(ws[q], magic), f1 = biased_hi(ws[q], magic);
+                acc_nz = __fadd2_rn(acc_nz, make_float2(sat_add(f0, c_nz), sat_add(f1, c_nz)));
+                acc_a = __fadd2_rn(acc_a, make_float2(sat_add(f0, c_a), sat_add(f1, c_a)));
+                acc_b = __fadd2_rn(acc_b, make_float2(sat_add(f0, c_b), sat_add(f1, c_b)));
+            }
+            // a >= b voxel by voxel: the vector touches the window iff a and b advanced differently
+            const float2 inwin = __fadd2_rn(acc_a, make_float2(-acc_b.x, -acc_b.y));
+            if (inwin.x != inwin_prev.x || inwin.y != inwin_prev.y) park(v[j]);
+            inwin_prev = inwin;
+        }
+        seen_vec += kCountUnroll;
+        if (++rounds == 32768u) {          // keep the float counters far below 2^24
+            flush();
+            inwin_prev = zero2;
+            rounds = 0;
+        }
     }
+    if (blockIdx.x == 0) {                 // the vectors after the last full chunk, voxel by voxel
+        const uint16_t* rest = reinterpret_cast<const uint16_t*>(body + nfull * kChunkVec);
+        const size_t nrest = (nvec - nfull * kChunkVec) * 8;
+        for (size_t i = threadIdx.x; i < nrest; i += kCountThreads) one(rest[i]);
+    }
+    flush();
     __syncthreads();
     {   // drain the queue: one parked vector per thread per round, every lane busy
         const uint32_t nq = min(qtail, (uint32_t)kQueueCap);
@@ -381,14 +431,14 @@ window_count_kernel(const uint16_t* __restrict__ vol, size_t count, int pedestal
             }
         }
     }
-    uint32_t nz = seen - zeros;
+    unsigned long long nz = nz_total, below = below_total;
     for (int o = 16; o; o >>= 1) {
         nz += __shfl_xor_sync(0xffffffffu, nz, o);
         below += __shfl_xor_sync(0xffffffffu, below, o);
     }
     if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&blk[0], (unsigned long long)nz);
-        atomicAdd(&blk[1], (unsigned long long)below);
+        atomicAdd(&blk[0], nz);
+        atomicAdd(&blk[1], below);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -467,7 +517,7 @@ int launch_percentile(tsp_handle* h, const uint16_t* d_vol, size_t count, int pe
     TSP_LAUNCH_CHECK(h);
     window_select_kernel<<<1, 1024, 0, s>>>(hist_a, pedestal, d_status);
     TSP_LAUNCH_CHECK(h);
-    window_count_kernel<<<h->sm_count * 4, kCountThreads, 0, s>>>(d_vol, count, pedestal, d_status, win, counters);
+    window_count_kernel<<<h->sm_count * 2, kCountThreads, 0, s>>>(d_vol, count, pedestal, d_status, win, counters);
     TSP_LAUNCH_CHECK(h);
     window_finalize_kernel<<<1, 1024, 0, s>>>(win, counters, (unsigned long long)count, pedestal, d_status);
     TSP_LAUNCH_CHECK(h);
