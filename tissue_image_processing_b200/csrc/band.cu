@@ -331,6 +331,301 @@ __global__ void __launch_bounds__(kBandThreads, 2) band_project_kernel(const Ban
     }
 }
 
+// ---- K5-K7 fused, second generation -------------------------------------------------------------
+// Same tile walk as band_project_kernel, with the per-plane work cut to what the data need:
+//   * the indicator [cz == t] of a tile row is an 80-bit mask (three warp ballots); the 17-tap x blur of a
+//     binary line is a table lookup: window bits 0..8 and 9..16 index two shared tables of partial tap sums
+//     (2 LDS + 1 FADD per pixel instead of 17 FMA and 17 compares); all-zero / all-one windows are free;
+//   * per-plane shared buffers are double buffered: ONE block barrier per present plane;
+//   * a 48-bit column mask per pixel group says which rows of the x-blurred plane are non-zero: warps whose
+//     17-row windows see nothing skip the y pass of that plane altogether;
+//   * y pass, z scatter and the weighted max use packed FFMA2 / FMUL2 (two pixels per instruction).
+constexpr int kB2Threads = 256;
+constexpr int kB2CW = kBandTX + 2 * kBandHalo;      // 80
+constexpr int kB2CH = kBandTY + 2 * kBandHalo;      // 48
+
+__constant__ float2 c_w2p[17];    // (w, w) pairs of the sigma = 2 taps
+__constant__ float2 c_w1p[9];     // (w, w) pairs of the sigma = 1 taps
+
+__device__ __forceinline__ float band_u16f_lo(uint32_t w, uint32_t magic) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, 0x7410;" : "=r"(r) : "r"(w), "r"(magic));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ float band_u16f_hi(uint32_t w, uint32_t magic) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, 0x7432;" : "=r"(r) : "r"(w), "r"(magic));
+    return __uint_as_float(r);
+}
+
+template <bool AIRY, bool TWO>
+__global__ void __launch_bounds__(kB2Threads, 2) band_project2_kernel(const BandArgs a) {
+    __shared__ __align__(16) int cz_s[kB2CH][kB2CW];
+    __shared__ __align__(16) uint32_t rowmask[2][kB2CH][4];
+    __shared__ __align__(16) float r_s[2][kB2CH][kBandTX];       // row layout: [half][group][4]
+    __shared__ unsigned long long colbits[3][8];
+    __shared__ float lut_lo[512], lut_hi[256];
+    __shared__ uint32_t present[kBandMaxPlanes / 32];
+    __shared__ int zlo_s, zhi_s;
+
+    if (a.status[ST_BAND_ERR]) return;          // the reference raises before projecting
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int x0 = blockIdx.x * kBandTX, y0 = blockIdx.y * kBandTY;
+    if (tid == 0) {
+        zlo_s = INT32_MAX;
+        zhi_s = INT32_MIN;
+    }
+    for (int i = tid; i < (a.Z >> 5) + 1 && i < kBandMaxPlanes / 32; i += kB2Threads) present[i] = 0;
+    for (int i = tid; i < 512; i += kB2Threads) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) s += ((i >> k) & 1) ? c_w2[k] : 0.f;
+        lut_lo[i] = s;
+    }
+    {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += ((tid >> k) & 1) ? c_w2[9 + k] : 0.f;
+        lut_hi[tid] = s;
+    }
+    if (tid < 24) colbits[tid >> 3][tid & 7] = 0ull;
+    __syncthreads();
+    {
+        constexpr int kPer = (kB2CH * kB2CW + kB2Threads - 1) / kB2Threads;
+        int vals[kPer];
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            const int i = tid + k * kB2Threads;
+            const int yy = min(max(y0 - kBandHalo + i / kB2CW, 0), a.Y - 1);
+            const int xx = min(max(x0 - kBandHalo + i % kB2CW, 0), a.X - 1);
+            vals[k] = i < kB2CH * kB2CW ? __ldg(a.zmap + (size_t)yy * a.X + xx) : 0;
+        }
+        int lo = INT32_MAX, hi = INT32_MIN;
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            const int i = tid + k * kB2Threads;
+            if (i < kB2CH * kB2CW) {
+                int v = vals[k];
+                if (a.shift != 0) v = min(max(v + a.shift, 0), a.Z);
+                cz_s[i / kB2CW][i % kB2CW] = v;
+                lo = min(lo, v);
+                hi = max(hi, v);
+                atomicOr(&present[v >> 5], 1u << (v & 31));
+            }
+        }
+        for (int o = 16; o; o >>= 1) {
+            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        if (lane == 0) {
+            atomicMin(&zlo_s, lo);
+            atomicMax(&zhi_s, hi);
+        }
+    }
+    __syncthreads();
+    const int zlo = zlo_s, zhi = zhi_s;
+    const float one_val = lut_lo[511] + lut_hi[255];
+
+    const int g = tid & 7, row = tid >> 3;                     // 8 pixels x0+8g .. +7 of row y0+row
+    const int x = x0 + g * kBandPix, y = y0 + row;
+    const bool inside = y < a.Y && x < a.X;
+    const int c0 = blockIdx.z * kBandMaxCh;
+    const size_t plane = (size_t)a.Y * a.X;
+    const uint16_t* src0 = a.stack + (size_t)a.ch[c0] * a.channel_stride + a.z0_offset + (size_t)y * a.X + x;
+    const uint16_t* src1 = a.stack + (size_t)a.ch[c0 + (TWO ? 1 : 0)] * a.channel_stride + a.z0_offset +
+                           (size_t)y * a.X + x;
+    const float nb = -((float)a.pedestal + 8388608.0f);
+    const float2 nbias = make_float2(nb, nb);
+    uint32_t magic = 0x4B000000u;
+    asm volatile("" : "+r"(magic));
+
+    // ballots of plane t into rowmask[buf] (+ the zeroed column mask of that plane)
+    auto build_masks = [&](int t, int buf, int cb) {
+#pragma unroll
+        for (int rr = 0; rr < kB2CH / 8; ++rr) {
+            const int r = warp + 8 * rr;
+            uint32_t mine = 0;
+#pragma unroll
+            for (int seg = 0; seg < 3; ++seg) {
+                const int col = 32 * seg + lane;
+                const int v = col < kB2CW ? cz_s[r][col] : -1;
+                const uint32_t b = __ballot_sync(0xffffffffu, v == t);
+                if (lane == seg) mine = b;
+            }
+            if (lane < 4) rowmask[buf][r][lane] = mine;          // word 3 = 0
+        }
+        if (tid < 8) colbits[cb][tid] = 0ull;
+    };
+    auto next_present = [&](int t) {                             // smallest present plane > t, or INT_MAX
+        for (int q = t + 1; q <= zhi; ++q)
+            if ((present[q >> 5] >> (q & 31)) & 1u) return q;
+        return INT32_MAX;
+    };
+    // x pass of the plane whose masks are in rowmask[buf]: r_s[buf] and colbits[cb]
+    auto x_pass = [&](int buf, int cb) {
+#pragma unroll
+        for (int round = 0; round < 2; ++round) {
+            const int r = round * 32 + row;
+            if (round == 1 && r >= kB2CH) break;                 // warp-uniform (warps 0..3 take the second round)
+            const uint4 m = *reinterpret_cast<const uint4*>(&rowmask[buf][r][0]);
+            const uint32_t wlo = g < 4 ? m.x : m.y, whi = g < 4 ? m.y : m.z;
+            const uint32_t W = __funnelshift_r(wlo, whi, 8 * (g & 3)) & 0xFFFFFFu;
+            float o[8];
+            if (W == 0u) {
+#pragma unroll
+                for (int p = 0; p < 8; ++p) o[p] = 0.f;
+            } else if (W == 0xFFFFFFu) {
+#pragma unroll
+                for (int p = 0; p < 8; ++p) o[p] = one_val;
+            } else {
+#pragma unroll
+                for (int p = 0; p < 8; ++p) o[p] = lut_lo[(W >> p) & 511u] + lut_hi[(W >> (p + 9)) & 255u];
+            }
+            float4* dst = reinterpret_cast<float4*>(&r_s[buf][r][0]);
+            dst[g] = make_float4(o[0], o[1], o[2], o[3]);
+            dst[8 + g] = make_float4(o[4], o[5], o[6], o[7]);
+            const uint32_t B = __ballot_sync(0xffffffffu, W != 0u);          // bit 8*rr + g, rows 4*warp + rr
+            if (lane < 8) {
+                const uint32_t nib = ((B >> lane) & 1u) | (((B >> (lane + 8)) & 1u) << 1) |
+                                     (((B >> (lane + 16)) & 1u) << 2) | (((B >> (lane + 24)) & 1u) << 3);
+                if (nib) atomicOr(&colbits[cb][lane], (unsigned long long)nib << (round * 32 + 4 * warp));
+            }
+        }
+    };
+
+    float2 win[4][11];            // pending masks of planes t-4 .. t+4(+2), two pixels per entry
+    float2 best0[4], best1[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int i = 0; i < 11; ++i) win[q][i] = make_float2(0.f, 0.f);
+        best0[q] = best1[q] = make_float2(0.f, 0.f);
+    }
+    int live = 0;
+
+    uint4 nxt0 = make_uint4(0, 0, 0, 0), nxt1 = nxt0;
+    {
+        const int z = zlo - 4;
+        if (inside && z >= 0 && z < a.Z) {
+            nxt0 = band_load8(src0 + (size_t)z * plane, x, a.X, a.vec != 0);
+            if (TWO) nxt1 = band_load8(src1 + (size_t)z * plane, x, a.X, a.vec != 0);
+        }
+    }
+
+    int buf = 0, cb = 0;
+    build_masks(zlo, 0, 0);                      // zlo is always present
+    __syncthreads();
+
+    for (int tb = zlo; tb <= zhi + 8; tb += 3) {
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int t = tb + u;
+            if (t > zhi + 8) break;                                    // block-uniform
+            const uint4 cur0 = nxt0, cur1 = nxt1;
+            {   // prefetch the voxels of the next output plane while this one is processed
+                const int zn = t - 3;
+                if (inside && zn >= 0 && zn < a.Z && t + 1 <= zhi + 8) {
+                    nxt0 = band_load8(src0 + (size_t)zn * plane, x, a.X, a.vec != 0);
+                    if (TWO) nxt1 = band_load8(src1 + (size_t)zn * plane, x, a.X, a.vec != 0);
+                }
+            }
+            const bool have = t <= zhi && ((present[t >> 5] >> (t & 31)) & 1u);
+            if (have) {                                                // block-uniform
+                x_pass(buf, cb);
+                const int tn = next_present(t);
+                const int cbn = cb == 2 ? 0 : cb + 1;
+                if (tn != INT32_MAX) build_masks(tn, buf ^ 1, cbn);
+                __syncthreads();
+                // y pass: a_new = sum_dy w2[dy] * r_s[row + dy][8g ..], skipped by warps that see only zeros
+                const bool mine = ((colbits[cb][g] >> row) & 0x1FFFFull) != 0ull;
+                if (__any_sync(0xffffffffu, mine)) {
+                    float2 an[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) an[q] = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int dy = 0; dy < 17; ++dy) {
+                        const float4* src = reinterpret_cast<const float4*>(&r_s[buf][row + dy][0]);
+                        const float4 lo4 = src[g], hi4 = src[8 + g];
+                        const float2 w = c_w2p[dy];
+                        an[0] = __ffma2_rn(make_float2(lo4.x, lo4.y), w, an[0]);
+                        an[1] = __ffma2_rn(make_float2(lo4.z, lo4.w), w, an[1]);
+                        an[2] = __ffma2_rn(make_float2(hi4.x, hi4.y), w, an[2]);
+                        an[3] = __ffma2_rn(make_float2(hi4.z, hi4.w), w, an[3]);
+                    }
+                    if (mine) {
+                        live = 9;
+                        // plane t feeds the masks of z = t-4+k (window slot u+k) with the (z, t) entry of the
+                        // edge-replicating z matrix: interior rows are the plain sigma=1 taps
+                        const bool edge = t - 4 < 4 || t + 4 > a.Z - 5;
+#pragma unroll
+                        for (int k = 0; k < 9; ++k) {
+                            const int z = t - 4 + k;
+                            float2 w = c_w1p[8 - k];
+                            if (edge) {
+                                const float we = (z >= 0 && z < a.Z) ? __ldg(a.wz + z * 9 + (8 - k)) : 0.f;
+                                w = make_float2(we, we);
+                            }
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) win[q][u + k] = __ffma2_rn(w, an[q], win[q][u + k]);
+                        }
+                    }
+                }
+                buf ^= 1;
+                cb = cbn;
+            }
+            const int z = t - 4;
+            if (live > 0 && inside && z >= 0 && z < a.Z) {
+                const uint32_t w0[4] = {cur0.x, cur0.y, cur0.z, cur0.w};
+                const uint32_t w1[4] = {cur1.x, cur1.y, cur1.z, cur1.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float2 m = win[q][u];
+                    float2 f = __fadd2_rn(make_float2(band_u16f_lo(w0[q], magic), band_u16f_hi(w0[q], magic)), nbias);
+                    if (AIRY) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); }
+                    const float2 pr = __fmul2_rn(f, m);
+                    best0[q].x = fmaxf(best0[q].x, pr.x);
+                    best0[q].y = fmaxf(best0[q].y, pr.y);
+                    if (TWO) {
+                        float2 f1 = __fadd2_rn(make_float2(band_u16f_lo(w1[q], magic), band_u16f_hi(w1[q], magic)), nbias);
+                        if (AIRY) { f1.x = fmaxf(f1.x, 0.f); f1.y = fmaxf(f1.y, 0.f); }
+                        const float2 pr1 = __fmul2_rn(f1, m);
+                        best1[q].x = fmaxf(best1[q].x, pr1.x);
+                        best1[q].y = fmaxf(best1[q].y, pr1.y);
+                    }
+                }
+            }
+            live -= live > 0;
+        }
+        // slide the window by 3 planes
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) win[q][i] = win[q][i + 3];
+            win[q][8] = win[q][9] = win[q][10] = make_float2(0.f, 0.f);
+        }
+    }
+    if (inside) {
+        float* dst = a.proj + ((size_t)a.ch[c0] * a.Y + y) * a.X + x;
+        const float b0[8] = {best0[0].x, best0[0].y, best0[1].x, best0[1].y, best0[2].x, best0[2].y, best0[3].x, best0[3].y};
+        if (x + 7 < a.X && (a.X & 3) == 0) {
+            reinterpret_cast<float4*>(dst)[0] = make_float4(b0[0], b0[1], b0[2], b0[3]);
+            reinterpret_cast<float4*>(dst)[1] = make_float4(b0[4], b0[5], b0[6], b0[7]);
+        } else {
+#pragma unroll
+            for (int p = 0; p < kBandPix; ++p)
+                if (x + p < a.X) dst[p] = b0[p];
+        }
+        if (TWO) {
+            float* dst1 = a.proj + ((size_t)a.ch[c0 + 1] * a.Y + y) * a.X + x;
+            const float b1[8] = {best1[0].x, best1[0].y, best1[1].x, best1[1].y, best1[2].x, best1[2].y, best1[3].x, best1[3].y};
+#pragma unroll
+            for (int p = 0; p < kBandPix; ++p)
+                if (x + p < a.X) dst1[p] = b1[p];
+        }
+    }
+}
+
 static int get_wz_table(tsp_handle* h, int Z, const float** out) {
     char key[32];
     snprintf(key, sizeof key, "wz%d", Z);
@@ -344,6 +639,11 @@ static int get_wz_table(tsp_handle* h, int Z, const float** out) {
         float w1f[9];
         for (int i = 0; i < 9; ++i) w1f[i] = (float)w1[i];
         TSP_CUDA(cudaMemcpyToSymbol(c_w1, w1f, sizeof w1f));
+        float2 w2p[17], w1p[9];
+        for (int i = 0; i < 17; ++i) w2p[i] = make_float2(w2f[i], w2f[i]);
+        for (int i = 0; i < 9; ++i) w1p[i] = make_float2(w1f[i], w1f[i]);
+        TSP_CUDA(cudaMemcpyToSymbol(c_w2p, w2p, sizeof w2p));
+        TSP_CUDA(cudaMemcpyToSymbol(c_w1p, w1p, sizeof w1p));
         h->band_consts = true;
     }
     auto it = h->tables.find(key);
@@ -389,6 +689,30 @@ static int launch_band_range(tsp_handle* h, const int32_t* d_zmap, int Z, int Y,
     return TSP_OK;
 }
 
+// channels are projected two per CTA; an odd channel count ends with a one-channel launch
+static void launch_band_variant(BandArgs a, dim3 grid, int pedestal, cudaStream_t s) {
+    if (getenv("TSP_BAND_V1")) {
+        band_project_kernel<<<grid, kBandThreads, 0, s>>>(a);
+        return;
+    }
+    const int pairs = a.nch / 2;
+    if (pairs > 0) {
+        BandArgs b = a;
+        b.nch = 2 * pairs;
+        dim3 g2(grid.x, grid.y, pairs);
+        if (pedestal) band_project2_kernel<true, true><<<g2, kB2Threads, 0, s>>>(b);
+        else band_project2_kernel<false, true><<<g2, kB2Threads, 0, s>>>(b);
+    }
+    if (a.nch & 1) {
+        BandArgs b = a;
+        b.ch[0] = a.ch[a.nch - 1];
+        b.nch = 1;
+        dim3 g1(grid.x, grid.y, 1);
+        if (pedestal) band_project2_kernel<true, false><<<g1, kB2Threads, 0, s>>>(b);
+        else band_project2_kernel<false, false><<<g1, kB2Threads, 0, s>>>(b);
+    }
+}
+
 int launch_band_project_ex(tsp_handle* h, const uint16_t* d_stack, size_t channel_stride, size_t z0_offset,
                            const int32_t* d_zmap, float* d_proj, int C, int Z, int Y, int X, int ref_c,
                            int shift, int pedestal, int32_t* d_status, bool range_known, cudaStream_t s) {
@@ -425,7 +749,7 @@ int launch_band_project_ex(tsp_handle* h, const uint16_t* d_stack, size_t channe
     for (int c = 0; c < C; ++c)
         if (shift == 0 || c == ref_c) a.ch[a.nch++] = c;
     grid.z = (a.nch + kBandMaxCh - 1) / kBandMaxCh;
-    band_project_kernel<<<grid, kBandThreads, 0, s>>>(a);
+    launch_band_variant(a, grid, pedestal, s);
     TSP_LAUNCH_CHECK(h);
     if (shift != 0 && C > 1) {
         a.shift = shift;
@@ -433,7 +757,7 @@ int launch_band_project_ex(tsp_handle* h, const uint16_t* d_stack, size_t channe
         for (int c = 0; c < C; ++c)
             if (c != ref_c) a.ch[a.nch++] = c;
         grid.z = (a.nch + kBandMaxCh - 1) / kBandMaxCh;
-        band_project_kernel<<<grid, kBandThreads, 0, s>>>(a);
+        launch_band_variant(a, grid, pedestal, s);
         TSP_LAUNCH_CHECK(h);
     }
     return TSP_OK;
