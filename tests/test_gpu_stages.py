@@ -120,6 +120,32 @@ def test_band_projection_from_oracle_height_map(nat, shift, ref):
     np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-5, atol=0)
 
 
+@pytest.mark.parametrize("shape,C,shift,noisy", [((40, 96, 128), 1, 0, True), ((37, 70, 200), 2, 0, True),
+                                                 ((21, 64, 64), 3, 2, False), ((30, 33, 72), 2, -2, True)])
+def test_band_projection_tma_ring(nat, shape, C, shift, noisy, monkeypatch):
+    """TMA path of the band stage (X % 8 == 0, tile inside the image): plane ranges deeper than the ring (a noisy
+    height map walks every plane, refilling the ring), one / two / three channels, shifted masks; against the
+    oracle and bit for bit against the register-prefetch kernel (TSP_BAND_V2=1), which does the same arithmetic."""
+    Z, Y, X = shape
+    img = synth.synth_stack(Z, Y, X, C=C, seed=sum(shape))
+    if img.ndim == 3:
+        img = img[None]
+    rng = np.random.default_rng(7)
+    hi = Z - 1 - max(shift, 0)
+    if noisy:
+        zmap = rng.integers(0, hi + 1, size=(Y, X)).astype(np.int64)
+    else:
+        zmap = np.clip(synth.height_field(Z, Y, X).astype(np.int64), 0, hi)
+    image = img.astype(np.float32)
+    z_other = zmap if shift == 0 else np.clip(zmap + shift, 0, Z)
+    want = orc.project_channels(image, 0, orc.band_mask(zmap, Z), orc.band_mask(z_other, Z))
+    got = nat.band_project(_cuda(img), _cuda(zmap.astype(np.int32)), reference_channel=0, atoh_shift=shift).cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=0)
+    monkeypatch.setenv("TSP_BAND_V2", "1")
+    alt = nat.band_project(_cuda(img), _cuda(zmap.astype(np.int32)), reference_channel=0, atoh_shift=shift).cpu().numpy()
+    assert np.array_equal(got, alt)
+
+
 def test_band_projection_index_error(nat):
     img = synth.synth_stack(6, 20, 20, seed=1)
     zmap = np.full((20, 20), 6, dtype=np.int32)

@@ -28,6 +28,24 @@ void prof_mark(tsp_handle* h, cudaStream_t s, int stage) {
     h->prof_stage.push_back(stage);
 }
 
+int get_tensor_map_encoder(EncodeTiledFn* out) {
+    static EncodeTiledFn encode = nullptr;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        TSP_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || !fn) {
+            set_error("cuTensorMapEncodeTiled is not available from this driver");
+            return TSP_ERR_CUDA;
+        }
+        encode = (EncodeTiledFn)fn;
+    }
+    *out = encode;
+    return TSP_OK;
+}
+
 static const char* kStageNames[STG_COUNT] = {"percentile", "decimate", "coarse", "interp_argmax", "prepare",
                                              "blur_pre", "blur_score", "argmax", "band", "widen"};
 

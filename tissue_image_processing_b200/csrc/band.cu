@@ -626,6 +626,315 @@ __global__ void __launch_bounds__(kB2Threads, 2) band_project2_kernel(const Band
     }
 }
 
+// ---- K5-K7 fused, third generation: the voxels arrive by TMA ---------------------------------------
+// band_project2_kernel keeps one plane (16 bytes per thread) of raw voxels in flight, so every plane of the walk
+// costs a full HBM round trip: the kernel is latency bound (ncu: ~20 us per CTA for ~11 us of issue work in the
+// whole grid).  Here the mask arithmetic is unchanged, but as soon as the tile's plane range [zlo-4, zhi+4] is
+// known the CTA asks the TMA unit for every plane of it at once: one 64 x 32 x 1 (x 1 channel) box per plane
+// (cp.async.bulk.tensor.4d over the (X, Y, Z, C) map of the cropped stack), each completing on the mbarrier of
+// its ring stage.  The loads overlap the mask building; the weighted max reads the voxels from shared memory.
+// Ranges deeper than the ring are refilled half a ring at a time behind a block barrier.  Rows / columns past
+// the image edge arrive as zeros (they are never stored).
+constexpr int kB3PlaneBytes = kBandTY * kBandTX * 2;          // 4096: one channel of one plane of the tile
+
+template <bool AIRY, bool TWO>
+__global__ void __launch_bounds__(kB2Threads, 2) band_project3_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                      const BandArgs a) {
+    constexpr int NST = TWO ? 8 : 16;                             // ring stages (planes in flight)
+    constexpr int HALF = NST / 2;
+    constexpr int STAGE = (TWO ? 2 : 1) * kB3PlaneBytes;
+    extern __shared__ __align__(128) unsigned char b3_ring[];     // [NST][STAGE] + NST mbarriers
+    __shared__ __align__(16) int cz_s[kB2CH][kB2CW];
+    __shared__ __align__(16) uint32_t rowmask[2][kB2CH][4];
+    __shared__ __align__(16) float r_s[2][kB2CH][kBandTX];       // row layout: [half][group][4]
+    __shared__ unsigned long long colbits[3][8];
+    __shared__ float lut_lo[512], lut_hi[256];
+    __shared__ uint32_t present[kBandMaxPlanes / 32];
+    __shared__ int zlo_s, zhi_s;
+
+    if (a.status[ST_BAND_ERR]) return;          // the reference raises before projecting
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int x0 = blockIdx.x * kBandTX, y0 = blockIdx.y * kBandTY;
+    const uint32_t ring_s = smem_u32(b3_ring);
+    const uint32_t bar_s = ring_s + NST * STAGE;
+    if (tid == 0) {
+        zlo_s = INT32_MAX;
+        zhi_s = INT32_MIN;
+#pragma unroll
+        for (int s = 0; s < NST; ++s) mbar_init(bar_s + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    for (int i = tid; i < (a.Z >> 5) + 1 && i < kBandMaxPlanes / 32; i += kB2Threads) present[i] = 0;
+    for (int i = tid; i < 512; i += kB2Threads) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) s += ((i >> k) & 1) ? c_w2[k] : 0.f;
+        lut_lo[i] = s;
+    }
+    {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += ((tid >> k) & 1) ? c_w2[9 + k] : 0.f;
+        lut_hi[tid] = s;
+    }
+    if (tid < 24) colbits[tid >> 3][tid & 7] = 0ull;
+    __syncthreads();
+    {
+        constexpr int kPer = (kB2CH * kB2CW + kB2Threads - 1) / kB2Threads;
+        int vals[kPer];
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            const int i = tid + k * kB2Threads;
+            const int yy = min(max(y0 - kBandHalo + i / kB2CW, 0), a.Y - 1);
+            const int xx = min(max(x0 - kBandHalo + i % kB2CW, 0), a.X - 1);
+            vals[k] = i < kB2CH * kB2CW ? __ldg(a.zmap + (size_t)yy * a.X + xx) : 0;
+        }
+        int lo = INT32_MAX, hi = INT32_MIN;
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            const int i = tid + k * kB2Threads;
+            if (i < kB2CH * kB2CW) {
+                int v = vals[k];
+                if (a.shift != 0) v = min(max(v + a.shift, 0), a.Z);
+                cz_s[i / kB2CW][i % kB2CW] = v;
+                lo = min(lo, v);
+                hi = max(hi, v);
+                atomicOr(&present[v >> 5], 1u << (v & 31));
+            }
+        }
+        for (int o = 16; o; o >>= 1) {
+            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        if (lane == 0) {
+            atomicMin(&zlo_s, lo);
+            atomicMax(&zhi_s, hi);
+        }
+    }
+    __syncthreads();
+    const int zlo = zlo_s, zhi = zhi_s;
+    // planes the walk multiplies: z = zlo-4 .. zhi+4 inside the stack; plane index i = z - zbeg
+    const int zbeg = max(zlo - 4, 0), zend = min(zhi + 4, a.Z - 1);
+    const int npl = zend - zbeg + 1;
+    const int c0 = blockIdx.z * kBandMaxCh;
+    const int ch0 = a.ch[c0], ch1 = a.ch[c0 + (TWO ? 1 : 0)];
+    auto issue = [&](int i) {                                    // one thread per plane: arm the stage, ask the TMA unit
+        const int stage = i % NST;
+        const uint32_t bar = bar_s + 8 * stage, dst = ring_s + stage * STAGE;
+        mbar_expect_tx(bar, STAGE);
+        tma_load_4d(dst, &tmap, x0, y0, zbeg + i, ch0, bar);
+        if (TWO) tma_load_4d(dst + kB3PlaneBytes, &tmap, x0, y0, zbeg + i, ch1, bar);
+    };
+    if (tid < NST && tid < npl) issue(tid);
+
+    const float one_val = lut_lo[511] + lut_hi[255];
+    const int g = tid & 7, row = tid >> 3;                     // 8 pixels x0+8g .. +7 of row y0+row
+    const int x = x0 + g * kBandPix, y = y0 + row;
+    const bool inside = y < a.Y && x < a.X;
+    const float nb = -((float)a.pedestal + 8388608.0f);
+    const float2 nbias = make_float2(nb, nb);
+    uint32_t magic = 0x4B000000u;
+    asm volatile("" : "+r"(magic));
+    const unsigned char* my_vox = b3_ring + row * (kBandTX * 2) + g * 16;
+
+    // ballots of plane t into rowmask[buf] (+ the zeroed column mask of that plane)
+    auto build_masks = [&](int t, int buf, int cb) {
+#pragma unroll
+        for (int rr = 0; rr < kB2CH / 8; ++rr) {
+            const int r = warp + 8 * rr;
+            uint32_t mine = 0;
+#pragma unroll
+            for (int seg = 0; seg < 3; ++seg) {
+                const int col = 32 * seg + lane;
+                const int v = col < kB2CW ? cz_s[r][col] : -1;
+                const uint32_t b = __ballot_sync(0xffffffffu, v == t);
+                if (lane == seg) mine = b;
+            }
+            if (lane < 4) rowmask[buf][r][lane] = mine;          // word 3 = 0
+        }
+        if (tid < 8) colbits[cb][tid] = 0ull;
+    };
+    auto next_present = [&](int t) {                             // smallest present plane > t, or INT_MAX
+        for (int q = t + 1; q <= zhi; ++q)
+            if ((present[q >> 5] >> (q & 31)) & 1u) return q;
+        return INT32_MAX;
+    };
+    // x pass of the plane whose masks are in rowmask[buf]: r_s[buf] and colbits[cb]
+    auto x_pass = [&](int buf, int cb) {
+#pragma unroll
+        for (int round = 0; round < 2; ++round) {
+            const int r = round * 32 + row;
+            if (round == 1 && r >= kB2CH) break;                 // warp-uniform (warps 0..3 take the second round)
+            const uint4 m = *reinterpret_cast<const uint4*>(&rowmask[buf][r][0]);
+            const uint32_t wlo = g < 4 ? m.x : m.y, whi = g < 4 ? m.y : m.z;
+            const uint32_t W = __funnelshift_r(wlo, whi, 8 * (g & 3)) & 0xFFFFFFu;
+            float o[8];
+            if (W == 0u) {
+#pragma unroll
+                for (int p = 0; p < 8; ++p) o[p] = 0.f;
+            } else if (W == 0xFFFFFFu) {
+#pragma unroll
+                for (int p = 0; p < 8; ++p) o[p] = one_val;
+            } else {
+#pragma unroll
+                for (int p = 0; p < 8; ++p) o[p] = lut_lo[(W >> p) & 511u] + lut_hi[(W >> (p + 9)) & 255u];
+            }
+            float4* dst = reinterpret_cast<float4*>(&r_s[buf][r][0]);
+            dst[g] = make_float4(o[0], o[1], o[2], o[3]);
+            dst[8 + g] = make_float4(o[4], o[5], o[6], o[7]);
+            const uint32_t B = __ballot_sync(0xffffffffu, W != 0u);          // bit 8*rr + g, rows 4*warp + rr
+            if (lane < 8) {
+                const uint32_t nib = ((B >> lane) & 1u) | (((B >> (lane + 8)) & 1u) << 1) |
+                                     (((B >> (lane + 16)) & 1u) << 2) | (((B >> (lane + 24)) & 1u) << 3);
+                if (nib) atomicOr(&colbits[cb][lane], (unsigned long long)nib << (round * 32 + 4 * warp));
+            }
+        }
+    };
+
+    float2 win[4][11];            // pending masks of planes t-4 .. t+4(+2), two pixels per entry
+    float2 best0[4], best1[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int i = 0; i < 11; ++i) win[q][i] = make_float2(0.f, 0.f);
+        best0[q] = best1[q] = make_float2(0.f, 0.f);
+    }
+    int live = 0;
+
+    int buf = 0, cb = 0;
+    build_masks(zlo, 0, 0);                      // zlo is always present
+    __syncthreads();
+
+    for (int tb = zlo; tb <= zhi + 8; tb += 3) {
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int t = tb + u;
+            if (t > zhi + 8) break;                                    // block-uniform
+            const bool have = t <= zhi && ((present[t >> 5] >> (t & 31)) & 1u);
+            if (have) {                                                // block-uniform
+                x_pass(buf, cb);
+                const int tn = next_present(t);
+                const int cbn = cb == 2 ? 0 : cb + 1;
+                if (tn != INT32_MAX) build_masks(tn, buf ^ 1, cbn);
+                __syncthreads();
+                // y pass: a_new = sum_dy w2[dy] * r_s[row + dy][8g ..], skipped by warps that see only zeros
+                const bool mine = ((colbits[cb][g] >> row) & 0x1FFFFull) != 0ull;
+                if (__any_sync(0xffffffffu, mine)) {
+                    float2 an[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) an[q] = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int dy = 0; dy < 17; ++dy) {
+                        const float4* src = reinterpret_cast<const float4*>(&r_s[buf][row + dy][0]);
+                        const float4 lo4 = src[g], hi4 = src[8 + g];
+                        const float2 w = c_w2p[dy];
+                        an[0] = __ffma2_rn(make_float2(lo4.x, lo4.y), w, an[0]);
+                        an[1] = __ffma2_rn(make_float2(lo4.z, lo4.w), w, an[1]);
+                        an[2] = __ffma2_rn(make_float2(hi4.x, hi4.y), w, an[2]);
+                        an[3] = __ffma2_rn(make_float2(hi4.z, hi4.w), w, an[3]);
+                    }
+                    if (mine) {
+                        live = 9;
+                        const bool edge = t - 4 < 4 || t + 4 > a.Z - 5;
+#pragma unroll
+                        for (int k = 0; k < 9; ++k) {
+                            const int z = t - 4 + k;
+                            float2 w = c_w1p[8 - k];
+                            if (edge) {
+                                const float we = (z >= 0 && z < a.Z) ? __ldg(a.wz + z * 9 + (8 - k)) : 0.f;
+                                w = make_float2(we, we);
+                            }
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) win[q][u + k] = __ffma2_rn(w, an[q], win[q][u + k]);
+                        }
+                    }
+                }
+                buf ^= 1;
+                cb = cbn;
+            }
+            const int z = t - 4;
+            if (z >= zbeg && z <= zend) {                              // block-uniform
+                const int i = z - zbeg, stage = i % NST;
+                mbar_wait(bar_s + 8 * stage, (uint32_t)(i / NST) & 1u);
+                if (live > 0) {
+                    const uint4 cur0 = *reinterpret_cast<const uint4*>(my_vox + stage * STAGE);
+                    const uint32_t w0[4] = {cur0.x, cur0.y, cur0.z, cur0.w};
+                    uint32_t w1[4] = {0, 0, 0, 0};
+                    if (TWO) {
+                        const uint4 cur1 = *reinterpret_cast<const uint4*>(my_vox + stage * STAGE + kB3PlaneBytes);
+                        w1[0] = cur1.x; w1[1] = cur1.y; w1[2] = cur1.z; w1[3] = cur1.w;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float2 m = win[q][u];
+                        float2 f = __fadd2_rn(make_float2(band_u16f_lo(w0[q], magic), band_u16f_hi(w0[q], magic)), nbias);
+                        if (AIRY) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); }
+                        const float2 pr = __fmul2_rn(f, m);
+                        best0[q].x = fmaxf(best0[q].x, pr.x);
+                        best0[q].y = fmaxf(best0[q].y, pr.y);
+                        if (TWO) {
+                            float2 f1 = __fadd2_rn(make_float2(band_u16f_lo(w1[q], magic), band_u16f_hi(w1[q], magic)), nbias);
+                            if (AIRY) { f1.x = fmaxf(f1.x, 0.f); f1.y = fmaxf(f1.y, 0.f); }
+                            const float2 pr1 = __fmul2_rn(f1, m);
+                            best1[q].x = fmaxf(best1[q].x, pr1.x);
+                            best1[q].y = fmaxf(best1[q].y, pr1.y);
+                        }
+                    }
+                }
+                // half a ring consumed and planes still to come: refill those stages
+                if ((i % HALF) == HALF - 1 && (i / HALF + 2) * HALF < npl) {
+                    __syncthreads();
+                    const int j = (i / HALF + 2) * HALF + tid;
+                    if (tid < HALF && j < npl) issue(j);
+                }
+            }
+            live -= live > 0;
+        }
+        // slide the window by 3 planes
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) win[q][i] = win[q][i + 3];
+            win[q][8] = win[q][9] = win[q][10] = make_float2(0.f, 0.f);
+        }
+    }
+    if (inside) {
+        float* dst = a.proj + ((size_t)ch0 * a.Y + y) * a.X + x;
+        reinterpret_cast<float4*>(dst)[0] = make_float4(best0[0].x, best0[0].y, best0[1].x, best0[1].y);
+        reinterpret_cast<float4*>(dst)[1] = make_float4(best0[2].x, best0[2].y, best0[3].x, best0[3].y);
+        if (TWO) {
+            float* dst1 = a.proj + ((size_t)ch1 * a.Y + y) * a.X + x;
+            reinterpret_cast<float4*>(dst1)[0] = make_float4(best1[0].x, best1[0].y, best1[1].x, best1[1].y);
+            reinterpret_cast<float4*>(dst1)[1] = make_float4(best1[2].x, best1[2].y, best1[3].x, best1[3].y);
+        }
+    }
+}
+
+constexpr int kB3Smem1 = 16 * kB3PlaneBytes + 16 * 8;
+constexpr int kB3Smem2 = 8 * 2 * kB3PlaneBytes + 8 * 8;
+
+// (X, Y, Z, C) map of the cropped stack, boxes of 64 x 32 x 1 x 1, zero fill outside
+static int make_band_tensor_map(const uint16_t* base, size_t channel_stride, int C, int Z, int Y, int X,
+                                CUtensorMap* out) {
+    EncodeTiledFn encode = nullptr;
+    int rc = get_tensor_map_encoder(&encode);
+    if (rc) return rc;
+    const cuuint64_t dims[4] = {(cuuint64_t)X, (cuuint64_t)Y, (cuuint64_t)Z, (cuuint64_t)C};
+    const cuuint64_t strides[3] = {(cuuint64_t)X * 2, (cuuint64_t)X * Y * 2, (cuuint64_t)channel_stride * 2};
+    const cuuint32_t box[4] = {(cuuint32_t)kBandTX, (cuuint32_t)kBandTY, 1, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, (void*)base, dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) for the band stage C=%d Z=%d Y=%d X=%d", (int)r, C, Z, Y, X);
+        return TSP_ERR_CUDA;
+    }
+    return TSP_OK;
+}
+
 static int get_wz_table(tsp_handle* h, int Z, const float** out) {
     char key[32];
     snprintf(key, sizeof key, "wz%d", Z);
@@ -690,27 +999,53 @@ static int launch_band_range(tsp_handle* h, const int32_t* d_zmap, int Z, int Y,
 }
 
 // channels are projected two per CTA; an odd channel count ends with a one-channel launch
-static void launch_band_variant(BandArgs a, dim3 grid, int pedestal, cudaStream_t s) {
+static int launch_band_variant(tsp_handle* h, BandArgs a, dim3 grid, int pedestal, int C, cudaStream_t s) {
     if (getenv("TSP_BAND_V1")) {
         band_project_kernel<<<grid, kBandThreads, 0, s>>>(a);
-        return;
+        return TSP_OK;
+    }
+    // TMA path: rows 16-byte aligned (the tensor map's stride rule), tile not larger than the image
+    const bool tma = a.vec && (a.X % 8 == 0) && a.X >= kBandTX && a.Y >= kBandTY && !getenv("TSP_BAND_V2");
+    CUtensorMap tmap;
+    if (tma) {
+        int rc = make_band_tensor_map(a.stack + a.z0_offset, a.channel_stride, C, a.Z, a.Y, a.X, &tmap);
+        if (rc) return rc;
+        std::lock_guard<std::mutex> lock(h->mu);
+        if (!h->band3_attr) {
+            TSP_CUDA(cudaFuncSetAttribute(band_project3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB3Smem1));
+            TSP_CUDA(cudaFuncSetAttribute(band_project3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB3Smem1));
+            TSP_CUDA(cudaFuncSetAttribute(band_project3_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB3Smem2));
+            TSP_CUDA(cudaFuncSetAttribute(band_project3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB3Smem2));
+            h->band3_attr = true;
+        }
     }
     const int pairs = a.nch / 2;
     if (pairs > 0) {
         BandArgs b = a;
         b.nch = 2 * pairs;
         dim3 g2(grid.x, grid.y, pairs);
-        if (pedestal) band_project2_kernel<true, true><<<g2, kB2Threads, 0, s>>>(b);
-        else band_project2_kernel<false, true><<<g2, kB2Threads, 0, s>>>(b);
+        if (tma) {
+            if (pedestal) band_project3_kernel<true, true><<<g2, kB2Threads, kB3Smem2, s>>>(tmap, b);
+            else band_project3_kernel<false, true><<<g2, kB2Threads, kB3Smem2, s>>>(tmap, b);
+        } else {
+            if (pedestal) band_project2_kernel<true, true><<<g2, kB2Threads, 0, s>>>(b);
+            else band_project2_kernel<false, true><<<g2, kB2Threads, 0, s>>>(b);
+        }
     }
     if (a.nch & 1) {
         BandArgs b = a;
         b.ch[0] = a.ch[a.nch - 1];
         b.nch = 1;
         dim3 g1(grid.x, grid.y, 1);
-        if (pedestal) band_project2_kernel<true, false><<<g1, kB2Threads, 0, s>>>(b);
-        else band_project2_kernel<false, false><<<g1, kB2Threads, 0, s>>>(b);
+        if (tma) {
+            if (pedestal) band_project3_kernel<true, false><<<g1, kB2Threads, kB3Smem1, s>>>(tmap, b);
+            else band_project3_kernel<false, false><<<g1, kB2Threads, kB3Smem1, s>>>(tmap, b);
+        } else {
+            if (pedestal) band_project2_kernel<true, false><<<g1, kB2Threads, 0, s>>>(b);
+            else band_project2_kernel<false, false><<<g1, kB2Threads, 0, s>>>(b);
+        }
     }
+    return TSP_OK;
 }
 
 int launch_band_project_ex(tsp_handle* h, const uint16_t* d_stack, size_t channel_stride, size_t z0_offset,
@@ -749,7 +1084,8 @@ int launch_band_project_ex(tsp_handle* h, const uint16_t* d_stack, size_t channe
     for (int c = 0; c < C; ++c)
         if (shift == 0 || c == ref_c) a.ch[a.nch++] = c;
     grid.z = (a.nch + kBandMaxCh - 1) / kBandMaxCh;
-    launch_band_variant(a, grid, pedestal, s);
+    rc = launch_band_variant(h, a, grid, pedestal, C, s);
+    if (rc) return rc;
     TSP_LAUNCH_CHECK(h);
     if (shift != 0 && C > 1) {
         a.shift = shift;
@@ -757,7 +1093,8 @@ int launch_band_project_ex(tsp_handle* h, const uint16_t* d_stack, size_t channe
         for (int c = 0; c < C; ++c)
             if (c != ref_c) a.ch[a.nch++] = c;
         grid.z = (a.nch + kBandMaxCh - 1) / kBandMaxCh;
-        launch_band_variant(a, grid, pedestal, s);
+        rc = launch_band_variant(h, a, grid, pedestal, C, s);
+        if (rc) return rc;
         TSP_LAUNCH_CHECK(h);
     }
     return TSP_OK;

@@ -6,13 +6,14 @@
 //
 // A full 65536-bin histogram costs one shared-memory atomic per voxel (~0.45 ms for 268 M voxels).
 // Large volumes therefore take the order statistics in three steps, all exact:
-//   1. hist16_kernel on a pseudo-random 1/stride subsample of 16-byte vectors -> a value window
-//      [lo, lo+W) that contains the wanted ranks with overwhelming probability
+//   1. sample_window_kernel: coarse histogram of a pseudo-random 1/stride subsample of 16-byte vectors; its
+//      last CTA picks a value window [lo, lo+W) that contains the wanted ranks with overwhelming probability
 //   2. window_count_kernel: one streaming pass that only COUNTS (voxels > pedestal, voxels < lo)
-//      and histograms the few voxels inside the window
-//   3. window_finalize_kernel: the ranks are resolved inside the window, or - if the window missed
-//      or was too wide - a flag arms the full-histogram fallback (step 1's kernel over everything).
-// Small volumes (stride 1) use the full histogram directly.
+//      and histograms the few voxels inside the window; its last CTA resolves the ranks inside the window,
+//      or - if the window missed or was too wide - arms
+//   3. hist_percentile_kernel, the full-histogram fallback (returns at once when not armed).
+// Small volumes (stride 1) use the full histogram directly.  "Last CTA" = atomic ticket after a fence, so the
+// whole percentile is three launches.
 #include "common.cuh"
 
 namespace tsp {
@@ -39,26 +40,20 @@ __device__ __forceinline__ uint32_t hash32(uint32_t x) {
     return x;
 }
 
-// stride == 1: exact histogram of all `count` voxels.  stride = 2^k > 1: one 16-byte vector out of
-// every `stride`, at a hashed position inside its group (head/tail voxels are skipped).
-// `gate`: when non-null the kernel only runs if *gate != 0 (full-histogram fallback).
-__global__ void __launch_bounds__(kHistThreads, 1)
-hist16_kernel(const uint16_t* __restrict__ vol, size_t count, uint32_t* __restrict__ ghist, uint32_t stride,
-              const int32_t* __restrict__ gate) {
-    if (gate && *gate == 0) return;
-    extern __shared__ uint32_t sh[];
+// exact 65536-bin histogram of all `count` voxels into ghist (per-CTA privatised in shared memory)
+__device__ void hist_full_body(const uint16_t* __restrict__ vol, size_t count, uint32_t* __restrict__ ghist,
+                               uint32_t* sh) {
     for (int i = threadIdx.x; i < kHistBins / 2; i += kHistThreads) sh[i] = 0;
     __syncthreads();
 
     const uintptr_t addr = reinterpret_cast<uintptr_t>(vol);
     size_t head = ((16 - (addr & 15)) & 15) / 2;
     if (head > count) head = count;
-    const size_t nvec_all = (count - head) / 8;
-    const size_t tail0 = head + nvec_all * 8;
+    const size_t nvec = (count - head) / 8;
+    const size_t tail0 = head + nvec * 8;
     const uint4* body = reinterpret_cast<const uint4*>(vol + head);
-    const size_t nvec = nvec_all / stride;                    // sampled vectors
 
-    if (blockIdx.x == 0 && stride == 1) {
+    if (blockIdx.x == 0) {
         for (size_t i = threadIdx.x; i < head; i += kHistThreads) hist_add(sh, vol[i]);
         for (size_t i = tail0 + threadIdx.x; i < count; i += kHistThreads) hist_add(sh, vol[i]);
     }
@@ -71,25 +66,16 @@ hist16_kernel(const uint16_t* __restrict__ vol, size_t count, uint32_t* __restri
 #pragma unroll
         for (int j = 0; j < kVecPerThread; ++j) {
             const size_t idx = base + (size_t)j * kHistThreads + threadIdx.x;
-            size_t src = idx;
-            if (stride > 1) src = idx * stride + (hash32((uint32_t)idx) & (stride - 1));
-            v[j] = idx < nvec ? __ldg(body + src) : make_uint4(0, 0, 0, 0);
+            v[j] = idx < nvec ? __ldg(body + idx) : make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
         for (int j = 0; j < kVecPerThread; ++j) {
             const size_t idx = base + (size_t)j * kHistThreads + threadIdx.x;
             if (idx < nvec) {
-                if (stride > 1) {
-                    // sample: neighbouring voxels are correlated, two of the eight (4 apart) carry most of the
-                    // information at a quarter of the shared-memory atomics (the bound of this kernel)
-                    hist_add(sh, v[j].x & 0xffffu);
-                    hist_add(sh, v[j].z & 0xffffu);
-                } else {
-                    hist_add_word(sh, v[j].x);
-                    hist_add_word(sh, v[j].y);
-                    hist_add_word(sh, v[j].z);
-                    hist_add_word(sh, v[j].w);
-                }
+                hist_add_word(sh, v[j].x);
+                hist_add_word(sh, v[j].y);
+                hist_add_word(sh, v[j].z);
+                hist_add_word(sh, v[j].w);
             }
         }
         __syncthreads();
@@ -121,7 +107,8 @@ hist16_kernel(const uint16_t* __restrict__ vol, size_t count, uint32_t* __restri
 }
 
 // ---- block-wide rank lookup in a table of counts --------------------------------------------------
-// 1024 threads.  counts[0..L), L a multiple of 4096; bins below `first_bin` are ignored.  Returns the
+// All threads of the block (a multiple of 32, at most 1024).  counts[0..L), L a multiple of 128 * warps; bins
+// below `first_bin` are ignored.  Loads go to L2 (ld.cg): the table may have just been written by other CTAs.  Returns the
 // total of the counted bins and, for each of the two ranks (0-based, after `base` earlier elements),
 // the smallest bin whose cumulative count exceeds it (-1 when the rank is outside the table).
 struct RankLookup {
@@ -135,7 +122,8 @@ __device__ RankLookup block_rank_lookup(const uint32_t* __restrict__ counts, int
     __shared__ unsigned long long warp_off[33];
     __shared__ int found[2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int seg = L / 32;                                   // bins per warp, multiple of 128
+    const int nwarps = blockDim.x >> 5;
+    const int seg = L / nwarps;                               // bins per warp, multiple of 128
     const uint4* c4 = reinterpret_cast<const uint4*>(counts);
     if (threadIdx.x < 2) found[threadIdx.x] = -1;
     auto masked = [&](int b0, uint4 v) {
@@ -148,7 +136,7 @@ __device__ RankLookup block_rank_lookup(const uint32_t* __restrict__ counts, int
     unsigned long long mine = 0;
     for (int c = 0; c < seg / 128; ++c) {
         const int b0 = warp * seg + c * 128 + lane * 4;
-        const uint4 v = masked(b0, c4[b0 / 4]);
+        const uint4 v = masked(b0, __ldcg(c4 + b0 / 4));
         mine += (unsigned long long)v.x + v.y + v.z + v.w;
     }
     for (int o = 16; o; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
@@ -156,11 +144,11 @@ __device__ RankLookup block_rank_lookup(const uint32_t* __restrict__ counts, int
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned long long acc = base;
-        for (int w = 0; w < 32; ++w) {
+        for (int w = 0; w < nwarps; ++w) {
             warp_off[w] = acc;
             acc += warp_tot[w];
         }
-        warp_off[32] = acc;
+        for (int w = nwarps; w <= 32; ++w) warp_off[w] = acc;
     }
     __syncthreads();
     const unsigned long long ranks[2] = {r0, r1};
@@ -169,7 +157,7 @@ __device__ RankLookup block_rank_lookup(const uint32_t* __restrict__ counts, int
         unsigned long long run = wlo;
         for (int c = 0; c < seg / 128; ++c) {
             const int b0 = warp * seg + c * 128 + lane * 4;
-            const uint4 v = masked(b0, c4[b0 / 4]);
+            const uint4 v = masked(b0, __ldcg(c4 + b0 / 4));
             const unsigned long long s4 = (unsigned long long)v.x + v.y + v.z + v.w;
             unsigned long long incl = s4;
             for (int o = 1; o < 32; o <<= 1) {
@@ -241,11 +229,19 @@ __device__ void write_result(int32_t* status, unsigned long long n, float p) {
     status[ST_NZ_HI] = (int32_t)(n >> 32);
 }
 
+// true in exactly one CTA of the grid: the one that finishes last (its threads then see every other CTA's
+// global writes and atomics).  All threads of the block must call it.
+__device__ bool is_last_block(unsigned int* ticket) {
+    __shared__ bool last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    return last;
+}
+
 // ---- exact percentile from a full histogram (also the fallback) -----------------------------------
-__global__ void __launch_bounds__(1024, 1)
-percentile_finalize_kernel(const uint32_t* __restrict__ ghist, int pedestal, int32_t* __restrict__ status,
-                           const int32_t* __restrict__ gate) {
-    if (gate && *gate == 0) return;
+__device__ void percentile_finalize(const uint32_t* __restrict__ ghist, int pedestal, int32_t* __restrict__ status) {
     // pass 1: total of the non-zero voxels, pass 2: the two ranks
     RankLookup first = block_rank_lookup(ghist, kHistBins, pedestal + 1, 0, ~0ull, ~0ull);
     const unsigned long long n = first.total;
@@ -259,10 +255,28 @@ percentile_finalize_kernel(const uint32_t* __restrict__ ghist, int pedestal, int
         write_result(status, n, numpy_lerp((float)(look.bin[0] - pedestal), (float)(look.bin[1] - pedestal), rp.gamma));
 }
 
-// ---- step 1b: value window from the sample histogram ----------------------------------------------
-__global__ void __launch_bounds__(1024, 1)
-window_select_kernel(const uint32_t* __restrict__ shist, int pedestal, int32_t* __restrict__ status) {
-    RankLookup first = block_rank_lookup(shist, kHistBins, pedestal + 1, 0, ~0ull, ~0ull);
+// full histogram of all voxels; the CTA that finishes last resolves the percentile.  `gate`: when non-null the
+// kernel only runs if *gate != 0 (fallback armed by ST_NEED_FULL).
+__global__ void __launch_bounds__(kHistThreads, 1)
+hist_percentile_kernel(const uint16_t* __restrict__ vol, size_t count, uint32_t* __restrict__ ghist, int pedestal,
+                       int32_t* __restrict__ status, unsigned int* __restrict__ ticket, const int32_t* __restrict__ gate) {
+    if (gate && *gate == 0) return;
+    extern __shared__ uint32_t sh[];
+    hist_full_body(vol, count, ghist, sh);
+    if (!is_last_block(ticket)) return;
+    percentile_finalize(ghist, pedestal, status);
+}
+
+// ---- step 1: value window from a sample ------------------------------------------------------------
+// One 16-byte vector out of every `stride` (a power of two), at a hashed position inside its group; two of its
+// eight voxels (4 apart - neighbours are correlated) go into a coarse histogram of 8-value bins, non-zero
+// voxels only.  The CTA that finishes last turns the sample ranks 0.95 (ns - 1) -/+ 9 sigma into the raw-value
+// window [lo, lo + w) that window_count_kernel resolves exactly.
+constexpr int kCoarseShift = 3;
+constexpr int kCoarseBins = kHistBins >> kCoarseShift;      // 8192
+
+__device__ void window_select(const uint32_t* __restrict__ shist, int pedestal, int32_t* __restrict__ status) {
+    RankLookup first = block_rank_lookup(shist, kCoarseBins, 0, 0, ~0ull, ~0ull);
     const unsigned long long ns = first.total;
     if (ns < 1024) {                  // sample too thin to trust: go straight to the full histogram
         if (threadIdx.x == 0) {
@@ -276,17 +290,77 @@ window_select_kernel(const uint32_t* __restrict__ shist, int pedestal, int32_t* 
     const double lo_r = centre - margin, hi_r = centre + margin + 1.0;
     const unsigned long long r_lo = lo_r < 0.0 ? 0ull : (unsigned long long)lo_r;
     const unsigned long long r_hi = hi_r > (double)(ns - 1) ? ns - 1 : (unsigned long long)hi_r;
-    RankLookup look = block_rank_lookup(shist, kHistBins, pedestal + 1, 0, r_lo, r_hi);
+    RankLookup look = block_rank_lookup(shist, kCoarseBins, 0, 0, r_lo, r_hi);
     if (threadIdx.x == 0) {
-        int lo = look.bin[0] - 1, hi = look.bin[1] + 1;          // raw-value bins, one spare on each side
+        int lo = look.bin[0] << kCoarseShift, hi = (look.bin[1] << kCoarseShift) + (1 << kCoarseShift) - 1;
         if (lo < pedestal + 1) lo = pedestal + 1;
         if (hi > kHistBins - 1) hi = kHistBins - 1;
         const int w = hi - lo + 1;
-        const bool ok = w <= kWinBins;
+        const bool ok = w <= kWinBins && w > 0;
         status[ST_WIN_LO] = lo;
         status[ST_WIN_N] = w;
         status[ST_WIN_OK] = ok ? 1 : 0;
         status[ST_NEED_FULL] = ok ? 0 : 1;
+    }
+}
+
+__global__ void __launch_bounds__(kHistThreads, 1)
+sample_window_kernel(const uint16_t* __restrict__ vol, size_t count, uint32_t stride, int pedestal,
+                     uint32_t* __restrict__ shist, int32_t* __restrict__ status, unsigned int* __restrict__ ticket) {
+    __shared__ uint32_t sh[kCoarseBins];
+    for (int i = threadIdx.x; i < kCoarseBins; i += kHistThreads) sh[i] = 0;
+    __syncthreads();
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(vol);
+    size_t head = ((16 - (addr & 15)) & 15) / 2;
+    if (head > count) head = count;
+    const uint4* body = reinterpret_cast<const uint4*>(vol + head);
+    const size_t nvec = (count - head) / 8 / stride;           // sampled vectors
+    const uint32_t ped = (uint32_t)pedestal;
+    const size_t vec_per_chunk = (size_t)kHistThreads * kVecPerThread;
+    const size_t nchunks = (nvec + vec_per_chunk - 1) / vec_per_chunk;
+    for (size_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        const size_t base = chunk * vec_per_chunk;
+        uint2 v[kVecPerThread];
+#pragma unroll
+        for (int j = 0; j < kVecPerThread; ++j) {
+            const size_t idx = base + (size_t)j * kHistThreads + threadIdx.x;
+            const size_t src = idx * stride + (hash32((uint32_t)idx) & (stride - 1));
+            const uint4 q = idx < nvec ? __ldg(body + src) : make_uint4(0, 0, 0, 0);
+            v[j] = make_uint2(q.x & 0xffffu, q.z & 0xffffu);
+        }
+#pragma unroll
+        for (int j = 0; j < kVecPerThread; ++j) {
+            if (v[j].x > ped) atomicAdd(&sh[v[j].x >> kCoarseShift], 1u);      // padding vectors hold zeros
+            if (v[j].y > ped) atomicAdd(&sh[v[j].y >> kCoarseShift], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kCoarseBins; i += kHistThreads)
+        if (sh[i]) atomicAdd(&shist[i], sh[i]);
+    if (!is_last_block(ticket)) return;
+    window_select(shist, pedestal, status);
+}
+
+// ---- step 3 (run by the last CTA of window_count_kernel) -----------------------------------------------
+__device__ void window_finalize(const uint32_t* __restrict__ gwin, const unsigned long long* __restrict__ gcounters,
+                                unsigned long long count, int pedestal, int32_t* __restrict__ status) {
+    const unsigned long long n = __ldcg(gcounters);      // voxels > pedestal
+    if (n == 0) {
+        if (threadIdx.x == 0) write_result(status, 0, 0.f);
+        return;
+    }
+    const unsigned long long zeros = count - n;     // voxels <= pedestal (they are all below the window)
+    const unsigned long long below_nz = __ldcg(gcounters + 1) - zeros;
+    const RankPair rp = numpy_ranks(n);
+    RankLookup look = block_rank_lookup(gwin, kWinBins, 0, below_nz, rp.prev, rp.next);
+    if (threadIdx.x == 0) {
+        const int lo = status[ST_WIN_LO];
+        if (look.bin[0] < 0 || look.bin[1] < 0 || rp.prev < below_nz) {
+            status[ST_NEED_FULL] = 1;               // the sample window missed: exact fallback
+        } else {
+            write_result(status, n, numpy_lerp((float)(lo + look.bin[0] - pedestal),
+                                               (float)(lo + look.bin[1] - pedestal), rp.gamma));
+        }
     }
 }
 
@@ -320,7 +394,8 @@ __device__ __forceinline__ float biased_hi(uint32_t w, uint32_t magic) {
 
 __global__ void __launch_bounds__(kCountThreads, 2)
 window_count_kernel(const uint16_t* __restrict__ vol, size_t count, int pedestal, int32_t* __restrict__ status,
-                    uint32_t* __restrict__ gwin, unsigned long long* __restrict__ gcounters) {
+                    uint32_t* __restrict__ gwin, unsigned long long* __restrict__ gcounters,
+                    unsigned int* __restrict__ ticket) {
     if (status[ST_WIN_OK] == 0) return;
     __shared__ uint32_t win[kWinBins];
     __shared__ uint4 queue[kQueueCap];
@@ -447,42 +522,19 @@ window_count_kernel(const uint16_t* __restrict__ vol, size_t count, int pedestal
     }
     for (int i = threadIdx.x; i < kWinBins; i += kCountThreads)
         if (win[i]) atomicAdd(&gwin[i], win[i]);
-}
-
-// ---- step 3 ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024, 1)
-window_finalize_kernel(const uint32_t* __restrict__ gwin, const unsigned long long* __restrict__ gcounters,
-                       unsigned long long count, int pedestal, int32_t* __restrict__ status) {
-    if (status[ST_WIN_OK] == 0) return;            // NEED_FULL already set by window_select_kernel
-    const unsigned long long n = gcounters[0];      // voxels > pedestal
-    if (n == 0) {
-        if (threadIdx.x == 0) write_result(status, 0, 0.f);
-        return;
-    }
-    const unsigned long long zeros = count - n;     // voxels <= pedestal (they are all below the window)
-    const unsigned long long below_nz = gcounters[1] - zeros;
-    const RankPair rp = numpy_ranks(n);
-    RankLookup look = block_rank_lookup(gwin, kWinBins, 0, below_nz, rp.prev, rp.next);
-    if (threadIdx.x == 0) {
-        const int lo = status[ST_WIN_LO];
-        if (look.bin[0] < 0 || look.bin[1] < 0 || rp.prev < below_nz) {
-            status[ST_NEED_FULL] = 1;               // the sample window missed: exact fallback
-        } else {
-            write_result(status, n, numpy_lerp((float)(lo + look.bin[0] - pedestal),
-                                               (float)(lo + look.bin[1] - pedestal), rp.gamma));
-        }
-    }
+    if (!is_last_block(ticket)) return;
+    window_finalize(gwin, gcounters, (unsigned long long)count, pedestal, status);
 }
 
 // ---- launchers ------------------------------------------------------------------------------------
 size_t percentile_scratch_bytes() {
-    // [sample/full histogram 256 KB][fallback histogram 256 KB][window 16 KB][counters 64 B]
-    return 2 * kHistBins * sizeof(uint32_t) + kWinBins * sizeof(uint32_t) + 64;
+    // [full histogram 256 KB][sample histogram 32 KB][window 16 KB][counters + tickets 64 B]
+    return (kHistBins + kCoarseBins + kWinBins) * sizeof(uint32_t) + 64;
 }
 
 static int ensure_hist_attr(tsp_handle* h) {
     if (!h->hist_attr) {
-        TSP_CUDA(cudaFuncSetAttribute(hist16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmemBytes));
+        TSP_CUDA(cudaFuncSetAttribute(hist_percentile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmemBytes));
         h->hist_attr = true;
     }
     return TSP_OK;
@@ -495,37 +547,34 @@ static int hist_grid(tsp_handle* h, size_t count, uint32_t stride) {
 }
 
 // d_scratch: percentile_scratch_bytes() bytes.  Writes ST_HAS_NONZERO / ST_P95_BITS / ST_NZ_* into d_status.
+// Three launches: sample + window, exact count + resolve, gated full-histogram fallback.
 int launch_percentile(tsp_handle* h, const uint16_t* d_vol, size_t count, int pedestal, int32_t* d_status,
                       void* d_scratch, cudaStream_t s) {
     int rc = ensure_hist_attr(h);
     if (rc) return rc;
-    uint32_t* hist_a = (uint32_t*)d_scratch;
-    uint32_t* hist_b = hist_a + kHistBins;
-    uint32_t* win = hist_b + kHistBins;
+    uint32_t* hist_full = (uint32_t*)d_scratch;
+    uint32_t* hist_sample = hist_full + kHistBins;
+    uint32_t* win = hist_sample + kCoarseBins;
     unsigned long long* counters = (unsigned long long*)(win + kWinBins);
+    unsigned int* tickets = (unsigned int*)(counters + 2);
     TSP_CUDA(cudaMemsetAsync(d_scratch, 0, percentile_scratch_bytes(), s));
     uint32_t stride = 1;
     while ((count / stride) > 2 * kSampleTarget && stride < 1024) stride *= 2;
     if (stride == 1) {
-        hist16_kernel<<<hist_grid(h, count, 1), kHistThreads, kHistSmemBytes, s>>>(d_vol, count, hist_a, 1, nullptr);
-        TSP_LAUNCH_CHECK(h);
-        percentile_finalize_kernel<<<1, 1024, 0, s>>>(hist_a, pedestal, d_status, nullptr);
+        hist_percentile_kernel<<<hist_grid(h, count, 1), kHistThreads, kHistSmemBytes, s>>>(
+            d_vol, count, hist_full, pedestal, d_status, tickets, nullptr);
         TSP_LAUNCH_CHECK(h);
         return TSP_OK;
     }
-    hist16_kernel<<<hist_grid(h, count, stride), kHistThreads, kHistSmemBytes, s>>>(d_vol, count, hist_a, stride, nullptr);
+    sample_window_kernel<<<hist_grid(h, count, stride), kHistThreads, 0, s>>>(d_vol, count, stride, pedestal,
+                                                                             hist_sample, d_status, tickets + 1);
     TSP_LAUNCH_CHECK(h);
-    window_select_kernel<<<1, 1024, 0, s>>>(hist_a, pedestal, d_status);
+    window_count_kernel<<<h->sm_count * 2, kCountThreads, 0, s>>>(d_vol, count, pedestal, d_status, win, counters,
+                                                                  tickets + 2);
     TSP_LAUNCH_CHECK(h);
-    window_count_kernel<<<h->sm_count * 2, kCountThreads, 0, s>>>(d_vol, count, pedestal, d_status, win, counters);
-    TSP_LAUNCH_CHECK(h);
-    window_finalize_kernel<<<1, 1024, 0, s>>>(win, counters, (unsigned long long)count, pedestal, d_status);
-    TSP_LAUNCH_CHECK(h);
-    // exact fallback, armed by ST_NEED_FULL (both kernels return at once otherwise)
-    hist16_kernel<<<hist_grid(h, count, 1), kHistThreads, kHistSmemBytes, s>>>(d_vol, count, hist_b, 1,
-                                                                             d_status + ST_NEED_FULL);
-    TSP_LAUNCH_CHECK(h);
-    percentile_finalize_kernel<<<1, 1024, 0, s>>>(hist_b, pedestal, d_status, d_status + ST_NEED_FULL);
+    // exact fallback, armed by ST_NEED_FULL (returns at once otherwise)
+    hist_percentile_kernel<<<hist_grid(h, count, 1), kHistThreads, kHistSmemBytes, s>>>(
+        d_vol, count, hist_full, pedestal, d_status, tickets, d_status + ST_NEED_FULL);
     TSP_LAUNCH_CHECK(h);
     return TSP_OK;
 }
