@@ -209,13 +209,14 @@ int tsp_project_frame(tsp_handle* h, const tsp_frame_desc* desc, const uint16_t*
     const uint16_t* ref = d_stack + (size_t)desc->reference_channel * chan_stride + z0_off;
 
     prof_mark(h, s, -1);
-    TSP_CUDA(cudaMemsetAsync(w.status, 0, kStatusWords * sizeof(int32_t), s));
-    rc = launch_percentile(h, ref, nvox, ped, w.status, w.hist, s);
+    const bool fast = desc->mode == TSP_MODE_FAST;
+    rc = launch_percentile(h, ref, nvox, ped, w.status, w.hist, s, fast ? w.fast : nullptr,
+                           fast ? fast_accum_bytes(c.zc, Y, X) : 0);
     if (rc) return rc;
     prof_mark(h, s, STG_PERCENTILE);
 
-    if (desc->mode == TSP_MODE_FAST) {
-        rc = launch_fast_score_argmax(h, ref, d_zmap, c.zc, Y, X, ped, c.z_offset, w.status, w.fast, s);
+    if (fast) {
+        rc = launch_fast_score_argmax(h, ref, d_zmap, c.zc, Y, X, ped, c.z_offset, w.status, w.fast, s, true);
         if (rc) return rc;
         rc = launch_band_project_ex(h, d_stack, chan_stride, z0_off, d_zmap, d_proj, C, c.zc, Y, X,
                                     desc->reference_channel, desc->atoh_shift, ped, w.status, true, s);
@@ -444,7 +445,6 @@ int tsp_percentile95_nonzero_u16(tsp_handle* h, const uint16_t* d_volume, size_t
     if (rc) return rc;
     int32_t* st = (int32_t*)h->d_scratch;
     uint32_t* hist = (uint32_t*)((char*)h->d_scratch + align_up(kStatusWords * sizeof(int32_t), 256));
-    TSP_CUDA(cudaMemsetAsync(st, 0, kStatusWords * sizeof(int32_t), s));
     rc = launch_percentile(h, d_volume, count, airyscan ? kAiryscanPedestal : 0, st, hist, s);
     if (rc) return rc;
     TSP_CUDA(cudaMemcpyAsync(h->h_status, st, kStatusWords * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
@@ -466,7 +466,6 @@ int tsp_focus_score_f32(tsp_handle* h, const uint16_t* d_channel, float* d_score
     uint32_t* hist = (uint32_t*)((char*)h->d_scratch + align_up(kStatusWords * sizeof(int32_t), 256));
     const size_t nvox = (size_t)planes * rows * cols;
     const int ped = airyscan ? kAiryscanPedestal : 0;
-    TSP_CUDA(cudaMemsetAsync(st, 0, kStatusWords * sizeof(int32_t), s));
     rc = launch_percentile(h, d_channel, nvox, ped, st, hist, s);
     if (rc) return rc;
     rc = launch_prepare(h, d_channel, d_score, nvox, ped, st, s);

@@ -170,7 +170,7 @@ void prof_mark(tsp_handle* h, cudaStream_t s, int stage);   // stage -1 opens a 
 // stage launchers (each returns TSP_OK or an error code)
 size_t percentile_scratch_bytes();
 int launch_percentile(tsp_handle* h, const uint16_t* d_vol, size_t count, int pedestal, int32_t* d_status,
-                      void* d_scratch, cudaStream_t s);
+                      void* d_scratch, cudaStream_t s, void* zero_ptr = nullptr, size_t zero_bytes = 0);
 int launch_prepare(tsp_handle* h, const uint16_t* d_in, float* d_out, size_t count, int pedestal,
                    const int32_t* d_status, cudaStream_t s);
 int launch_convert_u16_f32(tsp_handle* h, const uint16_t* d_in, float* d_out, size_t count,
@@ -197,8 +197,9 @@ int launch_widen_outputs(tsp_handle* h, const float* d_proj, const int32_t* d_zm
 
 // fast (multirate) score stage
 size_t fast_workspace_bytes(int Z, int Y, int X);
+size_t fast_accum_bytes(int Z, int Y, int X);      // leading bytes of the fast workspace that must be zero on entry
 int launch_fast_score_argmax(tsp_handle* h, const uint16_t* d_channel, int32_t* d_zmap, int Z, int Y,
                              int X, int pedestal, int z_offset, int32_t* d_status, void* d_ws,
-                             cudaStream_t s);
+                             cudaStream_t s, bool accum_zeroed = false);
 
 }  // namespace tsp

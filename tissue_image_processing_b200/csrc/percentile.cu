@@ -268,9 +268,9 @@ hist_percentile_kernel(const uint16_t* __restrict__ vol, size_t count, uint32_t*
 }
 
 // ---- step 1: value window from a sample ------------------------------------------------------------
-// One 16-byte vector out of every `stride` (a power of two), at a hashed position inside its group; two of its
-// eight voxels (4 apart - neighbours are correlated) go into a coarse histogram of 8-value bins, non-zero
-// voxels only.  The CTA that finishes last turns the sample ranks 0.95 (ns - 1) -/+ 9 sigma into the raw-value
+// One 128-byte line out of every `stride` (a power of two), at a hashed position inside its group - whole lines,
+// because scattered 16-byte reads cost a DRAM transaction each; two of the eight voxels of every 16-byte vector
+// (4 apart - neighbours are correlated) go into a coarse histogram of 8-value bins, non-zero voxels only.  The CTA that finishes last turns the sample ranks 0.95 (ns - 1) -/+ 9 sigma into the raw-value
 // window [lo, lo + w) that window_count_kernel resolves exactly.
 constexpr int kCoarseShift = 3;
 constexpr int kCoarseBins = kHistBins >> kCoarseShift;      // 8192
@@ -314,7 +314,7 @@ sample_window_kernel(const uint16_t* __restrict__ vol, size_t count, uint32_t st
     size_t head = ((16 - (addr & 15)) & 15) / 2;
     if (head > count) head = count;
     const uint4* body = reinterpret_cast<const uint4*>(vol + head);
-    const size_t nvec = (count - head) / 8 / stride;           // sampled vectors
+    const size_t nvec = ((count - head) / 8 / stride) & ~(size_t)7;      // sampled vectors: whole lines of 8
     const uint32_t ped = (uint32_t)pedestal;
     const size_t vec_per_chunk = (size_t)kHistThreads * kVecPerThread;
     const size_t nchunks = (nvec + vec_per_chunk - 1) / vec_per_chunk;
@@ -324,7 +324,9 @@ sample_window_kernel(const uint16_t* __restrict__ vol, size_t count, uint32_t st
 #pragma unroll
         for (int j = 0; j < kVecPerThread; ++j) {
             const size_t idx = base + (size_t)j * kHistThreads + threadIdx.x;
-            const size_t src = idx * stride + (hash32((uint32_t)idx) & (stride - 1));
+            // whole 128-byte lines (8 consecutive vectors, one per lane of an octet): one line out of every `stride`
+            const size_t line = idx >> 3;
+            const size_t src = ((line * stride + (hash32((uint32_t)line) & (stride - 1))) << 3) + (idx & 7);
             const uint4 q = idx < nvec ? __ldg(body + src) : make_uint4(0, 0, 0, 0);
             v[j] = make_uint2(q.x & 0xffffu, q.z & 0xffffu);
         }
@@ -395,7 +397,10 @@ __device__ __forceinline__ float biased_hi(uint32_t w, uint32_t magic) {
 __global__ void __launch_bounds__(kCountThreads, 2)
 window_count_kernel(const uint16_t* __restrict__ vol, size_t count, int pedestal, int32_t* __restrict__ status,
                     uint32_t* __restrict__ gwin, unsigned long long* __restrict__ gcounters,
-                    unsigned int* __restrict__ ticket) {
+                    unsigned int* __restrict__ ticket, uint4* __restrict__ zero_ptr, size_t zero_vecs) {
+    // side job: clear the accumulation volume of the next stage (saves a separate memset pass between kernels)
+    for (size_t i = (size_t)blockIdx.x * kCountThreads + threadIdx.x; i < zero_vecs; i += (size_t)gridDim.x * kCountThreads)
+        zero_ptr[i] = make_uint4(0, 0, 0, 0);
     if (status[ST_WIN_OK] == 0) return;
     __shared__ uint32_t win[kWinBins];
     __shared__ uint4 queue[kQueueCap];
@@ -548,8 +553,10 @@ static int hist_grid(tsp_handle* h, size_t count, uint32_t stride) {
 
 // d_scratch: percentile_scratch_bytes() bytes.  Writes ST_HAS_NONZERO / ST_P95_BITS / ST_NZ_* into d_status.
 // Three launches: sample + window, exact count + resolve, gated full-histogram fallback.
+// Also clears the status block (kStatusWords words) and - for the next stage - zero_bytes at zero_ptr (16-byte
+// aligned, may be null).
 int launch_percentile(tsp_handle* h, const uint16_t* d_vol, size_t count, int pedestal, int32_t* d_status,
-                      void* d_scratch, cudaStream_t s) {
+                      void* d_scratch, cudaStream_t s, void* zero_ptr, size_t zero_bytes) {
     int rc = ensure_hist_attr(h);
     if (rc) return rc;
     uint32_t* hist_full = (uint32_t*)d_scratch;
@@ -557,9 +564,20 @@ int launch_percentile(tsp_handle* h, const uint16_t* d_vol, size_t count, int pe
     uint32_t* win = hist_sample + kCoarseBins;
     unsigned long long* counters = (unsigned long long*)(win + kWinBins);
     unsigned int* tickets = (unsigned int*)(counters + 2);
-    TSP_CUDA(cudaMemsetAsync(d_scratch, 0, percentile_scratch_bytes(), s));
+    if ((char*)d_scratch - (char*)d_status == (ptrdiff_t)align_up(kStatusWords * sizeof(int32_t), 256)) {
+        TSP_CUDA(cudaMemsetAsync(d_status, 0, align_up(kStatusWords * sizeof(int32_t), 256) + percentile_scratch_bytes(), s));
+    } else {
+        TSP_CUDA(cudaMemsetAsync(d_status, 0, kStatusWords * sizeof(int32_t), s));
+        TSP_CUDA(cudaMemsetAsync(d_scratch, 0, percentile_scratch_bytes(), s));
+    }
+    const bool zero_vec_ok = zero_ptr && (reinterpret_cast<uintptr_t>(zero_ptr) & 15) == 0 && zero_bytes % 16 == 0;
     uint32_t stride = 1;
     while ((count / stride) > 2 * kSampleTarget && stride < 1024) stride *= 2;
+    if (stride == 1 || !zero_vec_ok) {
+        if (zero_ptr && zero_bytes) TSP_CUDA(cudaMemsetAsync(zero_ptr, 0, zero_bytes, s));
+        zero_ptr = nullptr;
+        zero_bytes = 0;
+    }
     if (stride == 1) {
         hist_percentile_kernel<<<hist_grid(h, count, 1), kHistThreads, kHistSmemBytes, s>>>(
             d_vol, count, hist_full, pedestal, d_status, tickets, nullptr);
@@ -570,7 +588,7 @@ int launch_percentile(tsp_handle* h, const uint16_t* d_vol, size_t count, int pe
                                                                              hist_sample, d_status, tickets + 1);
     TSP_LAUNCH_CHECK(h);
     window_count_kernel<<<h->sm_count * 2, kCountThreads, 0, s>>>(d_vol, count, pedestal, d_status, win, counters,
-                                                                  tickets + 2);
+                                                                  tickets + 2, (uint4*)zero_ptr, zero_bytes / 16);
     TSP_LAUNCH_CHECK(h);
     // exact fallback, armed by ST_NEED_FULL (returns at once otherwise)
     hist_percentile_kernel<<<hist_grid(h, count, 1), kHistThreads, kHistSmemBytes, s>>>(
