@@ -116,6 +116,8 @@ struct BandArgs {
     int pedestal;
     int nch;
     int vec;                    // rows are 16-byte aligned: uint4 loads
+    int zvec;                   // height-map rows are 16-byte aligned: int4 loads
+    const float* lut;           // x-blur lookup tables of a binary row: [512] taps 0..8, [256] taps 9..16
     int ch[16];
 };
 
@@ -626,16 +628,23 @@ __global__ void __launch_bounds__(kB2Threads, 2) band_project2_kernel(const Band
     }
 }
 
-// ---- K5-K7 fused, third generation: the voxels arrive by TMA ---------------------------------------
+// ---- K5-K7 fused, TMA generation --------------------------------------------------------------------
 // band_project2_kernel keeps one plane (16 bytes per thread) of raw voxels in flight, so every plane of the walk
-// costs a full HBM round trip: the kernel is latency bound (ncu: ~20 us per CTA for ~11 us of issue work in the
-// whole grid).  Here the mask arithmetic is unchanged, but as soon as the tile's plane range [zlo-4, zhi+4] is
-// known the CTA asks the TMA unit for every plane of it at once: one 64 x 32 x 1 (x 1 channel) box per plane
-// (cp.async.bulk.tensor.4d over the (X, Y, Z, C) map of the cropped stack), each completing on the mbarrier of
-// its ring stage.  The loads overlap the mask building; the weighted max reads the voxels from shared memory.
-// Ranges deeper than the ring are refilled half a ring at a time behind a block barrier.  Rows / columns past
-// the image edge arrive as zeros (they are never stored).
+// costs a full HBM round trip, and it spends most of its issue slots on bookkeeping.  This kernel does the same
+// arithmetic with:
+//   * the voxels by TMA: as soon as the tile's plane range [zlo-4, zhi+4] is known the CTA asks for every plane of
+//     it at once - one 64 x 32 x 1 (x 1 channel) box per plane (cp.async.bulk.tensor.4d over the (X, Y, Z, C) map
+//     of the cropped stack) into a ring of 16 stages, completing on one mbarrier per half ring; the loads overlap
+//     the mask building and the weighted max reads shared memory.  Deeper ranges refill half a ring at a time;
+//   * the height-map tile as uint16 in shared memory, loaded with 16-byte vectors (interior tiles), range by
+//     warp reductions; the indicator masks of FOUR consecutive planes come out of one sweep over it (ballots),
+//     together with a per-warp "plane present" flag - no atomics, no present-plane bitmap;
+//   * the pending-mask window as a 9-slot CIRCULAR register file: the plane loop switches on (t - zlo) mod 9 so
+//     that every slot index is a compile-time constant - no window shifting (12 % of the old kernel's instructions);
+//   * the x-blur lookup tables precomputed on the host; a warp skips the y pass of a plane none of its 20 window
+//     rows sees (one word per 4 rows of the x-blurred plane says which 8-pixel groups are non-zero).
 constexpr int kB3PlaneBytes = kBandTY * kBandTX * 2;          // 4096: one channel of one plane of the tile
+constexpr int kB3Chunk = 4;                                    // planes whose masks are built per sweep
 
 template <bool AIRY, bool TWO>
 __global__ void __launch_bounds__(kB2Threads, 2) band_project3_kernel(const __grid_constant__ CUtensorMap tmap,
@@ -643,13 +652,13 @@ __global__ void __launch_bounds__(kB2Threads, 2) band_project3_kernel(const __gr
     constexpr int NST = TWO ? 8 : 16;                             // ring stages (planes in flight)
     constexpr int HALF = NST / 2;
     constexpr int STAGE = (TWO ? 2 : 1) * kB3PlaneBytes;
-    extern __shared__ __align__(128) unsigned char b3_ring[];     // [NST][STAGE] + NST mbarriers
-    __shared__ __align__(16) int cz_s[kB2CH][kB2CW];
-    __shared__ __align__(16) uint32_t rowmask[2][kB2CH][4];
+    extern __shared__ __align__(128) unsigned char b3_ring[];     // [NST][STAGE] + 2 mbarriers
+    __shared__ __align__(16) uint16_t cz_s[kB2CH][kB2CW];
+    __shared__ __align__(16) uint32_t rowmask[2][kB3Chunk][kB2CH][4];
     __shared__ __align__(16) float r_s[2][kB2CH][kBandTX];       // row layout: [half][group][4]
-    __shared__ unsigned long long colbits[3][8];
+    __shared__ uint32_t rownz[2][12];                             // [4 rows][8 groups] bits: group holds a non-zero
+    __shared__ __align__(16) uint32_t pres[2][8];                 // bit p: warp w saw plane p of the chunk
     __shared__ float lut_lo[512], lut_hi[256];
-    __shared__ uint32_t present[kBandMaxPlanes / 32];
     __shared__ int zlo_s, zhi_s;
 
     if (a.status[ST_BAND_ERR]) return;          // the reference raises before projecting
@@ -661,53 +670,62 @@ __global__ void __launch_bounds__(kB2Threads, 2) band_project3_kernel(const __gr
     if (tid == 0) {
         zlo_s = INT32_MAX;
         zhi_s = INT32_MIN;
-#pragma unroll
-        for (int s = 0; s < NST; ++s) mbar_init(bar_s + 8 * s, 1);
+        mbar_init(bar_s, 1);
+        mbar_init(bar_s + 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    for (int i = tid; i < (a.Z >> 5) + 1 && i < kBandMaxPlanes / 32; i += kB2Threads) present[i] = 0;
-    for (int i = tid; i < 512; i += kB2Threads) {
-        float s = 0.f;
-#pragma unroll
-        for (int k = 0; k < 9; ++k) s += ((i >> k) & 1) ? c_w2[k] : 0.f;
-        lut_lo[i] = s;
-    }
+    lut_lo[tid] = __ldg(a.lut + tid);
+    lut_lo[256 + tid] = __ldg(a.lut + 256 + tid);
+    lut_hi[tid] = __ldg(a.lut + 512 + tid);
     {
-        float s = 0.f;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) s += ((tid >> k) & 1) ? c_w2[9 + k] : 0.f;
-        lut_hi[tid] = s;
-    }
-    if (tid < 24) colbits[tid >> 3][tid & 7] = 0ull;
-    __syncthreads();
-    {
-        constexpr int kPer = (kB2CH * kB2CW + kB2Threads - 1) / kB2Threads;
-        int vals[kPer];
-#pragma unroll
-        for (int k = 0; k < kPer; ++k) {
-            const int i = tid + k * kB2Threads;
-            const int yy = min(max(y0 - kBandHalo + i / kB2CW, 0), a.Y - 1);
-            const int xx = min(max(x0 - kBandHalo + i % kB2CW, 0), a.X - 1);
-            vals[k] = i < kB2CH * kB2CW ? __ldg(a.zmap + (size_t)yy * a.X + xx) : 0;
-        }
         int lo = INT32_MAX, hi = INT32_MIN;
+        auto put = [&](int v) {
+            if (a.shift != 0) v = min(max(v + a.shift, 0), a.Z);
+            lo = min(lo, v);
+            hi = max(hi, v);
+            return (uint32_t)v;
+        };
+        const bool interior = a.zvec && x0 >= kBandHalo && x0 + kBandTX + kBandHalo <= a.X && y0 >= kBandHalo &&
+                              y0 + kBandTY + kBandHalo <= a.Y;
+        if (interior) {                      // 48 rows x 20 int4, no clamping
+            const int4* base = reinterpret_cast<const int4*>(a.zmap + (size_t)(y0 - kBandHalo) * a.X + (x0 - kBandHalo));
+            const size_t rstride = (size_t)a.X / 4;
+            int4 vals[4];
 #pragma unroll
-        for (int k = 0; k < kPer; ++k) {
-            const int i = tid + k * kB2Threads;
-            if (i < kB2CH * kB2CW) {
-                int v = vals[k];
-                if (a.shift != 0) v = min(max(v + a.shift, 0), a.Z);
-                cz_s[i / kB2CW][i % kB2CW] = v;
-                lo = min(lo, v);
-                hi = max(hi, v);
-                atomicOr(&present[v >> 5], 1u << (v & 31));
+            for (int k = 0; k < 4; ++k) {
+                const int i = tid + k * kB2Threads;
+                vals[k] = i < kB2CH * (kB2CW / 4) ? __ldg(base + (size_t)(i / (kB2CW / 4)) * rstride + i % (kB2CW / 4))
+                                                  : make_int4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = tid + k * kB2Threads;
+                if (i < kB2CH * (kB2CW / 4)) {
+                    const uint32_t p0 = put(vals[k].x) | (put(vals[k].y) << 16);
+                    const uint32_t p1 = put(vals[k].z) | (put(vals[k].w) << 16);
+                    *reinterpret_cast<uint2*>(&cz_s[i / (kB2CW / 4)][(i % (kB2CW / 4)) * 4]) = make_uint2(p0, p1);
+                }
+            }
+        } else {
+            constexpr int kPer = (kB2CH * kB2CW + kB2Threads - 1) / kB2Threads;
+            int vals[kPer];
+#pragma unroll
+            for (int k = 0; k < kPer; ++k) {
+                const int i = tid + k * kB2Threads;
+                const int yy = min(max(y0 - kBandHalo + i / kB2CW, 0), a.Y - 1);
+                const int xx = min(max(x0 - kBandHalo + i % kB2CW, 0), a.X - 1);
+                vals[k] = i < kB2CH * kB2CW ? __ldg(a.zmap + (size_t)yy * a.X + xx) : 0;
+            }
+#pragma unroll
+            for (int k = 0; k < kPer; ++k) {
+                const int i = tid + k * kB2Threads;
+                if (i < kB2CH * kB2CW) cz_s[i / kB2CW][i % kB2CW] = (uint16_t)put(vals[k]);
             }
         }
-        for (int o = 16; o; o >>= 1) {
-            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-        }
+        lo = __reduce_min_sync(0xffffffffu, lo);
+        hi = __reduce_max_sync(0xffffffffu, hi);
+        __syncthreads();                         // zlo_s / zhi_s initialised
         if (lane == 0) {
             atomicMin(&zlo_s, lo);
             atomicMax(&zhi_s, hi);
@@ -720,14 +738,23 @@ __global__ void __launch_bounds__(kB2Threads, 2) band_project3_kernel(const __gr
     const int npl = zend - zbeg + 1;
     const int c0 = blockIdx.z * kBandMaxCh;
     const int ch0 = a.ch[c0], ch1 = a.ch[c0 + (TWO ? 1 : 0)];
-    auto issue = [&](int i) {                                    // one thread per plane: arm the stage, ask the TMA unit
-        const int stage = i % NST;
-        const uint32_t bar = bar_s + 8 * stage, dst = ring_s + stage * STAGE;
-        mbar_expect_tx(bar, STAGE);
-        tma_load_4d(dst, &tmap, x0, y0, zbeg + i, ch0, bar);
-        if (TWO) tma_load_4d(dst + kB3PlaneBytes, &tmap, x0, y0, zbeg + i, ch1, bar);
+    // warp 0: lane 0 arms the barrier of a half ring with its byte count, then one lane per plane asks the TMA unit
+    auto issue_half = [&](int hh) {
+        const int first = hh * HALF, n = min(HALF, npl - first);
+        const uint32_t bar = bar_s + 8 * (hh & 1);
+        if (lane == 0) mbar_expect_tx(bar, (uint32_t)n * STAGE);
+        __syncwarp();
+        if (lane < n) {
+            const int i = first + lane;
+            const uint32_t dst = ring_s + (i % NST) * STAGE;
+            tma_load_4d(dst, &tmap, x0, y0, zbeg + i, ch0, bar);
+            if (TWO) tma_load_4d(dst + kB3PlaneBytes, &tmap, x0, y0, zbeg + i, ch1, bar);
+        }
     };
-    if (tid < NST && tid < npl) issue(tid);
+    if (warp == 0) {
+        issue_half(0);
+        if (npl > HALF) issue_half(1);
+    }
 
     const float one_val = lut_lo[511] + lut_hi[255];
     const int g = tid & 7, row = tid >> 3;                     // 8 pixels x0+8g .. +7 of row y0+row
@@ -739,92 +766,93 @@ __global__ void __launch_bounds__(kB2Threads, 2) band_project3_kernel(const __gr
     asm volatile("" : "+r"(magic));
     const unsigned char* my_vox = b3_ring + row * (kBandTX * 2) + g * 16;
 
-    // ballots of plane t into rowmask[buf] (+ the zeroed column mask of that plane)
-    auto build_masks = [&](int t, int buf, int cb) {
+    // indicator masks of planes t0 .. t0+3 into rowmask[cbuf] (+ which of them this warp saw)
+    auto build_masks = [&](int t0, int cbuf) {
+        uint32_t anyp[kB3Chunk] = {0, 0, 0, 0};
 #pragma unroll
         for (int rr = 0; rr < kB2CH / 8; ++rr) {
             const int r = warp + 8 * rr;
-            uint32_t mine = 0;
+            const int v0 = cz_s[r][lane], v1 = cz_s[r][32 + lane];
+            const int v2 = lane < kB2CW - 64 ? cz_s[r][64 + lane] : -1;
+            uint4 mine = make_uint4(0, 0, 0, 0);
 #pragma unroll
-            for (int seg = 0; seg < 3; ++seg) {
-                const int col = 32 * seg + lane;
-                const int v = col < kB2CW ? cz_s[r][col] : -1;
-                const uint32_t b = __ballot_sync(0xffffffffu, v == t);
-                if (lane == seg) mine = b;
+            for (int p = 0; p < kB3Chunk; ++p) {
+                const uint32_t b0 = __ballot_sync(0xffffffffu, v0 == t0 + p);
+                const uint32_t b1 = __ballot_sync(0xffffffffu, v1 == t0 + p);
+                const uint32_t b2 = __ballot_sync(0xffffffffu, v2 == t0 + p);
+                anyp[p] |= b0 | b1 | b2;
+                if (lane == p) mine = make_uint4(b0, b1, b2, 0u);
             }
-            if (lane < 4) rowmask[buf][r][lane] = mine;          // word 3 = 0
+            if (lane < kB3Chunk) *reinterpret_cast<uint4*>(&rowmask[cbuf][lane][r][0]) = mine;
         }
-        if (tid < 8) colbits[cb][tid] = 0ull;
+        if (lane == 0)
+            pres[cbuf][warp] = (anyp[0] ? 1u : 0u) | (anyp[1] ? 2u : 0u) | (anyp[2] ? 4u : 0u) | (anyp[3] ? 8u : 0u);
     };
-    auto next_present = [&](int t) {                             // smallest present plane > t, or INT_MAX
-        for (int q = t + 1; q <= zhi; ++q)
-            if ((present[q >> 5] >> (q & 31)) & 1u) return q;
-        return INT32_MAX;
-    };
-    // x pass of the plane whose masks are in rowmask[buf]: r_s[buf] and colbits[cb]
-    auto x_pass = [&](int buf, int cb) {
+    // x pass of plane (cbuf, p): r_s[buf] and rownz[buf]
+    auto x_pass = [&](int cbuf, int p, int buf) {
 #pragma unroll
         for (int round = 0; round < 2; ++round) {
             const int r = round * 32 + row;
             if (round == 1 && r >= kB2CH) break;                 // warp-uniform (warps 0..3 take the second round)
-            const uint4 m = *reinterpret_cast<const uint4*>(&rowmask[buf][r][0]);
+            const uint4 m = *reinterpret_cast<const uint4*>(&rowmask[cbuf][p][r][0]);
             const uint32_t wlo = g < 4 ? m.x : m.y, whi = g < 4 ? m.y : m.z;
             const uint32_t W = __funnelshift_r(wlo, whi, 8 * (g & 3)) & 0xFFFFFFu;
             float o[8];
             if (W == 0u) {
 #pragma unroll
-                for (int p = 0; p < 8; ++p) o[p] = 0.f;
+                for (int q = 0; q < 8; ++q) o[q] = 0.f;
             } else if (W == 0xFFFFFFu) {
 #pragma unroll
-                for (int p = 0; p < 8; ++p) o[p] = one_val;
+                for (int q = 0; q < 8; ++q) o[q] = one_val;
             } else {
 #pragma unroll
-                for (int p = 0; p < 8; ++p) o[p] = lut_lo[(W >> p) & 511u] + lut_hi[(W >> (p + 9)) & 255u];
+                for (int q = 0; q < 8; ++q) o[q] = lut_lo[(W >> q) & 511u] + lut_hi[(W >> (q + 9)) & 255u];
             }
             float4* dst = reinterpret_cast<float4*>(&r_s[buf][r][0]);
             dst[g] = make_float4(o[0], o[1], o[2], o[3]);
             dst[8 + g] = make_float4(o[4], o[5], o[6], o[7]);
             const uint32_t B = __ballot_sync(0xffffffffu, W != 0u);          // bit 8*rr + g, rows 4*warp + rr
-            if (lane < 8) {
-                const uint32_t nib = ((B >> lane) & 1u) | (((B >> (lane + 8)) & 1u) << 1) |
-                                     (((B >> (lane + 16)) & 1u) << 2) | (((B >> (lane + 24)) & 1u) << 3);
-                if (nib) atomicOr(&colbits[cb][lane], (unsigned long long)nib << (round * 32 + 4 * warp));
-            }
+            if (lane == 0) rownz[buf][round * 8 + warp] = B;
         }
     };
 
-    float2 win[4][11];            // pending masks of planes t-4 .. t+4(+2), two pixels per entry
+    float2 win[4][9];             // pending masks, slot of plane z = (z - (zlo - 4)) mod 9; two pixels per entry
     float2 best0[4], best1[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
 #pragma unroll
-        for (int i = 0; i < 11; ++i) win[q][i] = make_float2(0.f, 0.f);
+        for (int i = 0; i < 9; ++i) win[q][i] = make_float2(0.f, 0.f);
         best0[q] = best1[q] = make_float2(0.f, 0.f);
     }
     int live = 0;
 
-    int buf = 0, cb = 0;
-    build_masks(zlo, 0, 0);                      // zlo is always present
+    build_masks(zlo, 0);
     __syncthreads();
 
-    for (int tb = zlo; tb <= zhi + 8; tb += 3) {
+    int buf = 0, slot = 0;
+    uint32_t havebits = 0;
+    for (int t = zlo; t <= zhi + 8; ++t) {
+        const int rel = t - zlo, cbuf = (rel >> 2) & 1, pin = rel & 3;
+        bool scatter = false;
+        float2 an[4];
 #pragma unroll
-        for (int u = 0; u < 3; ++u) {
-            const int t = tb + u;
-            if (t > zhi + 8) break;                                    // block-uniform
-            const bool have = t <= zhi && ((present[t >> 5] >> (t & 31)) & 1u);
-            if (have) {                                                // block-uniform
-                x_pass(buf, cb);
-                const int tn = next_present(t);
-                const int cbn = cb == 2 ? 0 : cb + 1;
-                if (tn != INT32_MAX) build_masks(tn, buf ^ 1, cbn);
+        for (int q = 0; q < 4; ++q) an[q] = make_float2(0.f, 0.f);
+        if (t <= zhi) {                                            // block-uniform
+            // the chunk's flags are read once, right behind the barrier that published them: pres[cbuf] is rewritten
+            // by the next chunk's first plane, which absent planes do not separate from this one by a barrier
+            if (pin == 0) {
+                const uint4 pa = *reinterpret_cast<const uint4*>(&pres[cbuf][0]);
+                const uint4 pb = *reinterpret_cast<const uint4*>(&pres[cbuf][4]);
+                havebits = pa.x | pa.y | pa.z | pa.w | pb.x | pb.y | pb.z | pb.w;
+            }
+            const bool have = (havebits >> pin) & 1u;
+            if (have) {
+                x_pass(cbuf, pin, buf);
+                if (pin == 0 && t + kB3Chunk <= zhi) build_masks(t + kB3Chunk, cbuf ^ 1);
                 __syncthreads();
-                // y pass: a_new = sum_dy w2[dy] * r_s[row + dy][8g ..], skipped by warps that see only zeros
-                const bool mine = ((colbits[cb][g] >> row) & 0x1FFFFull) != 0ull;
-                if (__any_sync(0xffffffffu, mine)) {
-                    float2 an[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) an[q] = make_float2(0.f, 0.f);
+                // y pass: a_new = sum_dy w2[dy] * r_s[row + dy][8g ..], skipped by warps whose 20 rows see only zeros
+                const uint32_t* nzw = &rownz[buf][warp];
+                if ((nzw[0] | nzw[1] | nzw[2] | nzw[3] | nzw[4]) != 0u) {
 #pragma unroll
                     for (int dy = 0; dy < 17; ++dy) {
                         const float4* src = reinterpret_cast<const float4*>(&r_s[buf][row + dy][0]);
@@ -835,69 +863,81 @@ __global__ void __launch_bounds__(kB2Threads, 2) band_project3_kernel(const __gr
                         an[2] = __ffma2_rn(make_float2(hi4.x, hi4.y), w, an[2]);
                         an[3] = __ffma2_rn(make_float2(hi4.z, hi4.w), w, an[3]);
                     }
-                    if (mine) {
-                        live = 9;
-                        const bool edge = t - 4 < 4 || t + 4 > a.Z - 5;
-#pragma unroll
-                        for (int k = 0; k < 9; ++k) {
-                            const int z = t - 4 + k;
-                            float2 w = c_w1p[8 - k];
-                            if (edge) {
-                                const float we = (z >= 0 && z < a.Z) ? __ldg(a.wz + z * 9 + (8 - k)) : 0.f;
-                                w = make_float2(we, we);
-                            }
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) win[q][u + k] = __ffma2_rn(w, an[q], win[q][u + k]);
-                        }
-                    }
+                    scatter = true;
+                    live = 9;
                 }
                 buf ^= 1;
-                cb = cbn;
+            } else if (pin == 0 && t + kB3Chunk <= zhi) {
+                build_masks(t + kB3Chunk, cbuf ^ 1);
+                __syncthreads();
             }
-            const int z = t - 4;
-            if (z >= zbeg && z <= zend) {                              // block-uniform
-                const int i = z - zbeg, stage = i % NST;
-                mbar_wait(bar_s + 8 * stage, (uint32_t)(i / NST) & 1u);
-                if (live > 0) {
-                    const uint4 cur0 = *reinterpret_cast<const uint4*>(my_vox + stage * STAGE);
-                    const uint32_t w0[4] = {cur0.x, cur0.y, cur0.z, cur0.w};
-                    uint32_t w1[4] = {0, 0, 0, 0};
-                    if (TWO) {
-                        const uint4 cur1 = *reinterpret_cast<const uint4*>(my_vox + stage * STAGE + kB3PlaneBytes);
-                        w1[0] = cur1.x; w1[1] = cur1.y; w1[2] = cur1.z; w1[3] = cur1.w;
-                    }
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float2 m = win[q][u];
-                        float2 f = __fadd2_rn(make_float2(band_u16f_lo(w0[q], magic), band_u16f_hi(w0[q], magic)), nbias);
-                        if (AIRY) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); }
-                        const float2 pr = __fmul2_rn(f, m);
-                        best0[q].x = fmaxf(best0[q].x, pr.x);
-                        best0[q].y = fmaxf(best0[q].y, pr.y);
-                        if (TWO) {
-                            float2 f1 = __fadd2_rn(make_float2(band_u16f_lo(w1[q], magic), band_u16f_hi(w1[q], magic)), nbias);
-                            if (AIRY) { f1.x = fmaxf(f1.x, 0.f); f1.y = fmaxf(f1.y, 0.f); }
-                            const float2 pr1 = __fmul2_rn(f1, m);
-                            best1[q].x = fmaxf(best1[q].x, pr1.x);
-                            best1[q].y = fmaxf(best1[q].y, pr1.y);
-                        }
-                    }
-                }
-                // half a ring consumed and planes still to come: refill those stages
-                if ((i % HALF) == HALF - 1 && (i / HALF + 2) * HALF < npl) {
-                    __syncthreads();
-                    const int j = (i / HALF + 2) * HALF + tid;
-                    if (tid < HALF && j < npl) issue(j);
-                }
-            }
-            live -= live > 0;
         }
-        // slide the window by 3 planes
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) win[q][i] = win[q][i + 3];
-            win[q][8] = win[q][9] = win[q][10] = make_float2(0.f, 0.f);
+        // voxels of plane z = t - 4 (all threads wait at the first plane of each half ring)
+        const int z = t - 4;
+        const bool walk = z >= zbeg && z <= zend;                  // block-uniform
+        uint4 cur0 = make_uint4(0, 0, 0, 0), cur1 = cur0;
+        int i = 0;
+        if (walk) {
+            i = z - zbeg;
+            const int stage = i % NST;
+            if (i % HALF == 0) mbar_wait(bar_s + 8 * ((i / HALF) & 1), (uint32_t)(i / NST) & 1u);
+            if (live > 0) {
+                cur0 = *reinterpret_cast<const uint4*>(my_vox + stage * STAGE);
+                if (TWO) cur1 = *reinterpret_cast<const uint4*>(my_vox + stage * STAGE + kB3PlaneBytes);
+            }
+        }
+        const bool mult = walk && live > 0;
+        const bool edge = t - 4 < 4 || t + 4 > a.Z - 5;
+        // plane t feeds the masks of z = t-4+k (slot (S+k) mod 9) with the (z, t) entry of the edge-replicating z
+        // matrix (interior rows: the plain sigma=1 taps); then slot S = plane t-4 is complete: weighted max, clear
+#define TSP_B3_CASE(S)                                                                                              \
+    case S: {                                                                                                       \
+        if (scatter) {                                                                                              \
+            _Pragma("unroll") for (int k = 0; k < 9; ++k) {                                                         \
+                float2 w = c_w1p[8 - k];                                                                            \
+                if (edge) {                                                                                         \
+                    const int zz = t - 4 + k;                                                                       \
+                    const float we = (zz >= 0 && zz < a.Z) ? __ldg(a.wz + zz * 9 + (8 - k)) : 0.f;                  \
+                    w = make_float2(we, we);                                                                        \
+                }                                                                                                   \
+                _Pragma("unroll") for (int q = 0; q < 4; ++q)                                                       \
+                    win[q][(S + k) % 9] = __ffma2_rn(w, an[q], win[q][(S + k) % 9]);                                \
+            }                                                                                                       \
+        }                                                                                                           \
+        if (mult) {                                                                                                 \
+            const uint32_t w0[4] = {cur0.x, cur0.y, cur0.z, cur0.w};                                                \
+            const uint32_t w1[4] = {cur1.x, cur1.y, cur1.z, cur1.w};                                                \
+            _Pragma("unroll") for (int q = 0; q < 4; ++q) {                                                         \
+                const float2 m = win[q][S];                                                                         \
+                float2 f = __fadd2_rn(make_float2(band_u16f_lo(w0[q], magic), band_u16f_hi(w0[q], magic)), nbias);  \
+                if (AIRY) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); }                                         \
+                const float2 pr = __fmul2_rn(f, m);                                                                 \
+                best0[q].x = fmaxf(best0[q].x, pr.x);                                                               \
+                best0[q].y = fmaxf(best0[q].y, pr.y);                                                               \
+                if (TWO) {                                                                                          \
+                    float2 f1 = __fadd2_rn(make_float2(band_u16f_lo(w1[q], magic), band_u16f_hi(w1[q], magic)), nbias); \
+                    if (AIRY) { f1.x = fmaxf(f1.x, 0.f); f1.y = fmaxf(f1.y, 0.f); }                                 \
+                    const float2 pr1 = __fmul2_rn(f1, m);                                                           \
+                    best1[q].x = fmaxf(best1[q].x, pr1.x);                                                          \
+                    best1[q].y = fmaxf(best1[q].y, pr1.y);                                                          \
+                }                                                                                                   \
+            }                                                                                                       \
+        }                                                                                                           \
+        _Pragma("unroll") for (int q = 0; q < 4; ++q) win[q][S] = make_float2(0.f, 0.f);                            \
+    } break;
+        if (scatter || live > 0) {
+            switch (slot) {
+                TSP_B3_CASE(0) TSP_B3_CASE(1) TSP_B3_CASE(2) TSP_B3_CASE(3) TSP_B3_CASE(4)
+                TSP_B3_CASE(5) TSP_B3_CASE(6) TSP_B3_CASE(7) TSP_B3_CASE(8)
+            }
+        }
+#undef TSP_B3_CASE
+        slot = slot == 8 ? 0 : slot + 1;
+        live -= live > 0;
+        // half a ring consumed and planes still to come: refill those stages
+        if (walk && (i % HALF) == HALF - 1 && (i / HALF + 2) * HALF < npl) {
+            __syncthreads();
+            if (warp == 0) issue_half(i / HALF + 2);
         }
     }
     if (inside) {
@@ -912,8 +952,8 @@ __global__ void __launch_bounds__(kB2Threads, 2) band_project3_kernel(const __gr
     }
 }
 
-constexpr int kB3Smem1 = 16 * kB3PlaneBytes + 16 * 8;
-constexpr int kB3Smem2 = 8 * 2 * kB3PlaneBytes + 8 * 8;
+constexpr int kB3Smem1 = 16 * kB3PlaneBytes + 16;
+constexpr int kB3Smem2 = 8 * 2 * kB3PlaneBytes + 16;
 
 // (X, Y, Z, C) map of the cropped stack, boxes of 64 x 32 x 1 x 1, zero fill outside
 static int make_band_tensor_map(const uint16_t* base, size_t channel_stride, int C, int Z, int Y, int X,
@@ -932,6 +972,35 @@ static int make_band_tensor_map(const uint16_t* base, size_t channel_stride, int
         set_error("cuTensorMapEncodeTiled failed (%d) for the band stage C=%d Z=%d Y=%d X=%d", (int)r, C, Z, Y, X);
         return TSP_ERR_CUDA;
     }
+    return TSP_OK;
+}
+
+// x-blur lookup tables of band_project3_kernel: the sigma=2 response of a binary row, split into taps 0..8 and 9..16
+// (float sums in tap order, as the kernels that build them on the fly do)
+static int get_band_lut(tsp_handle* h, const float** out) {
+    std::lock_guard<std::mutex> lock(h->mu);
+    auto it = h->tables.find("band_lut");
+    if (it != h->tables.end()) {
+        *out = (const float*)it->second;
+        return TSP_OK;
+    }
+    std::vector<double> w2 = gaussian_taps(2.0);
+    std::vector<float> tab(768);
+    for (int i = 0; i < 512; ++i) {
+        float s = 0.f;
+        for (int k = 0; k < 9; ++k) s += ((i >> k) & 1) ? (float)w2[k] : 0.f;
+        tab[i] = s;
+    }
+    for (int i = 0; i < 256; ++i) {
+        float s = 0.f;
+        for (int k = 0; k < 8; ++k) s += ((i >> k) & 1) ? (float)w2[9 + k] : 0.f;
+        tab[512 + i] = s;
+    }
+    float* d = nullptr;
+    TSP_CUDA(cudaMalloc(&d, tab.size() * sizeof(float)));
+    TSP_CUDA(cudaMemcpy(d, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice));
+    h->tables["band_lut"] = d;
+    *out = d;
     return TSP_OK;
 }
 
@@ -1062,9 +1131,14 @@ int launch_band_project_ex(tsp_handle* h, const uint16_t* d_stack, size_t channe
     const float* wz = nullptr;
     int rc = get_wz_table(h, Z, &wz);
     if (rc) return rc;
+    const float* lut = nullptr;
+    rc = get_band_lut(h, &lut);
+    if (rc) return rc;
     rc = launch_band_range(h, d_zmap, Z, Y, X, shift, d_status, range_known, s);
     if (rc) return rc;
     BandArgs a;
+    a.lut = lut;
+    a.zvec = (X % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_zmap) & 15) == 0) ? 1 : 0;
     a.stack = d_stack;
     a.channel_stride = channel_stride;
     a.z0_offset = z0_offset;

@@ -1,19 +1,21 @@
 """Per-source-line instruction counts and stall samples of one kernel in an .ncu-rep (needs -lineinfo and
---import-source on):  python tools/ncu_lines.py rep [top]"""
+--import-source on):  python tools/ncu_lines.py rep kernel_regex [top]"""
 import csv, subprocess, sys, collections
-rep = sys.argv[1]
-top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"],
+rep, kre = sys.argv[1], sys.argv[2]
+top = int(sys.argv[3]) if len(sys.argv) > 3 else 30
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "-k", "regex:" + kre],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr = None
 per = collections.OrderedDict()
 cur = None
+seen = set()
 for r in rows:
     if len(r) > 6 and r[0] == "Line No":
         hdr = r
         ix = hdr.index("Instructions Executed")
         sx = hdr.index("# Samples")
+        ax = 2
         continue
     if hdr is None or len(r) <= ix:
         continue
@@ -24,7 +26,8 @@ for r in rows:
         n, s = int(r[ix]), int(r[sx])
     except ValueError:
         continue
-    if cur is not None and r[2].strip():
+    if cur is not None and r[ax].strip() and r[ax] not in seen:     # every SASS address once
+        seen.add(r[ax])
         per[cur][0] += n
         per[cur][1] += s
         per[cur][2] += 1
