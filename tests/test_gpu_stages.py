@@ -121,18 +121,33 @@ def test_band_projection_from_oracle_height_map(nat, shift, ref):
 
 
 @pytest.mark.parametrize("shape,C,shift,noisy", [((40, 96, 128), 1, 0, True), ((37, 70, 200), 2, 0, True),
-                                                 ((21, 64, 64), 3, 2, False), ((30, 33, 72), 2, -2, True)])
+                                                 ((21, 64, 64), 3, 2, False), ((30, 33, 72), 2, -2, True),
+                                                 ((44, 160, 192), 1, 0, "gappy"), ((35, 96, 136), 2, 0, "gappy"),
+                                                 ((26, 160, 256), 2, 0, "mixed"), ((19, 96, 192), 3, -1, "mixed"),
+                                                 ((6, 64, 128), 1, 0, "mixed"), ((64, 256, 320), 1, 0, False)])
 def test_band_projection_tma_ring(nat, shape, C, shift, noisy, monkeypatch):
-    """TMA path of the band stage (X % 8 == 0, tile inside the image): plane ranges deeper than the ring (a noisy
-    height map walks every plane, refilling the ring), one / two / three channels, shifted masks; against the
-    oracle and bit for bit against the register-prefetch kernel (TSP_BAND_V2=1), which does the same arithmetic."""
+    """TMA path of the band stage (X % 8 == 0, tile inside the image): shallow tiles in the register kernel, plane
+    ranges deeper than the ring (a noisy height map walks every plane, refilling the ring) through the worklist, one /
+    two / three channels, shifted masks; against the oracle and bit for bit against the older kernels
+    (TSP_BAND_V3=1, TSP_BAND_V2=1), which do the same arithmetic in the same order."""
     Z, Y, X = shape
     img = synth.synth_stack(Z, Y, X, C=C, seed=sum(shape))
     if img.ndim == 3:
         img = img[None]
     rng = np.random.default_rng(7)
     hi = Z - 1 - max(shift, 0)
-    if noisy:
+    if noisy == "gappy":           # few distinct heights: most planes of a tile's range are absent (skipped sweeps)
+        levels = np.array([1, 2, 9, 10, 11, 23, hi - 3, hi])
+        zmap = levels[rng.integers(0, levels.size, size=(Y, X))].astype(np.int64)
+        zmap[: Y // 2, : X // 2] = 12
+    elif noisy == "mixed":         # shallow tiles (register kernel) next to deep ones (worklist), surfaces at both stack ends
+        zmap = np.clip(synth.height_field(Z, Y, X).astype(np.int64), 0, hi)
+        zmap[:40, :70] = 0
+        zmap[:40, 70:140] = hi
+        zmap[40:56, :64] = 1
+        zmap[-32:, -64:] = rng.integers(0, hi + 1, size=(32, 64))
+        zmap[Y // 2, X // 2] = min(hi, zmap[Y // 2, X // 2] + 3)
+    elif noisy:
         zmap = rng.integers(0, hi + 1, size=(Y, X)).astype(np.int64)
     else:
         zmap = np.clip(synth.height_field(Z, Y, X).astype(np.int64), 0, hi)
@@ -141,9 +156,10 @@ def test_band_projection_tma_ring(nat, shape, C, shift, noisy, monkeypatch):
     want = orc.project_channels(image, 0, orc.band_mask(zmap, Z), orc.band_mask(z_other, Z))
     got = nat.band_project(_cuda(img), _cuda(zmap.astype(np.int32)), reference_channel=0, atoh_shift=shift).cpu().numpy()
     np.testing.assert_allclose(got, want, rtol=1e-5, atol=0)
-    monkeypatch.setenv("TSP_BAND_V2", "1")
-    alt = nat.band_project(_cuda(img), _cuda(zmap.astype(np.int32)), reference_channel=0, atoh_shift=shift).cpu().numpy()
-    assert np.array_equal(got, alt)
+    for variant in ("TSP_BAND_V3", "TSP_BAND_V2"):      # generic TMA kernel alone; register-prefetch kernel
+        monkeypatch.setenv(variant, "1")
+        alt = nat.band_project(_cuda(img), _cuda(zmap.astype(np.int32)), reference_channel=0, atoh_shift=shift).cpu().numpy()
+        assert np.array_equal(got, alt), variant
 
 
 def test_band_projection_index_error(nat):

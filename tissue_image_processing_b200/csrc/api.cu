@@ -208,6 +208,8 @@ int tsp_project_frame(tsp_handle* h, const tsp_frame_desc* desc, const uint16_t*
     const int ped = desc->airyscan ? kAiryscanPedestal : 0;
     const uint16_t* ref = d_stack + (size_t)desc->reference_channel * chan_stride + z0_off;
 
+    // the percentile scratch is idle again by the time the band stage runs: it holds the deep-tile worklist
+    int* worklist = band_worklist_bytes(Y, X) <= percentile_scratch_bytes() ? (int*)w.hist : nullptr;
     prof_mark(h, s, -1);
     const bool fast = desc->mode == TSP_MODE_FAST;
     rc = launch_percentile(h, ref, nvox, ped, w.status, w.hist, s, fast ? w.fast : nullptr,
@@ -219,7 +221,7 @@ int tsp_project_frame(tsp_handle* h, const tsp_frame_desc* desc, const uint16_t*
         rc = launch_fast_score_argmax(h, ref, d_zmap, c.zc, Y, X, ped, c.z_offset, w.status, w.fast, s, true);
         if (rc) return rc;
         rc = launch_band_project_ex(h, d_stack, chan_stride, z0_off, d_zmap, d_proj, C, c.zc, Y, X,
-                                    desc->reference_channel, desc->atoh_shift, ped, w.status, true, s);
+                                    desc->reference_channel, desc->atoh_shift, ped, w.status, true, s, worklist);
         prof_mark(h, s, STG_BAND);
         return rc;
     }
@@ -244,7 +246,7 @@ int tsp_project_frame(tsp_handle* h, const tsp_frame_desc* desc, const uint16_t*
                                              w.status, true, s);
     else
         rc = launch_band_project_ex(h, d_stack, chan_stride, z0_off, d_zmap, d_proj, C, c.zc, Y, X,
-                                    desc->reference_channel, desc->atoh_shift, ped, w.status, true, s);
+                                    desc->reference_channel, desc->atoh_shift, ped, w.status, true, s, worklist);
     prof_mark(h, s, STG_BAND);
     return rc;
 }
@@ -484,7 +486,10 @@ int tsp_argmax_z_f32(tsp_handle* h, const float* d_score, int32_t* d_zmap, int p
     return launch_argmax(h, d_score, d_zmap, planes, rows, cols, z_offset, nullptr, (cudaStream_t)cuda_stream);
 }
 
-size_t tsp_band_workspace_bytes(int, int, int, int) { return align_up(kStatusWords * sizeof(int32_t), 256); }
+// [status block][worklist of the tiles the shallow-range band kernel leaves to the generic one]
+size_t tsp_band_workspace_bytes(int, int, int rows, int cols) {
+    return align_up(kStatusWords * sizeof(int32_t), 256) + align_up(band_worklist_bytes(rows, cols), 256);
+}
 
 int tsp_band_project(tsp_handle* h, const uint16_t* d_stack, const int32_t* d_zmap, float* d_proj, int channels,
                      int planes, int rows, int cols, int reference_channel, int atoh_shift, int airyscan,
@@ -498,7 +503,8 @@ int tsp_band_project(tsp_handle* h, const uint16_t* d_stack, const int32_t* d_zm
     const size_t plane = (size_t)rows * cols;
     return launch_band_project_ex(h, d_stack, (size_t)planes * plane, 0, d_zmap, d_proj, channels, planes, rows,
                                   cols, reference_channel, atoh_shift, airyscan ? kAiryscanPedestal : 0,
-                                  (int32_t*)d_workspace, false, s);
+                                  (int32_t*)d_workspace, false, s,
+                                  (int*)((char*)d_workspace + align_up(kStatusWords * sizeof(int32_t), 256)));
 }
 
 size_t tsp_project_m_workspace_bytes(int planes, int rows, int cols, int bin_size) {

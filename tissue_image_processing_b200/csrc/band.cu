@@ -81,7 +81,8 @@ __global__ void zmap_range_init_kernel(int32_t* status) {
 
 // the reference indexes the cropped stack with chosen_z (and clip(chosen_z+shift, 0, Z), upper bound
 // inclusive): any index >= Z raises IndexError; negative indices cannot occur.
-__global__ void band_check_kernel(int32_t* status, int Z, int shift, int decode) {
+__global__ void band_check_kernel(int32_t* status, int Z, int shift, int decode, int* worklist) {
+    if (worklist) worklist[0] = 0;
     if (decode) status[ST_ZMIN] = INT32_MAX - status[ST_ZMIN_INV];     // argmax kernels keep max(INT_MAX - z)
     const int hi = status[ST_ZMAX];
     int err = hi >= Z;
@@ -118,6 +119,8 @@ struct BandArgs {
     int vec;                    // rows are 16-byte aligned: uint4 loads
     int zvec;                   // height-map rows are 16-byte aligned: int4 loads
     const float* lut;           // x-blur lookup tables of a binary row: [512] taps 0..8, [256] taps 9..16
+    int* worklist;              // [0] = count, [1..] = linear tile ids left to the deep-range kernel (may be null)
+    int use_list;               // band_project3_kernel: take the tile from the worklist instead of blockIdx
     int ch[16];
 };
 
@@ -664,7 +667,15 @@ __global__ void __launch_bounds__(kB2Threads, 2) band_project3_kernel(const __gr
     if (a.status[ST_BAND_ERR]) return;          // the reference raises before projecting
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int x0 = blockIdx.x * kBandTX, y0 = blockIdx.y * kBandTY;
+    int bx = blockIdx.x, by = blockIdx.y;
+    if (a.use_list) {                           // the tiles band_project4_kernel left behind
+        const int lin = by * gridDim.x + bx;
+        if (lin >= a.worklist[0]) return;
+        const int tile = a.worklist[1 + lin];
+        bx = tile % gridDim.x;
+        by = tile / gridDim.x;
+    }
+    const int x0 = bx * kBandTX, y0 = by * kBandTY;
     const uint32_t ring_s = smem_u32(b3_ring);
     const uint32_t bar_s = ring_s + NST * STAGE;
     if (tid == 0) {
@@ -952,6 +963,256 @@ __global__ void __launch_bounds__(kB2Threads, 2) band_project3_kernel(const __gr
     }
 }
 
+
+// ---- K5-K7 fused, shallow-range kernel ---------------------------------------------------------------
+// The sigma=30 score makes height maps smooth: in almost every 32 x 64 tile (with its 8-pixel halo) the heights span
+// at most kB4NP planes.  For those tiles the pending-mask window of band_project3_kernel (72 registers, a switch per
+// plane, a barrier-separated pipeline per plane) is not needed:
+//   * the XY-blurred indicator planes A[zlo + j], j < kB4NP, are computed first and stay in registers (40);
+//   * the walk over z = zlo-4 .. zhi+4 (at most kB4NW planes, all requested from the TMA unit at once, one mbarrier)
+//     forms mask(z) = sum_j wz(z, zlo+j) A[j] on the fly - ascending j, the very FMA sequence of the scatter form, so
+//     the results are bit-identical - multiplies and keeps the maximum; everything is unrolled against compile-time
+//     (walk step, slot) pairs, the z weights come from a per-tile shared table (edge replication included);
+//   * 80 registers and 73 KB of shared memory: three CTAs per SM instead of two.
+// Tiles with a deeper range are appended to a worklist and done by band_project3_kernel (use_list) afterwards.
+constexpr int kB4NP = 5;
+constexpr int kB4NW = kB4NP + 8;
+constexpr int kB4Smem = kB4NW * kB3PlaneBytes + 16;
+
+template <bool AIRY>
+__global__ void __launch_bounds__(kB2Threads, 3) band_project4_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                      const BandArgs a) {
+    extern __shared__ __align__(128) unsigned char b4_ring[];     // [kB4NW][4096] + 1 mbarrier
+    __shared__ __align__(16) float r_s[kB2CH][kBandTX];           // x-blurred plane; before that the uint16 height tile
+    __shared__ __align__(16) uint32_t rowmask[kB4NP][kB2CH][4];
+    __shared__ __align__(16) float2 wtab[kB4NW][kB4NP + 1];       // (w, w): weight of A[j] in mask(zlo - 4 + i)
+    __shared__ float lut_lo[512], lut_hi[256];
+    __shared__ uint32_t rownz[12];
+    __shared__ uint32_t pres[8];
+    __shared__ int zlo_s, zhi_s;
+    uint16_t (*cz_s)[kB2CW] = reinterpret_cast<uint16_t (*)[kB2CW]>(&r_s[0][0]);
+
+    if (a.status[ST_BAND_ERR]) return;          // the reference raises before projecting
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int x0 = blockIdx.x * kBandTX, y0 = blockIdx.y * kBandTY;
+    const uint32_t ring_s = smem_u32(b4_ring);
+    const uint32_t bar_s = ring_s + kB4NW * kB3PlaneBytes;
+    if (tid == 0) {
+        zlo_s = INT32_MAX;
+        zhi_s = INT32_MIN;
+        mbar_init(bar_s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    lut_lo[tid] = __ldg(a.lut + tid);
+    lut_lo[256 + tid] = __ldg(a.lut + 256 + tid);
+    lut_hi[tid] = __ldg(a.lut + 512 + tid);
+    {
+        int lo = INT32_MAX, hi = INT32_MIN;
+        auto put = [&](int v) {
+            if (a.shift != 0) v = min(max(v + a.shift, 0), a.Z);
+            lo = min(lo, v);
+            hi = max(hi, v);
+            return (uint32_t)v;
+        };
+        const bool interior = a.zvec && x0 >= kBandHalo && x0 + kBandTX + kBandHalo <= a.X && y0 >= kBandHalo &&
+                              y0 + kBandTY + kBandHalo <= a.Y;
+        if (interior) {                      // 48 rows x 20 int4, no clamping
+            const int4* base = reinterpret_cast<const int4*>(a.zmap + (size_t)(y0 - kBandHalo) * a.X + (x0 - kBandHalo));
+            const size_t rstride = (size_t)a.X / 4;
+            int4 vals[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = tid + k * kB2Threads;
+                vals[k] = i < kB2CH * (kB2CW / 4) ? __ldg(base + (size_t)(i / (kB2CW / 4)) * rstride + i % (kB2CW / 4))
+                                                  : make_int4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = tid + k * kB2Threads;
+                if (i < kB2CH * (kB2CW / 4)) {
+                    const uint32_t p0 = put(vals[k].x) | (put(vals[k].y) << 16);
+                    const uint32_t p1 = put(vals[k].z) | (put(vals[k].w) << 16);
+                    *reinterpret_cast<uint2*>(&cz_s[i / (kB2CW / 4)][(i % (kB2CW / 4)) * 4]) = make_uint2(p0, p1);
+                }
+            }
+        } else {
+            constexpr int kPer = (kB2CH * kB2CW + kB2Threads - 1) / kB2Threads;
+            int vals[kPer];
+#pragma unroll
+            for (int k = 0; k < kPer; ++k) {
+                const int i = tid + k * kB2Threads;
+                const int yy = min(max(y0 - kBandHalo + i / kB2CW, 0), a.Y - 1);
+                const int xx = min(max(x0 - kBandHalo + i % kB2CW, 0), a.X - 1);
+                vals[k] = i < kB2CH * kB2CW ? __ldg(a.zmap + (size_t)yy * a.X + xx) : 0;
+            }
+#pragma unroll
+            for (int k = 0; k < kPer; ++k) {
+                const int i = tid + k * kB2Threads;
+                if (i < kB2CH * kB2CW) cz_s[i / kB2CW][i % kB2CW] = (uint16_t)put(vals[k]);
+            }
+        }
+        lo = __reduce_min_sync(0xffffffffu, lo);
+        hi = __reduce_max_sync(0xffffffffu, hi);
+        __syncthreads();                         // zlo_s / zhi_s initialised
+        if (lane == 0) {
+            atomicMin(&zlo_s, lo);
+            atomicMax(&zhi_s, hi);
+        }
+    }
+    __syncthreads();
+    const int zlo = zlo_s, zhi = zhi_s;
+    if (zhi - zlo >= kB4NP) {                    // block-uniform: a deep tile goes to the generic kernel
+        if (tid == 0 && blockIdx.z == 0) {
+            const int slot = atomicAdd(a.worklist, 1);
+            a.worklist[1 + slot] = blockIdx.y * gridDim.x + blockIdx.x;
+        }
+        return;
+    }
+    // planes the walk multiplies: z = zlo-4 .. zhi+4 inside the stack, all in flight at once
+    const int zbeg = max(zlo - 4, 0), zend = min(zhi + 4, a.Z - 1);
+    const int npl = zend - zbeg + 1;
+    const int ch = a.ch[blockIdx.z];
+    if (warp == 0) {
+        if (lane == 0) mbar_expect_tx(bar_s, (uint32_t)npl * kB3PlaneBytes);
+        __syncwarp();
+        if (lane < npl) tma_load_4d(ring_s + lane * kB3PlaneBytes, &tmap, x0, y0, zbeg + lane, ch, bar_s);
+    }
+    if (tid < kB4NW * kB4NP) {                   // z weights: row z of the edge-replicating matrix, column zlo + j
+        const int i = tid / kB4NP, j = tid % kB4NP;
+        const int z = zlo - 4 + i, k = j - i + 8;
+        const float w = (z >= 0 && z < a.Z && k >= 0 && k <= 8) ? __ldg(a.wz + z * 9 + k) : 0.f;
+        wtab[i][j] = make_float2(w, w);
+    }
+
+    const float one_val = lut_lo[511] + lut_hi[255];
+    const int g = tid & 7, row = tid >> 3;                     // 8 pixels x0+8g .. +7 of row y0+row
+    const int x = x0 + g * kBandPix, y = y0 + row;
+    const bool inside = y < a.Y && x < a.X;
+
+    // indicator masks of planes zlo .. zlo+4 in one sweep over the height tile (+ which of them this warp saw)
+    {
+        uint32_t seen = 0;
+#pragma unroll
+        for (int rr = 0; rr < kB2CH / 8; ++rr) {
+            const int r = warp + 8 * rr;
+            const int v0 = cz_s[r][lane] - zlo, v1 = cz_s[r][32 + lane] - zlo;
+            const int v2 = lane < kB2CW - 64 ? cz_s[r][64 + lane] - zlo : -1;
+            uint4 mine = make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int p = 0; p < kB4NP; ++p) {
+                const uint32_t b0 = __ballot_sync(0xffffffffu, v0 == p);
+                const uint32_t b1 = __ballot_sync(0xffffffffu, v1 == p);
+                const uint32_t b2 = __ballot_sync(0xffffffffu, v2 == p);
+                if ((b0 | b1 | b2) != 0u) seen |= 1u << p;
+                if (lane == p) mine = make_uint4(b0, b1, b2, 0u);
+            }
+            if (lane < kB4NP) *reinterpret_cast<uint4*>(&rowmask[lane][r][0]) = mine;
+        }
+        if (lane == 0) pres[warp] = seen;
+    }
+    __syncthreads();                             // masks and flags published; the height tile is dead from here on
+    uint32_t havebits;
+    {
+        const uint4 pa = *reinterpret_cast<const uint4*>(&pres[0]);
+        const uint4 pb = *reinterpret_cast<const uint4*>(&pres[4]);
+        havebits = pa.x | pa.y | pa.z | pa.w | pb.x | pb.y | pb.z | pb.w;
+    }
+
+    float2 A[kB4NP][4];
+    bool first = true;
+#pragma unroll
+    for (int j = 0; j < kB4NP; ++j) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) A[j][q] = make_float2(0.f, 0.f);
+        if (!((havebits >> j) & 1u)) continue;                    // block-uniform
+        if (!first) __syncthreads();                              // the previous plane's y pass is done with r_s
+        first = false;
+        // x pass: 17-tap blur of a binary row = two table lookups per pixel
+#pragma unroll
+        for (int round = 0; round < 2; ++round) {
+            const int r = round * 32 + row;
+            if (round == 1 && r >= kB2CH) break;                  // warp-uniform (warps 0..3 take the second round)
+            const uint4 m = *reinterpret_cast<const uint4*>(&rowmask[j][r][0]);
+            const uint32_t wlo = g < 4 ? m.x : m.y, whi = g < 4 ? m.y : m.z;
+            const uint32_t W = __funnelshift_r(wlo, whi, 8 * (g & 3)) & 0xFFFFFFu;
+            float o[8];
+            if (W == 0u) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) o[q] = 0.f;
+            } else if (W == 0xFFFFFFu) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) o[q] = one_val;
+            } else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) o[q] = lut_lo[(W >> q) & 511u] + lut_hi[(W >> (q + 9)) & 255u];
+            }
+            float4* dst = reinterpret_cast<float4*>(&r_s[r][0]);
+            dst[g] = make_float4(o[0], o[1], o[2], o[3]);
+            dst[8 + g] = make_float4(o[4], o[5], o[6], o[7]);
+            const uint32_t B = __ballot_sync(0xffffffffu, W != 0u);
+            if (lane == 0) rownz[round * 8 + warp] = B;
+        }
+        __syncthreads();
+        // y pass, skipped by warps whose 20 rows of the x-blurred plane are all zero
+        const uint32_t* nzw = &rownz[warp];
+        if ((nzw[0] | nzw[1] | nzw[2] | nzw[3] | nzw[4]) != 0u) {
+#pragma unroll
+            for (int dy = 0; dy < 17; ++dy) {
+                const float4* src = reinterpret_cast<const float4*>(&r_s[row + dy][0]);
+                const float4 lo4 = src[g], hi4 = src[8 + g];
+                const float2 w = c_w2p[dy];
+                A[j][0] = __ffma2_rn(make_float2(lo4.x, lo4.y), w, A[j][0]);
+                A[j][1] = __ffma2_rn(make_float2(lo4.z, lo4.w), w, A[j][1]);
+                A[j][2] = __ffma2_rn(make_float2(hi4.x, hi4.y), w, A[j][2]);
+                A[j][3] = __ffma2_rn(make_float2(hi4.z, hi4.w), w, A[j][3]);
+            }
+        }
+    }
+
+    const float nb = -((float)a.pedestal + 8388608.0f);
+    const float2 nbias = make_float2(nb, nb);
+    uint32_t magic = 0x4B000000u;
+    asm volatile("" : "+r"(magic));
+    const unsigned char* my_vox = b4_ring + row * (kBandTX * 2) + g * 16 - (size_t)zbeg * kB3PlaneBytes;
+    float2 best[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) best[q] = make_float2(0.f, 0.f);
+    mbar_wait(bar_s, 0);
+#pragma unroll
+    for (int i = 0; i < kB4NW; ++i) {
+        const int z = zlo - 4 + i;
+        if (z > zend) break;                                       // block-uniform
+        if (z < zbeg) continue;
+        const uint4 cur = *reinterpret_cast<const uint4*>(my_vox + (size_t)z * kB3PlaneBytes);
+        float2 m[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) m[q] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < kB4NP; ++j) {
+            if (j > i || j < i - 8) continue;                      // outside the 9-band: compile time
+            const float2 w = wtab[i][j];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) m[q] = __ffma2_rn(w, A[j][q], m[q]);
+        }
+        const uint32_t w0[4] = {cur.x, cur.y, cur.z, cur.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float2 f = __fadd2_rn(make_float2(band_u16f_lo(w0[q], magic), band_u16f_hi(w0[q], magic)), nbias);
+            if (AIRY) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); }
+            const float2 pr = __fmul2_rn(f, m[q]);
+            best[q].x = fmaxf(best[q].x, pr.x);
+            best[q].y = fmaxf(best[q].y, pr.y);
+        }
+    }
+    if (inside) {
+        float* dst = a.proj + ((size_t)ch * a.Y + y) * a.X + x;
+        reinterpret_cast<float4*>(dst)[0] = make_float4(best[0].x, best[0].y, best[1].x, best[1].y);
+        reinterpret_cast<float4*>(dst)[1] = make_float4(best[2].x, best[2].y, best[3].x, best[3].y);
+    }
+}
+
 constexpr int kB3Smem1 = 16 * kB3PlaneBytes + 16;
 constexpr int kB3Smem2 = 8 * 2 * kB3PlaneBytes + 16;
 
@@ -1048,10 +1309,12 @@ static int get_wz_table(tsp_handle* h, int Z, const float** out) {
     return TSP_OK;
 }
 
+__global__ void worklist_reset_kernel(int* worklist) { worklist[0] = 0; }
+
 static int launch_band_range(tsp_handle* h, const int32_t* d_zmap, int Z, int Y, int X, int shift,
-                             int32_t* d_status, bool range_known, cudaStream_t s) {
+                             int32_t* d_status, bool range_known, int* d_worklist, cudaStream_t s) {
     if (range_known) {
-        band_check_kernel<<<1, 1, 0, s>>>(d_status, Z, shift, 1);
+        band_check_kernel<<<1, 1, 0, s>>>(d_status, Z, shift, 1, d_worklist);
         TSP_LAUNCH_CHECK(h);
         return TSP_OK;
     }
@@ -1062,7 +1325,7 @@ static int launch_band_range(tsp_handle* h, const int32_t* d_zmap, int Z, int Y,
     if (blocks > (size_t)h->sm_count * 8) blocks = (size_t)h->sm_count * 8;
     zmap_range_kernel<<<(int)blocks, 256, 0, s>>>(d_zmap, n, d_status);
     TSP_LAUNCH_CHECK(h);
-    band_check_kernel<<<1, 1, 0, s>>>(d_status, Z, shift, 0);
+    band_check_kernel<<<1, 1, 0, s>>>(d_status, Z, shift, 0, d_worklist);
     TSP_LAUNCH_CHECK(h);
     return TSP_OK;
 }
@@ -1087,6 +1350,22 @@ static int launch_band_variant(tsp_handle* h, BandArgs a, dim3 grid, int pedesta
             TSP_CUDA(cudaFuncSetAttribute(band_project3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB3Smem2));
             h->band3_attr = true;
         }
+    }
+    // shallow tiles first, one channel per CTA; the deep ones come back through the worklist
+    if (tma && a.worklist && !getenv("TSP_BAND_V3")) {
+        {
+            std::lock_guard<std::mutex> lock(h->mu);
+            if (!h->band4_attr) {
+                TSP_CUDA(cudaFuncSetAttribute(band_project4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB4Smem));
+                TSP_CUDA(cudaFuncSetAttribute(band_project4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB4Smem));
+                h->band4_attr = true;
+            }
+        }
+        dim3 g4(grid.x, grid.y, a.nch);
+        if (pedestal) band_project4_kernel<true><<<g4, kB2Threads, kB4Smem, s>>>(tmap, a);
+        else band_project4_kernel<false><<<g4, kB2Threads, kB4Smem, s>>>(tmap, a);
+        TSP_LAUNCH_CHECK(h);
+        a.use_list = 1;
     }
     const int pairs = a.nch / 2;
     if (pairs > 0) {
@@ -1117,9 +1396,15 @@ static int launch_band_variant(tsp_handle* h, BandArgs a, dim3 grid, int pedesta
     return TSP_OK;
 }
 
+size_t band_worklist_bytes(int Y, int X) {
+    const size_t tiles = (size_t)((X + kBandTX - 1) / kBandTX) * ((Y + kBandTY - 1) / kBandTY);
+    return (tiles + 1) * sizeof(int);
+}
+
 int launch_band_project_ex(tsp_handle* h, const uint16_t* d_stack, size_t channel_stride, size_t z0_offset,
                            const int32_t* d_zmap, float* d_proj, int C, int Z, int Y, int X, int ref_c,
-                           int shift, int pedestal, int32_t* d_status, bool range_known, cudaStream_t s) {
+                           int shift, int pedestal, int32_t* d_status, bool range_known, cudaStream_t s,
+                           int* d_worklist) {
     if (Z > kBandMaxPlanes) {
         set_error("band projection supports at most %d planes", kBandMaxPlanes);
         return TSP_ERR_INVALID;
@@ -1134,9 +1419,11 @@ int launch_band_project_ex(tsp_handle* h, const uint16_t* d_stack, size_t channe
     const float* lut = nullptr;
     rc = get_band_lut(h, &lut);
     if (rc) return rc;
-    rc = launch_band_range(h, d_zmap, Z, Y, X, shift, d_status, range_known, s);
+    rc = launch_band_range(h, d_zmap, Z, Y, X, shift, d_status, range_known, d_worklist, s);
     if (rc) return rc;
     BandArgs a;
+    a.worklist = d_worklist;
+    a.use_list = 0;
     a.lut = lut;
     a.zvec = (X % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_zmap) & 15) == 0) ? 1 : 0;
     a.stack = d_stack;
@@ -1162,6 +1449,10 @@ int launch_band_project_ex(tsp_handle* h, const uint16_t* d_stack, size_t channe
     if (rc) return rc;
     TSP_LAUNCH_CHECK(h);
     if (shift != 0 && C > 1) {
+        if (d_worklist) {
+            worklist_reset_kernel<<<1, 1, 0, s>>>(d_worklist);
+            TSP_LAUNCH_CHECK(h);
+        }
         a.shift = shift;
         a.nch = 0;
         for (int c = 0; c < C; ++c)
@@ -1206,7 +1497,7 @@ int launch_band_project_bitexact_ex(tsp_handle* h, const uint16_t* d_stack, size
                                     size_t z0_offset, const int32_t* d_zmap, float* d_proj, int C, int Z,
                                     int Y, int X, int ref_c, int shift, int pedestal, float* d_volA,
                                     float* d_volB, int32_t* d_status, bool range_known, cudaStream_t s) {
-    int rc = launch_band_range(h, d_zmap, Z, Y, X, shift, d_status, range_known, s);
+    int rc = launch_band_range(h, d_zmap, Z, Y, X, shift, d_status, range_known, nullptr, s);
     if (rc) return rc;
     const size_t plane = (size_t)Y * X;
     size_t blocks = (plane + 255) / 256;

@@ -152,7 +152,7 @@ struct tsp_handle {
     };
     Slot slots[TSP_MAX_SLOTS];
     // per-device one-time setup done (constant memory, function attributes)
-    bool fast_consts = false, band_consts = false, hist_attr = false, ring_attr = false, band3_attr = false, xy_attr = false;
+    bool fast_consts = false, band_consts = false, hist_attr = false, ring_attr = false, band3_attr = false, band4_attr = false, xy_attr = false;
     // optional per-stage timing (tsp_set_profiling): CUDA events recorded on the launching stream
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;       // marks of calls not yet folded into the totals
@@ -185,7 +185,9 @@ int launch_argmax(tsp_handle* h, const float* d_score, int32_t* d_zmap, int Z, i
                   int z_offset, int32_t* d_status, cudaStream_t s);
 int launch_band_project_ex(tsp_handle* h, const uint16_t* d_stack, size_t channel_stride, size_t z0_offset,
                            const int32_t* d_zmap, float* d_proj, int C, int Z, int Y, int X, int ref_c,
-                           int shift, int pedestal, int32_t* d_status, bool range_known, cudaStream_t s);
+                           int shift, int pedestal, int32_t* d_status, bool range_known, cudaStream_t s,
+                           int* d_worklist = nullptr);
+size_t band_worklist_bytes(int Y, int X);
 int launch_band_project_bitexact_ex(tsp_handle* h, const uint16_t* d_stack, size_t channel_stride,
                                     size_t z0_offset, const int32_t* d_zmap, float* d_proj, int C, int Z,
                                     int Y, int X, int ref_c, int shift, int pedestal, float* d_volA,
