@@ -91,6 +91,7 @@ static int resolve_crop(const tsp_frame_desc* d, Crop* c) {
 struct Workspace {
     int32_t* status;
     uint32_t* hist;
+    int* worklist;
     float* volA;
     float* volB;
     void* fast;
@@ -105,6 +106,8 @@ static Workspace carve(const tsp_frame_desc* d, const Crop& c, void* base) {
     off += align_up(kStatusWords * sizeof(int32_t), 256);
     w.hist = (uint32_t*)(p + off);
     off += align_up(percentile_scratch_bytes(), 256);
+    w.worklist = (int*)(p + off);
+    off += align_up(band_worklist_bytes(d->rows, d->cols), 256);
     const size_t vol = align_up((size_t)c.zc * d->rows * d->cols * sizeof(float), 256);
     if (d->mode == TSP_MODE_FAST) {
         w.fast = p + off;
@@ -208,8 +211,7 @@ int tsp_project_frame(tsp_handle* h, const tsp_frame_desc* desc, const uint16_t*
     const int ped = desc->airyscan ? kAiryscanPedestal : 0;
     const uint16_t* ref = d_stack + (size_t)desc->reference_channel * chan_stride + z0_off;
 
-    // the percentile scratch is idle again by the time the band stage runs: it holds the deep-tile worklist
-    int* worklist = band_worklist_bytes(Y, X) <= percentile_scratch_bytes() ? (int*)w.hist : nullptr;
+    int* worklist = w.worklist;
     prof_mark(h, s, -1);
     const bool fast = desc->mode == TSP_MODE_FAST;
     rc = launch_percentile(h, ref, nvox, ped, w.status, w.hist, s, fast ? w.fast : nullptr,

@@ -81,8 +81,7 @@ __global__ void zmap_range_init_kernel(int32_t* status) {
 
 // the reference indexes the cropped stack with chosen_z (and clip(chosen_z+shift, 0, Z), upper bound
 // inclusive): any index >= Z raises IndexError; negative indices cannot occur.
-__global__ void band_check_kernel(int32_t* status, int Z, int shift, int decode, int* worklist) {
-    if (worklist) worklist[0] = 0;
+__global__ void band_check_kernel(int32_t* status, int Z, int shift, int decode) {
     if (decode) status[ST_ZMIN] = INT32_MAX - status[ST_ZMIN_INV];     // argmax kernels keep max(INT_MAX - z)
     const int hi = status[ST_ZMAX];
     int err = hi >= Z;
@@ -119,10 +118,30 @@ struct BandArgs {
     int vec;                    // rows are 16-byte aligned: uint4 loads
     int zvec;                   // height-map rows are 16-byte aligned: int4 loads
     const float* lut;           // x-blur lookup tables of a binary row: [512] taps 0..8, [256] taps 9..16
-    int* worklist;              // [0] = count, [1..] = linear tile ids left to the deep-range kernel (may be null)
-    int use_list;               // band_project3_kernel: take the tile from the worklist instead of blockIdx
+    int* worklist;              // linear tile ids left to the deep-range kernel, status[ST_WORK_COUNT] of them (may be null)
+    int use_list;               // band_project3_kernel: take the tiles from the worklist instead of blockIdx
+    int tiles_x;                // tiles per image row (decodes worklist entries)
+    int fused_check;            // 1: the IndexError rule is evaluated here from the argmax stage's range (no check kernel)
+    int err_shift;              // atoh_shift of the frame (the rule looks at it even in the un-shifted pass)
     int ch[16];
 };
+
+// the reference indexes the cropped stack with chosen_z (and clip(chosen_z+shift, 0, Z), upper bound inclusive):
+// any index >= Z raises IndexError; negative indices cannot occur.  Every CTA evaluates the rule from the range the
+// argmax stage left in the status block (ST_ZMAX, ST_ZMIN_INV = max(INT_MAX - z)); the first CTA records the verdict.
+__device__ __forceinline__ bool band_index_error(const BandArgs& a) {
+    if (!a.fused_check) return a.status[ST_BAND_ERR] != 0;
+    const int hi = a.status[ST_ZMAX], lo = INT32_MAX - a.status[ST_ZMIN_INV];
+    int err = hi >= a.Z;
+    if (a.err_shift != 0) err |= min(max(hi + a.err_shift, 0), a.Z) >= a.Z;
+    if (lo < 0) err = 1;
+    if (threadIdx.x == 0 && (blockIdx.x | blockIdx.y | blockIdx.z) == 0) {
+        int32_t* st = const_cast<int32_t*>(a.status);
+        st[ST_ZMIN] = lo;
+        st[ST_BAND_ERR] = err;
+    }
+    return err != 0;
+}
 
 // b_s column permutation: the two float4 halves of every 8-pixel group live in separate 32-float
 // halves of the row, so that the y pass reads conflict-free 16-byte vectors
@@ -145,7 +164,7 @@ __global__ void __launch_bounds__(kBandThreads, 2) band_project_kernel(const Ban
     __shared__ uint32_t present[kBandMaxPlanes / 32];
     __shared__ int zlo_s, zhi_s;
 
-    if (a.status[ST_BAND_ERR]) return;          // the reference raises before projecting
+    if (band_index_error(a)) return;            // the reference raises before projecting
 
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * kBandTX, y0 = blockIdx.y * kBandTY;
@@ -373,7 +392,7 @@ __global__ void __launch_bounds__(kB2Threads, 2) band_project2_kernel(const Band
     __shared__ uint32_t present[kBandMaxPlanes / 32];
     __shared__ int zlo_s, zhi_s;
 
-    if (a.status[ST_BAND_ERR]) return;          // the reference raises before projecting
+    if (band_index_error(a)) return;            // the reference raises before projecting
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int x0 = blockIdx.x * kBandTX, y0 = blockIdx.y * kBandTY;
@@ -664,16 +683,17 @@ __global__ void __launch_bounds__(kB2Threads, 2) band_project3_kernel(const __gr
     __shared__ float lut_lo[512], lut_hi[256];
     __shared__ int zlo_s, zhi_s;
 
-    if (a.status[ST_BAND_ERR]) return;          // the reference raises before projecting
+    if (band_index_error(a)) return;            // the reference raises before projecting
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // use_list: a small grid walks the tiles band_project4_kernel left behind; otherwise one tile per CTA
+    const int ntiles = a.use_list ? a.status[ST_WORK_COUNT] : 1;
+    for (int lin = a.use_list ? (int)blockIdx.x : 0; lin < ntiles; lin += a.use_list ? (int)gridDim.x : 1) {
     int bx = blockIdx.x, by = blockIdx.y;
-    if (a.use_list) {                           // the tiles band_project4_kernel left behind
-        const int lin = by * gridDim.x + bx;
-        if (lin >= a.worklist[0]) return;
-        const int tile = a.worklist[1 + lin];
-        bx = tile % gridDim.x;
-        by = tile / gridDim.x;
+    if (a.use_list) {
+        const int tile = a.worklist[lin];
+        bx = tile % a.tiles_x;
+        by = tile / a.tiles_x;
     }
     const int x0 = bx * kBandTX, y0 = by * kBandTY;
     const uint32_t ring_s = smem_u32(b3_ring);
@@ -961,6 +981,12 @@ __global__ void __launch_bounds__(kB2Threads, 2) band_project3_kernel(const __gr
             reinterpret_cast<float4*>(dst1)[1] = make_float4(best1[2].x, best1[2].y, best1[3].x, best1[3].y);
         }
     }
+    __syncthreads();                             // the next tile re-initialises the barriers and the tile state
+    if (tid == 0 && a.use_list) {
+        asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar_s) : "memory");
+        asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar_s + 8) : "memory");
+    }
+    }
 }
 
 
@@ -992,7 +1018,7 @@ __global__ void __launch_bounds__(kB2Threads, 3) band_project4_kernel(const __gr
     __shared__ int zlo_s, zhi_s;
     uint16_t (*cz_s)[kB2CW] = reinterpret_cast<uint16_t (*)[kB2CW]>(&r_s[0][0]);
 
-    if (a.status[ST_BAND_ERR]) return;          // the reference raises before projecting
+    if (band_index_error(a)) return;            // the reference raises before projecting
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int x0 = blockIdx.x * kBandTX, y0 = blockIdx.y * kBandTY;
@@ -1065,8 +1091,8 @@ __global__ void __launch_bounds__(kB2Threads, 3) band_project4_kernel(const __gr
     const int zlo = zlo_s, zhi = zhi_s;
     if (zhi - zlo >= kB4NP) {                    // block-uniform: a deep tile goes to the generic kernel
         if (tid == 0 && blockIdx.z == 0) {
-            const int slot = atomicAdd(a.worklist, 1);
-            a.worklist[1 + slot] = blockIdx.y * gridDim.x + blockIdx.x;
+            const int slot = atomicAdd(const_cast<int32_t*>(a.status) + ST_WORK_COUNT, 1);
+            a.worklist[slot] = blockIdx.y * gridDim.x + blockIdx.x;
         }
         return;
     }
@@ -1309,12 +1335,13 @@ static int get_wz_table(tsp_handle* h, int Z, const float** out) {
     return TSP_OK;
 }
 
-__global__ void worklist_reset_kernel(int* worklist) { worklist[0] = 0; }
+__global__ void worklist_reset_kernel(int32_t* status) { status[ST_WORK_COUNT] = 0; }
 
 static int launch_band_range(tsp_handle* h, const int32_t* d_zmap, int Z, int Y, int X, int shift,
-                             int32_t* d_status, bool range_known, int* d_worklist, cudaStream_t s) {
+                             int32_t* d_status, bool range_known, bool fused_check, cudaStream_t s) {
     if (range_known) {
-        band_check_kernel<<<1, 1, 0, s>>>(d_status, Z, shift, 1, d_worklist);
+        if (fused_check) return TSP_OK;          // the projection kernels apply the rule themselves
+        band_check_kernel<<<1, 1, 0, s>>>(d_status, Z, shift, 1);
         TSP_LAUNCH_CHECK(h);
         return TSP_OK;
     }
@@ -1325,7 +1352,7 @@ static int launch_band_range(tsp_handle* h, const int32_t* d_zmap, int Z, int Y,
     if (blocks > (size_t)h->sm_count * 8) blocks = (size_t)h->sm_count * 8;
     zmap_range_kernel<<<(int)blocks, 256, 0, s>>>(d_zmap, n, d_status);
     TSP_LAUNCH_CHECK(h);
-    band_check_kernel<<<1, 1, 0, s>>>(d_status, Z, shift, 0, d_worklist);
+    band_check_kernel<<<1, 1, 0, s>>>(d_status, Z, shift, 0);
     TSP_LAUNCH_CHECK(h);
     return TSP_OK;
 }
@@ -1367,6 +1394,11 @@ static int launch_band_variant(tsp_handle* h, BandArgs a, dim3 grid, int pedesta
         TSP_LAUNCH_CHECK(h);
         a.use_list = 1;
     }
+    // worklist mode: a small grid walks the (usually empty) list
+    if (a.use_list) {
+        const unsigned tiles = grid.x * grid.y, cap = 2u * (unsigned)h->sm_count;
+        grid = dim3(tiles < cap ? tiles : cap, 1, 1);
+    }
     const int pairs = a.nch / 2;
     if (pairs > 0) {
         BandArgs b = a;
@@ -1398,7 +1430,7 @@ static int launch_band_variant(tsp_handle* h, BandArgs a, dim3 grid, int pedesta
 
 size_t band_worklist_bytes(int Y, int X) {
     const size_t tiles = (size_t)((X + kBandTX - 1) / kBandTX) * ((Y + kBandTY - 1) / kBandTY);
-    return (tiles + 1) * sizeof(int);
+    return tiles * sizeof(int);
 }
 
 int launch_band_project_ex(tsp_handle* h, const uint16_t* d_stack, size_t channel_stride, size_t z0_offset,
@@ -1419,11 +1451,14 @@ int launch_band_project_ex(tsp_handle* h, const uint16_t* d_stack, size_t channe
     const float* lut = nullptr;
     rc = get_band_lut(h, &lut);
     if (rc) return rc;
-    rc = launch_band_range(h, d_zmap, Z, Y, X, shift, d_status, range_known, d_worklist, s);
+    rc = launch_band_range(h, d_zmap, Z, Y, X, shift, d_status, range_known, range_known, s);
     if (rc) return rc;
     BandArgs a;
     a.worklist = d_worklist;
     a.use_list = 0;
+    a.tiles_x = (X + kBandTX - 1) / kBandTX;
+    a.fused_check = range_known ? 1 : 0;
+    a.err_shift = shift;
     a.lut = lut;
     a.zvec = (X % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_zmap) & 15) == 0) ? 1 : 0;
     a.stack = d_stack;
@@ -1450,7 +1485,7 @@ int launch_band_project_ex(tsp_handle* h, const uint16_t* d_stack, size_t channe
     TSP_LAUNCH_CHECK(h);
     if (shift != 0 && C > 1) {
         if (d_worklist) {
-            worklist_reset_kernel<<<1, 1, 0, s>>>(d_worklist);
+            worklist_reset_kernel<<<1, 1, 0, s>>>(d_status);
             TSP_LAUNCH_CHECK(h);
         }
         a.shift = shift;
@@ -1497,7 +1532,7 @@ int launch_band_project_bitexact_ex(tsp_handle* h, const uint16_t* d_stack, size
                                     size_t z0_offset, const int32_t* d_zmap, float* d_proj, int C, int Z,
                                     int Y, int X, int ref_c, int shift, int pedestal, float* d_volA,
                                     float* d_volB, int32_t* d_status, bool range_known, cudaStream_t s) {
-    int rc = launch_band_range(h, d_zmap, Z, Y, X, shift, d_status, range_known, nullptr, s);
+    int rc = launch_band_range(h, d_zmap, Z, Y, X, shift, d_status, range_known, false, s);
     if (rc) return rc;
     const size_t plane = (size_t)Y * X;
     size_t blocks = (plane + 255) / 256;

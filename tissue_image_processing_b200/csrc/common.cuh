@@ -35,6 +35,7 @@ enum StatusWord {
     ST_WIN_OK = 10,      //             1 when the sample produced a usable window
     ST_NEED_FULL = 11,   //             1 arms the full-histogram fallback
     ST_ZMIN_INV = 12,    // max over pixels of INT_MAX - z (so that a zeroed block is the identity)
+    ST_WORK_COUNT = 13,  // band stage: tiles on the deep-range worklist
 };
 
 void set_error(const char* fmt, ...);
