@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TSP_ABI_VERSION 1
+#define TSP_ABI_VERSION 2
 
 /* error codes */
 #define TSP_OK 0
@@ -45,8 +45,17 @@ extern "C" {
 
 typedef struct tsp_handle tsp_handle; /* per-GPU context: tables, status words, staging buffers */
 
+/* score methods for bin_size > 1 (SP:39-53) */
+#define TSP_METHOD_MAX_AVERAGES 0  /* block mean of the sigma=30 score                            */
+#define TSP_METHOD_MAX_STD 1       /* block variance of the pre-blurred reference channel         */
+#define TSP_METHOD_MULTI_CHANNEL 2 /* block variance (reference) x block mean (next channel)      */
+
 /* Frame descriptor = the arguments of time_point_surface_projection (SP:17-19) that reach the
- * arithmetic, for bin_size == 1 and build_manifold == False. */
+ * arithmetic.  bin_size <= 1 and build_manifold == 0 (the zeroed defaults) select the plain
+ * operator; bin_size > 1 bins the score with `method` (SP:39-53) and resamples it with order-1
+ * interpolation (SP:59-65); build_manifold != 0 replaces the argmax by the region growing of
+ * SP:87-165 (at most 254 planes).  Both run the direct-FIR score (TSP_MODE_FAST behaves like
+ * TSP_MODE_EXACT for them). */
 typedef struct tsp_frame_desc {
     int32_t channels, planes, rows, cols; /* C, Z, Y, X of the uint16 stack                      */
     int32_t reference_channel;            /* SP:32                                               */
@@ -54,7 +63,10 @@ typedef struct tsp_frame_desc {
     int32_t airyscan;                     /* SP:27-29: subtract 10000, clamp at 0                */
     int32_t atoh_shift;                   /* SP:62: plane offset for the non-reference channels  */
     int32_t mode;                         /* TSP_MODE_*                                          */
-    int32_t reserved[6];                  /* must be 0                                           */
+    int32_t bin_size;                     /* SP:39: <= 1 none                                    */
+    int32_t method;                       /* TSP_METHOD_* (only read when bin_size > 1)          */
+    int32_t build_manifold;               /* SP:56-57                                            */
+    int32_t reserved[3];                  /* must be 0                                           */
 } tsp_frame_desc;
 
 /* What the operator learned about the frame (filled by the *_host calls and tsp_get_frame_status) */
@@ -139,6 +151,29 @@ int tsp_focus_score_f32(tsp_handle* h, const uint16_t* d_channel, float* d_score
 /* SP:61: first-maximum argmax over z (+ z_offset). */
 int tsp_argmax_z_f32(tsp_handle* h, const float* d_score, int32_t* d_zmap, int planes, int rows,
                      int cols, int z_offset, void* cuda_stream);
+
+/* SP:87-165 build_continues_manifold: d_chosen (rows,cols) int32 = the height map grown in square
+ * rings around the global maximum of d_score (planes,rows,cols), every pixel within +-1 plane of its
+ * already-placed neighbours (find_pixel_plane, quirks included).  planes <= 254. */
+size_t tsp_manifold_workspace_bytes(void);
+int tsp_build_manifold(tsp_handle* h, const float* d_score, int32_t* d_chosen, int planes, int rows,
+                       int cols, void* d_workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* SP:41-50 skimage.measure.block_reduce(volume, (1,b,b), np.mean | np.var): zero padded to a multiple
+ * of bin_size; d_out (planes, ceil(rows/b), ceil(cols/b)) float32. */
+int tsp_block_reduce_f32(tsp_handle* h, const float* d_volume, float* d_out, int planes, int rows,
+                         int cols, int bin_size, int variance, void* cuda_stream);
+
+/* SP:59-61 resize(score, (Z,Y,X)) [order 1, reflect; = scipy.ndimage.zoom(order=1, mode='mirror',
+ * grid_mode=True)] fused with the first-maximum argmax over z (+ z_offset).  d_score is the binned
+ * (planes, coarse_rows, coarse_cols) volume; d_workspace >= 256 bytes. */
+int tsp_resize_argmax_f32(tsp_handle* h, const float* d_score, int32_t* d_zmap, int planes, int rows,
+                          int cols, int coarse_rows, int coarse_cols, int z_offset, void* d_workspace,
+                          size_t workspace_bytes, void* cuda_stream);
+
+/* SP:63-65 np.round(resize(chosen_z.astype('float32'), (Y,X))).astype('int') of a coarse height map. */
+int tsp_resize_round_i32(tsp_handle* h, const int32_t* d_coarse, int32_t* d_zmap, int rows, int cols,
+                         int coarse_rows, int coarse_cols, void* cuda_stream);
 
 /* SP:62-81: band mask from a height map and weighted max projection of every channel, without
  * materialising the one-hot volume.  d_zmap indexes the (already cropped) stack.  Channels other

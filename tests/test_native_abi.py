@@ -34,10 +34,24 @@ def test_every_declared_symbol_is_exported(native):
 
 def test_abi_version_and_struct_sizes(native):
     lib = native.load_library()
-    assert lib.tsp_abi_version() == 1
+    assert lib.tsp_abi_version() == 2
     assert ctypes.sizeof(native.FrameDesc) == 16 * 4
     assert ctypes.sizeof(native.FrameStatus) == 5 * 4 + 4 + 8 + 4 + 5 * 4   # with alignment padding
     assert native.FrameStatus.nonzero_count.offset == 24
+    assert native.FrameDesc.bin_size.offset == 40 and native.FrameDesc.build_manifold.offset == 48
+
+
+def test_binned_workspace_query(native):
+    lib = native.load_library()
+    plain = native.make_desc(2, 16, 128, 128, mode="fast")
+    binned = native.make_desc(2, 16, 128, 128, mode="fast", bin_size=2, method="multi_channel")
+    manifold = native.make_desc(2, 16, 128, 128, mode="fast", build_manifold=True)
+    n0 = lib.tsp_project_workspace_bytes(ctypes.byref(plain))
+    n1 = lib.tsp_project_workspace_bytes(ctypes.byref(binned))
+    n2 = lib.tsp_project_workspace_bytes(ctypes.byref(manifold))
+    assert n1 >= 2 * 16 * 128 * 128 * 4 + 16 * 64 * 64 * 4 > n0 and n2 >= 2 * 16 * 128 * 128 * 4
+    bad = native.make_desc(1, 16, 128, 128, bin_size=2, method=7)
+    assert lib.tsp_project_workspace_bytes(ctypes.byref(bad)) == 0 and b"method" in lib.tsp_last_error()
 
 
 def test_workspace_query_needs_no_gpu(native):

@@ -24,7 +24,8 @@ class FrameDesc(C.Structure):
     _fields_ = [("channels", C.c_int32), ("planes", C.c_int32), ("rows", C.c_int32), ("cols", C.c_int32),
                 ("reference_channel", C.c_int32), ("min_z", C.c_int32), ("max_z", C.c_int32),
                 ("airyscan", C.c_int32), ("atoh_shift", C.c_int32), ("mode", C.c_int32),
-                ("reserved", C.c_int32 * 6)]
+                ("bin_size", C.c_int32), ("method", C.c_int32), ("build_manifold", C.c_int32),
+                ("reserved", C.c_int32 * 3)]
 
 
 class FrameStatus(C.Structure):
@@ -60,6 +61,15 @@ EXPORTS = {
     "tsp_band_project": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                    C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "tsp_band_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "tsp_manifold_workspace_bytes": (C.c_size_t, []),
+    "tsp_build_manifold": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                     C.c_size_t, C.c_void_p]),
+    "tsp_block_reduce_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.c_int, C.c_void_p]),
+    "tsp_resize_argmax_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "tsp_resize_round_i32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.c_void_p]),
     "tsp_project_m_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "tsp_project_m": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -158,8 +168,15 @@ def stage_times(reset=True, device=None):
     return {lib.tsp_stage_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n) if cnt[i]}
 
 
-def make_desc(C_, Z, Y, X, reference_channel=0, min_z=0, max_z=0, airyscan=False, atoh_shift=0, mode="fast"):
+METHODS = {"max_averages": 0, "max_std": 1, "multi_channel": 2}
+
+
+def make_desc(C_, Z, Y, X, reference_channel=0, min_z=0, max_z=0, airyscan=False, atoh_shift=0, mode="fast",
+              bin_size=1, method="max_averages", build_manifold=False):
     d = FrameDesc()
+    d.bin_size = int(bin_size)
+    d.method = METHODS[method] if isinstance(method, str) else int(method)
+    d.build_manifold = 1 if build_manifold else 0
     d.channels, d.planes, d.rows, d.cols = int(C_), int(Z), int(Y), int(X)
     d.reference_channel = int(reference_channel)
     d.min_z, d.max_z = int(min_z), int(max_z)
@@ -194,14 +211,16 @@ def pinned_empty(shape, dtype):
 
 
 def project_frame_host(stack, reference_channel, min_z=0, max_z=0, airyscan=False, atoh_shift=0, mode="fast",
-                       device=None, out_proj=None, out_zmap=None):
+                       device=None, out_proj=None, out_zmap=None, bin_size=1, method="max_averages",
+                       build_manifold=False):
     """stack: C-contiguous uint16 ndarray (C,Z,Y,X) in host memory.  Returns (projection float64 (C,Y,X),
     zmap int64 (Y,X), status dict)."""
     lib = load_library()
     h = handle(device)
     assert stack.dtype == np.uint16 and stack.ndim == 4 and stack.flags.c_contiguous
     Cn, Z, Y, X = stack.shape
-    desc = make_desc(Cn, Z, Y, X, reference_channel, min_z, max_z, airyscan, atoh_shift, mode)
+    desc = make_desc(Cn, Z, Y, X, reference_channel, min_z, max_z, airyscan, atoh_shift, mode, bin_size, method,
+                     build_manifold)
     proj = out_proj if out_proj is not None else pinned_empty((Cn, Y, X), np.float64)
     zmap = out_zmap if out_zmap is not None else pinned_empty((Y, X), np.int64)
     st = FrameStatus()
@@ -332,6 +351,64 @@ def argmax_z(d_score, z_offset=0, stream=None):
     rc = lib.tsp_argmax_z_f32(h, C.c_void_p(d_score.data_ptr()), C.c_void_p(zmap.data_ptr()), Z, Y, X,
                               int(z_offset), _stream_ptr(stream))
     check(rc, "tsp_argmax_z_f32")
+    return zmap
+
+
+def build_manifold_device(d_score, stream=None):
+    """SP:87-128 on a device score volume (Z,Y,X) float32 -> (Y,X) int32."""
+    import torch
+    lib, h = load_library(), handle(d_score.device.index)
+    Z, Y, X = d_score.shape
+    chosen = torch.empty((Y, X), dtype=torch.int32, device=d_score.device)
+    nws = int(lib.tsp_manifold_workspace_bytes())
+    ws = torch.empty(nws, dtype=torch.uint8, device=d_score.device)
+    rc = lib.tsp_build_manifold(h, C.c_void_p(d_score.data_ptr()), C.c_void_p(chosen.data_ptr()), Z, Y, X,
+                                C.c_void_p(ws.data_ptr()), nws, _stream_ptr(stream))
+    check(rc, "tsp_build_manifold")
+    return chosen
+
+
+def build_manifold(score, device=None):
+    """Host convenience: numpy float32 (Z,Y,X) -> int64 (Y,X) like the reference's build_continues_manifold."""
+    import torch
+    handle(device)
+    dev = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
+    d = torch.from_numpy(np.ascontiguousarray(score, dtype=np.float32)).to(dev)
+    return build_manifold_device(d).cpu().numpy().astype(np.int64)
+
+
+def block_reduce(d_volume, bin_size, variance=False, stream=None):
+    import torch
+    lib, h = load_library(), handle(d_volume.device.index)
+    Z, Y, X = d_volume.shape
+    out = torch.empty((Z, -(-Y // bin_size), -(-X // bin_size)), dtype=torch.float32, device=d_volume.device)
+    rc = lib.tsp_block_reduce_f32(h, C.c_void_p(d_volume.data_ptr()), C.c_void_p(out.data_ptr()), Z, Y, X,
+                                  int(bin_size), 1 if variance else 0, _stream_ptr(stream))
+    check(rc, "tsp_block_reduce_f32")
+    return out
+
+
+def resize_argmax(d_score, rows, cols, z_offset=0, stream=None):
+    import torch
+    lib, h = load_library(), handle(d_score.device.index)
+    Z, cy, cx = d_score.shape
+    zmap = torch.empty((rows, cols), dtype=torch.int32, device=d_score.device)
+    ws = torch.empty(256, dtype=torch.uint8, device=d_score.device)
+    rc = lib.tsp_resize_argmax_f32(h, C.c_void_p(d_score.data_ptr()), C.c_void_p(zmap.data_ptr()), Z, int(rows),
+                                   int(cols), cy, cx, int(z_offset), C.c_void_p(ws.data_ptr()), 256,
+                                   _stream_ptr(stream))
+    check(rc, "tsp_resize_argmax_f32")
+    return zmap
+
+
+def resize_round(d_coarse, rows, cols, stream=None):
+    import torch
+    lib, h = load_library(), handle(d_coarse.device.index)
+    cy, cx = d_coarse.shape
+    zmap = torch.empty((rows, cols), dtype=torch.int32, device=d_coarse.device)
+    rc = lib.tsp_resize_round_i32(h, C.c_void_p(d_coarse.data_ptr()), C.c_void_p(zmap.data_ptr()), int(rows),
+                                  int(cols), cy, cx, _stream_ptr(stream))
+    check(rc, "tsp_resize_round_i32")
     return zmap
 
 

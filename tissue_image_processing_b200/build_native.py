@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["api.cu", "percentile.cu", "fir.cu", "band.cu", "spm.cu", "fast.cu"]
+SOURCES = ["api.cu", "percentile.cu", "fir.cu", "band.cu", "spm.cu", "fast.cu", "binned.cu"]
 LIB = os.path.join(HERE, "libtsp_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

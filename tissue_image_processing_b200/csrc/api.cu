@@ -72,6 +72,10 @@ static int resolve_crop(const tsp_frame_desc* d, Crop* c) {
         set_error("unknown mode %d", d->mode);
         return TSP_ERR_INVALID;
     }
+    if (d->bin_size > 1 && (d->method < TSP_METHOD_MAX_AVERAGES || d->method > TSP_METHOD_MULTI_CHANNEL)) {
+        set_error("unknown method %d", d->method);
+        return TSP_ERR_INVALID;
+    }
     c->z_offset = d->min_z;
     if (d->max_z > 0) {
         const int hi = d->max_z < d->planes ? d->max_z : d->planes;
@@ -95,8 +99,16 @@ struct Workspace {
     float* volA;
     float* volB;
     void* fast;
+    // binned scores / manifold (general path)
+    float* binned;        // (zc, cy, cx) score
+    int32_t* status2;     // status block of the second channel's percentile (SP:46)
+    int32_t* coarse_z;    // (cy, cx) height map grown on the binned score
+    int32_t* zmap_other;  // (Y, X) height map of the other channels when it is resampled separately
+    void* mf_scratch;
     size_t total;
 };
+
+static bool general_path(const tsp_frame_desc* d) { return d->bin_size > 1 || d->build_manifold != 0; }
 
 static Workspace carve(const tsp_frame_desc* d, const Crop& c, void* base) {
     Workspace w{};
@@ -109,7 +121,24 @@ static Workspace carve(const tsp_frame_desc* d, const Crop& c, void* base) {
     w.worklist = (int*)(p + off);
     off += align_up(band_worklist_bytes(d->rows, d->cols), 256);
     const size_t vol = align_up((size_t)c.zc * d->rows * d->cols * sizeof(float), 256);
-    if (d->mode == TSP_MODE_FAST) {
+    if (general_path(d)) {
+        w.volA = (float*)(p + off);
+        off += vol;
+        w.volB = (float*)(p + off);
+        off += vol;
+        const int bin = d->bin_size > 1 ? d->bin_size : 1;
+        const size_t cy = (d->rows + bin - 1) / bin, cx = (d->cols + bin - 1) / bin;
+        w.binned = (float*)(p + off);
+        off += align_up((size_t)c.zc * cy * cx * sizeof(float), 256);
+        w.status2 = (int32_t*)(p + off);
+        off += align_up(kStatusWords * sizeof(int32_t), 256);
+        w.coarse_z = (int32_t*)(p + off);
+        off += align_up(cy * cx * sizeof(int32_t), 256);
+        w.zmap_other = (int32_t*)(p + off);
+        off += align_up((size_t)d->rows * d->cols * sizeof(int32_t), 256);
+        w.mf_scratch = p + off;
+        off += align_up(manifold_scratch_bytes(), 256);
+    } else if (d->mode == TSP_MODE_FAST) {
         w.fast = p + off;
         off += fast_workspace_bytes(c.zc, d->rows, d->cols);
     } else {
@@ -213,6 +242,84 @@ int tsp_project_frame(tsp_handle* h, const tsp_frame_desc* desc, const uint16_t*
 
     int* worklist = w.worklist;
     prof_mark(h, s, -1);
+    if (general_path(desc)) {
+        // SP:39-65 with bin_size > 1 and / or build_manifold: direct-FIR score volumes, binned, then either the
+        // resampled argmax or the region growing
+        const bool fp64 = desc->mode == TSP_MODE_BITEXACT;
+        const int bin = desc->bin_size > 1 ? desc->bin_size : 1;
+        const bool binned = bin > 1, manifold = desc->build_manifold != 0;
+        const int cy = (Y + bin - 1) / bin, cx = (X + bin - 1) / bin;
+        const double sig_pre[3] = {0.5, 1.0, 1.0};       // SP:37
+        const double sig_score[3] = {0.5, 30.0, 30.0};   // SP:55
+        rc = launch_percentile(h, ref, nvox, ped, w.status, w.hist, s);
+        if (rc) return rc;
+        prof_mark(h, s, STG_PERCENTILE);
+        rc = launch_prepare(h, ref, w.volA, nvox, ped, w.status, s);
+        if (rc) return rc;
+        rc = gaussian_blur<float>(h, w.volA, w.volB, w.volA, c.zc, Y, X, sig_pre, fp64, s);     // volB = pc
+        if (rc) return rc;
+        const float* score = nullptr;
+        if (!binned || desc->method == TSP_METHOD_MAX_AVERAGES) {
+            rc = gaussian_blur<float>(h, w.volB, w.volA, w.volB, c.zc, Y, X, sig_score, fp64, s);
+            if (rc) return rc;
+            score = w.volA;
+            if (binned) {
+                rc = launch_block_reduce(h, w.volA, w.binned, c.zc, Y, X, bin, false, false, s);
+                if (rc) return rc;
+                score = w.binned;
+            }
+        } else {
+            rc = launch_block_reduce(h, w.volB, w.binned, c.zc, Y, X, bin, true, false, s);    // SP:43 / SP:49
+            if (rc) return rc;
+            score = w.binned;
+            if (desc->method == TSP_METHOD_MULTI_CHANNEL) {                                     // SP:44-51
+                const int oc = (desc->reference_channel + 1) % C;
+                const uint16_t* other = d_stack + (size_t)oc * chan_stride + z0_off;
+                rc = launch_percentile_all(h, other, nvox, ped, w.status2, w.hist, s);
+                if (rc) return rc;
+                rc = launch_prepare(h, other, w.volA, nvox, ped, w.status2, s);
+                if (rc) return rc;
+                rc = gaussian_blur<float>(h, w.volA, w.volB, w.volA, c.zc, Y, X, sig_pre, fp64, s);
+                if (rc) return rc;
+                rc = gaussian_blur<float>(h, w.volB, w.volA, w.volB, c.zc, Y, X, sig_score, fp64, s);
+                if (rc) return rc;
+                rc = launch_block_reduce(h, w.volA, w.binned, c.zc, Y, X, bin, false, true, s);
+                if (rc) return rc;
+            }
+        }
+        prof_mark(h, s, STG_BLUR_SCORE);
+        const int32_t* zmap_other = nullptr;
+        bool range_known = true;
+        if (!manifold) {
+            rc = launch_resize_argmax(h, score, d_zmap, c.zc, Y, X, cy, cx, c.z_offset, w.status, s);
+            if (rc) return rc;
+        } else if (!binned) {
+            rc = launch_manifold(h, score, d_zmap, c.zc, Y, X, w.status, w.mf_scratch, s);      // SP:57: no min_z added
+            if (rc) return rc;
+        } else {
+            rc = launch_manifold(h, score, w.coarse_z, c.zc, cy, cx, w.status, w.mf_scratch, s);
+            if (rc) return rc;
+            rc = launch_resize_round(h, w.coarse_z, d_zmap, Y, X, cy, cx, 0, 0, s);            // SP:64
+            if (rc) return rc;
+            range_known = false;
+            if (desc->atoh_shift != 0 && C > 1) {
+                rc = launch_resize_round(h, w.coarse_z, w.zmap_other, Y, X, cy, cx, desc->atoh_shift, c.zc, s);   // SP:62, 65
+                if (rc) return rc;
+                zmap_other = w.zmap_other;
+            }
+        }
+        prof_mark(h, s, STG_ARGMAX);
+        if (fp64)
+            rc = launch_band_project_bitexact_ex(h, d_stack, chan_stride, z0_off, d_zmap, d_proj, C, c.zc, Y, X,
+                                                 desc->reference_channel, desc->atoh_shift, ped, w.volA, w.volB,
+                                                 w.status, range_known, s, zmap_other);
+        else
+            rc = launch_band_project_ex(h, d_stack, chan_stride, z0_off, d_zmap, d_proj, C, c.zc, Y, X,
+                                        desc->reference_channel, desc->atoh_shift, ped, w.status, range_known, s,
+                                        worklist, zmap_other);
+        prof_mark(h, s, STG_BAND);
+        return rc;
+    }
     const bool fast = desc->mode == TSP_MODE_FAST;
     rc = launch_percentile(h, ref, nvox, ped, w.status, w.hist, s, fast ? w.fast : nullptr,
                            fast ? fast_accum_bytes(c.zc, Y, X) : 0);
@@ -486,6 +593,51 @@ int tsp_argmax_z_f32(tsp_handle* h, const float* d_score, int32_t* d_zmap, int p
     if (!h || !d_score || !d_zmap || planes < 1 || rows < 1 || cols < 1) return TSP_ERR_INVALID;
     TSP_CUDA(cudaSetDevice(h->device));
     return launch_argmax(h, d_score, d_zmap, planes, rows, cols, z_offset, nullptr, (cudaStream_t)cuda_stream);
+}
+
+size_t tsp_manifold_workspace_bytes(void) {
+    return align_up(kStatusWords * sizeof(int32_t), 256) + align_up(manifold_scratch_bytes(), 256);
+}
+
+int tsp_build_manifold(tsp_handle* h, const float* d_score, int32_t* d_chosen, int planes, int rows, int cols,
+                       void* d_workspace, size_t workspace_bytes, void* cuda_stream) {
+    if (!h || !d_score || !d_chosen || !d_workspace || planes < 1 || rows < 1 || cols < 1) return TSP_ERR_INVALID;
+    if (workspace_bytes < tsp_manifold_workspace_bytes()) return TSP_ERR_WORKSPACE;
+    TSP_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    TSP_CUDA(cudaMemsetAsync(d_workspace, 0, kStatusWords * sizeof(int32_t), s));
+    return launch_manifold(h, d_score, d_chosen, planes, rows, cols, (int32_t*)d_workspace,
+                           (char*)d_workspace + align_up(kStatusWords * sizeof(int32_t), 256), s);
+}
+
+int tsp_block_reduce_f32(tsp_handle* h, const float* d_volume, float* d_out, int planes, int rows, int cols,
+                         int bin_size, int variance, void* cuda_stream) {
+    if (!h || !d_volume || !d_out || planes < 1 || rows < 1 || cols < 1 || bin_size < 1) return TSP_ERR_INVALID;
+    TSP_CUDA(cudaSetDevice(h->device));
+    return launch_block_reduce(h, d_volume, d_out, planes, rows, cols, bin_size, variance != 0, false,
+                               (cudaStream_t)cuda_stream);
+}
+
+int tsp_resize_argmax_f32(tsp_handle* h, const float* d_score, int32_t* d_zmap, int planes, int rows, int cols,
+                          int coarse_rows, int coarse_cols, int z_offset, void* d_workspace, size_t workspace_bytes,
+                          void* cuda_stream) {
+    if (!h || !d_score || !d_zmap || !d_workspace || planes < 1 || rows < 1 || cols < 1 || coarse_rows < 1 ||
+        coarse_cols < 1)
+        return TSP_ERR_INVALID;
+    if (workspace_bytes < kStatusWords * sizeof(int32_t)) return TSP_ERR_WORKSPACE;
+    TSP_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    TSP_CUDA(cudaMemsetAsync(d_workspace, 0, kStatusWords * sizeof(int32_t), s));
+    return launch_resize_argmax(h, d_score, d_zmap, planes, rows, cols, coarse_rows, coarse_cols, z_offset,
+                                (int32_t*)d_workspace, s);
+}
+
+int tsp_resize_round_i32(tsp_handle* h, const int32_t* d_coarse, int32_t* d_zmap, int rows, int cols,
+                         int coarse_rows, int coarse_cols, void* cuda_stream) {
+    if (!h || !d_coarse || !d_zmap || rows < 1 || cols < 1 || coarse_rows < 1 || coarse_cols < 1) return TSP_ERR_INVALID;
+    TSP_CUDA(cudaSetDevice(h->device));
+    return launch_resize_round(h, d_coarse, d_zmap, rows, cols, coarse_rows, coarse_cols, 0, 0,
+                               (cudaStream_t)cuda_stream);
 }
 
 // [status block][worklist of the tiles the shallow-range band kernel leaves to the generic one]

@@ -1338,7 +1338,8 @@ static int get_wz_table(tsp_handle* h, int Z, const float** out) {
 __global__ void worklist_reset_kernel(int32_t* status) { status[ST_WORK_COUNT] = 0; }
 
 static int launch_band_range(tsp_handle* h, const int32_t* d_zmap, int Z, int Y, int X, int shift,
-                             int32_t* d_status, bool range_known, bool fused_check, cudaStream_t s) {
+                             int32_t* d_status, bool range_known, bool fused_check, cudaStream_t s,
+                             const int32_t* d_zmap_other = nullptr) {
     if (range_known) {
         if (fused_check) return TSP_OK;          // the projection kernels apply the rule themselves
         band_check_kernel<<<1, 1, 0, s>>>(d_status, Z, shift, 1);
@@ -1352,6 +1353,10 @@ static int launch_band_range(tsp_handle* h, const int32_t* d_zmap, int Z, int Y,
     if (blocks > (size_t)h->sm_count * 8) blocks = (size_t)h->sm_count * 8;
     zmap_range_kernel<<<(int)blocks, 256, 0, s>>>(d_zmap, n, d_status);
     TSP_LAUNCH_CHECK(h);
+    if (d_zmap_other) {                          // a separate map for the other channels: both must stay inside
+        zmap_range_kernel<<<(int)blocks, 256, 0, s>>>(d_zmap_other, n, d_status);
+        TSP_LAUNCH_CHECK(h);
+    }
     band_check_kernel<<<1, 1, 0, s>>>(d_status, Z, shift, 0);
     TSP_LAUNCH_CHECK(h);
     return TSP_OK;
@@ -1436,7 +1441,13 @@ size_t band_worklist_bytes(int Y, int X) {
 int launch_band_project_ex(tsp_handle* h, const uint16_t* d_stack, size_t channel_stride, size_t z0_offset,
                            const int32_t* d_zmap, float* d_proj, int C, int Z, int Y, int X, int ref_c,
                            int shift, int pedestal, int32_t* d_status, bool range_known, cudaStream_t s,
-                           int* d_worklist) {
+                           int* d_worklist, const int32_t* d_zmap_other) {
+    // d_zmap_other: the height map of the non-reference channels when it is not clip(zmap + shift) (binned
+    // manifold, SP:62-65); the shift is then already inside it
+    if (d_zmap_other) {
+        range_known = false;
+        shift = 0;
+    }
     if (Z > kBandMaxPlanes) {
         set_error("band projection supports at most %d planes", kBandMaxPlanes);
         return TSP_ERR_INVALID;
@@ -1451,7 +1462,7 @@ int launch_band_project_ex(tsp_handle* h, const uint16_t* d_stack, size_t channe
     const float* lut = nullptr;
     rc = get_band_lut(h, &lut);
     if (rc) return rc;
-    rc = launch_band_range(h, d_zmap, Z, Y, X, shift, d_status, range_known, range_known, s);
+    rc = launch_band_range(h, d_zmap, Z, Y, X, shift, d_status, range_known, range_known, s, d_zmap_other);
     if (rc) return rc;
     BandArgs a;
     a.worklist = d_worklist;
@@ -1478,12 +1489,13 @@ int launch_band_project_ex(tsp_handle* h, const uint16_t* d_stack, size_t channe
     a.shift = 0;
     a.nch = 0;
     for (int c = 0; c < C; ++c)
-        if (shift == 0 || c == ref_c) a.ch[a.nch++] = c;
+        if ((shift == 0 && !d_zmap_other) || c == ref_c) a.ch[a.nch++] = c;
     grid.z = (a.nch + kBandMaxCh - 1) / kBandMaxCh;
     rc = launch_band_variant(h, a, grid, pedestal, C, s);
     if (rc) return rc;
     TSP_LAUNCH_CHECK(h);
-    if (shift != 0 && C > 1) {
+    if ((shift != 0 || d_zmap_other) && C > 1) {
+        if (d_zmap_other) a.zmap = d_zmap_other;
         if (d_worklist) {
             worklist_reset_kernel<<<1, 1, 0, s>>>(d_status);
             TSP_LAUNCH_CHECK(h);
@@ -1531,8 +1543,13 @@ __global__ void mulmax_kernel(const uint16_t* __restrict__ chan, const float* __
 int launch_band_project_bitexact_ex(tsp_handle* h, const uint16_t* d_stack, size_t channel_stride,
                                     size_t z0_offset, const int32_t* d_zmap, float* d_proj, int C, int Z,
                                     int Y, int X, int ref_c, int shift, int pedestal, float* d_volA,
-                                    float* d_volB, int32_t* d_status, bool range_known, cudaStream_t s) {
-    int rc = launch_band_range(h, d_zmap, Z, Y, X, shift, d_status, range_known, false, s);
+                                    float* d_volB, int32_t* d_status, bool range_known, cudaStream_t s,
+                                    const int32_t* d_zmap_other) {
+    if (d_zmap_other) {
+        range_known = false;
+        shift = 0;
+    }
+    int rc = launch_band_range(h, d_zmap, Z, Y, X, shift, d_status, range_known, false, s, d_zmap_other);
     if (rc) return rc;
     const size_t plane = (size_t)Y * X;
     size_t blocks = (plane + 255) / 256;
@@ -1540,13 +1557,15 @@ int launch_band_project_bitexact_ex(tsp_handle* h, const uint16_t* d_stack, size
     const double sig[3] = {1.0, 2.0, 2.0};
     for (int pass = 0; pass < 2; ++pass) {
         const int sh = pass == 0 ? 0 : shift;
-        if (pass == 1 && (shift == 0 || C == 1)) break;
-        onehot_kernel<<<(int)blocks, 256, 0, s>>>(d_zmap, d_volA, Z, plane, sh, d_status);
+        const bool two_maps = shift != 0 || d_zmap_other;
+        if (pass == 1 && (!two_maps || C == 1)) break;
+        onehot_kernel<<<(int)blocks, 256, 0, s>>>(pass == 1 && d_zmap_other ? d_zmap_other : d_zmap, d_volA, Z, plane, sh,
+                                                  d_status);
         TSP_LAUNCH_CHECK(h);
         rc = gaussian_blur<float>(h, d_volA, d_volB, d_volA, Z, Y, X, sig, true, s);
         if (rc) return rc;
         for (int c = 0; c < C; ++c) {
-            const bool uses = (shift == 0) ? (pass == 0) : ((c == ref_c) == (pass == 0));
+            const bool uses = !two_maps ? (pass == 0) : ((c == ref_c) == (pass == 0));
             if (!uses) continue;
             mulmax_kernel<<<(int)blocks, 256, 0, s>>>(d_stack + (size_t)c * channel_stride + z0_offset, d_volB,
                                                       d_proj + (size_t)c * plane, Z, plane, pedestal, d_status);

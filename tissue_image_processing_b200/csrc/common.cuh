@@ -153,7 +153,7 @@ struct tsp_handle {
     };
     Slot slots[TSP_MAX_SLOTS];
     // per-device one-time setup done (constant memory, function attributes)
-    bool fast_consts = false, band_consts = false, hist_attr = false, ring_attr = false, band3_attr = false, band4_attr = false, xy_attr = false;
+    bool fast_consts = false, band_consts = false, hist_attr = false, ring_attr = false, band3_attr = false, band4_attr = false, xy_attr = false, manifold_attr = false;
     // optional per-stage timing (tsp_set_profiling): CUDA events recorded on the launching stream
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;       // marks of calls not yet folded into the totals
@@ -187,12 +187,25 @@ int launch_argmax(tsp_handle* h, const float* d_score, int32_t* d_zmap, int Z, i
 int launch_band_project_ex(tsp_handle* h, const uint16_t* d_stack, size_t channel_stride, size_t z0_offset,
                            const int32_t* d_zmap, float* d_proj, int C, int Z, int Y, int X, int ref_c,
                            int shift, int pedestal, int32_t* d_status, bool range_known, cudaStream_t s,
-                           int* d_worklist = nullptr);
+                           int* d_worklist = nullptr, const int32_t* d_zmap_other = nullptr);
 size_t band_worklist_bytes(int Y, int X);
+// binned scores, their resampling and the continuous manifold (binned.cu)
+int launch_percentile_all(tsp_handle* h, const uint16_t* d_vol, size_t count, int pedestal, int32_t* d_status,
+                          void* d_scratch, cudaStream_t s);
+int launch_block_reduce(tsp_handle* h, const float* d_vol, float* d_out, int Z, int Y, int X, int bin,
+                        bool variance, bool multiply, cudaStream_t s);
+int launch_resize_argmax(tsp_handle* h, const float* d_score, int32_t* d_zmap, int Z, int Y, int X, int cy, int cx,
+                         int z_offset, int32_t* d_status, cudaStream_t s);
+int launch_resize_round(tsp_handle* h, const int32_t* d_coarse, int32_t* d_zmap, int Y, int X, int cy, int cx,
+                        int shift, int clip_hi, cudaStream_t s);
+size_t manifold_scratch_bytes();
+int launch_manifold(tsp_handle* h, const float* d_score, int32_t* d_chosen, int P, int R, int C, int32_t* d_status,
+                    void* d_scratch, cudaStream_t s);
 int launch_band_project_bitexact_ex(tsp_handle* h, const uint16_t* d_stack, size_t channel_stride,
                                     size_t z0_offset, const int32_t* d_zmap, float* d_proj, int C, int Z,
                                     int Y, int X, int ref_c, int shift, int pedestal, float* d_volA,
-                                    float* d_volB, int32_t* d_status, bool range_known, cudaStream_t s);
+                                    float* d_volB, int32_t* d_status, bool range_known, cudaStream_t s,
+                                    const int32_t* d_zmap_other = nullptr);
 int launch_project_m(tsp_handle* h, const uint16_t* d_channel, uint16_t* d_out, int Z, int Y, int X,
                      int method, int bin, void* d_ws, cudaStream_t s);
 int launch_widen_outputs(tsp_handle* h, const float* d_proj, const int32_t* d_zmap, double* d_proj64,

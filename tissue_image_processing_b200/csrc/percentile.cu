@@ -255,16 +255,33 @@ __device__ void percentile_finalize(const uint32_t* __restrict__ ghist, int pede
         write_result(status, n, numpy_lerp((float)(look.bin[0] - pedestal), (float)(look.bin[1] - pedestal), rp.gamma));
 }
 
+// SP:46 takes the percentile of ALL voxels of the second channel (zeros included): the voxels at or below the
+// pedestal are `zeros` leading values 0 in the sorted order
+__device__ void percentile_finalize_all(const uint32_t* __restrict__ ghist, int pedestal, unsigned long long count,
+                                        int32_t* __restrict__ status) {
+    RankLookup first = block_rank_lookup(ghist, kHistBins, pedestal + 1, 0, ~0ull, ~0ull);
+    const unsigned long long zeros = count - first.total;
+    const RankPair rp = numpy_ranks(count);
+    RankLookup look = block_rank_lookup(ghist, kHistBins, pedestal + 1, zeros, rp.prev, rp.next);
+    if (threadIdx.x == 0) {
+        const float v0 = look.bin[0] < 0 ? 0.f : (float)(look.bin[0] - pedestal);
+        const float v1 = look.bin[1] < 0 ? 0.f : (float)(look.bin[1] - pedestal);
+        write_result(status, count, numpy_lerp(v0, v1, rp.gamma));
+    }
+}
+
 // full histogram of all voxels; the CTA that finishes last resolves the percentile.  `gate`: when non-null the
 // kernel only runs if *gate != 0 (fallback armed by ST_NEED_FULL).
 __global__ void __launch_bounds__(kHistThreads, 1)
 hist_percentile_kernel(const uint16_t* __restrict__ vol, size_t count, uint32_t* __restrict__ ghist, int pedestal,
-                       int32_t* __restrict__ status, unsigned int* __restrict__ ticket, const int32_t* __restrict__ gate) {
+                       int32_t* __restrict__ status, unsigned int* __restrict__ ticket, const int32_t* __restrict__ gate,
+                       int all_voxels) {
     if (gate && *gate == 0) return;
     extern __shared__ uint32_t sh[];
     hist_full_body(vol, count, ghist, sh);
     if (!is_last_block(ticket)) return;
-    percentile_finalize(ghist, pedestal, status);
+    if (all_voxels) percentile_finalize_all(ghist, pedestal, (unsigned long long)count, status);
+    else percentile_finalize(ghist, pedestal, status);
 }
 
 // ---- step 1: value window from a sample ------------------------------------------------------------
@@ -580,7 +597,7 @@ int launch_percentile(tsp_handle* h, const uint16_t* d_vol, size_t count, int pe
     }
     if (stride == 1) {
         hist_percentile_kernel<<<hist_grid(h, count, 1), kHistThreads, kHistSmemBytes, s>>>(
-            d_vol, count, hist_full, pedestal, d_status, tickets, nullptr);
+            d_vol, count, hist_full, pedestal, d_status, tickets, nullptr, 0);
         TSP_LAUNCH_CHECK(h);
         return TSP_OK;
     }
@@ -592,7 +609,23 @@ int launch_percentile(tsp_handle* h, const uint16_t* d_vol, size_t count, int pe
     TSP_LAUNCH_CHECK(h);
     // exact fallback, armed by ST_NEED_FULL (returns at once otherwise)
     hist_percentile_kernel<<<hist_grid(h, count, 1), kHistThreads, kHistSmemBytes, s>>>(
-        d_vol, count, hist_full, pedestal, d_status, tickets, d_status + ST_NEED_FULL);
+        d_vol, count, hist_full, pedestal, d_status, tickets, d_status + ST_NEED_FULL, 0);
+    TSP_LAUNCH_CHECK(h);
+    return TSP_OK;
+}
+
+// SP:46: np.percentile(channel, 95) over every voxel (after the pedestal), exact, by the full histogram.
+// d_status: a status block of its own (ST_P95_BITS / ST_HAS_NONZERO are what launch_prepare reads).
+int launch_percentile_all(tsp_handle* h, const uint16_t* d_vol, size_t count, int pedestal, int32_t* d_status,
+                          void* d_scratch, cudaStream_t s) {
+    int rc = ensure_hist_attr(h);
+    if (rc) return rc;
+    uint32_t* hist_full = (uint32_t*)d_scratch;
+    unsigned int* tickets = (unsigned int*)((unsigned long long*)(hist_full + kHistBins + kCoarseBins + kWinBins) + 2);
+    TSP_CUDA(cudaMemsetAsync(d_status, 0, kStatusWords * sizeof(int32_t), s));
+    TSP_CUDA(cudaMemsetAsync(d_scratch, 0, percentile_scratch_bytes(), s));
+    hist_percentile_kernel<<<hist_grid(h, count, 1), kHistThreads, kHistSmemBytes, s>>>(
+        d_vol, count, hist_full, pedestal, d_status, tickets, nullptr, 1);
     TSP_LAUNCH_CHECK(h);
     return TSP_OK;
 }

@@ -7,6 +7,9 @@
 conventions; file I/O goes through the hooks of ``basic_image_manipulations`` (the reference's
 Bio-Formats stack is out of scope).
 
+``bin_size > 1`` (SP:39-53, methods max_averages / max_std / multi_channel) and ``build_manifold`` (SP:87-165)
+run on the GPU too; they use the direct-FIR score (``mode="fast"`` behaves like "exact" for them).
+
 Extension (keyword-only, defaults preserve reference behaviour): ``mode`` selects the score
 stage - "fast" (default, multirate sigma=30 stage), "exact" (direct FIR, fp32) or "bitexact"
 (direct FIR, scipy's float64 summation order; bit-identical height map and projection).
@@ -53,15 +56,14 @@ def time_point_surface_projection(time_point, axes, reference_channel, min_z=0, 
         # SP:37 blurs image[reference_channel] with three sigmas; anything but a 3-D channel fails in
         # scipy exactly like this
         raise RuntimeError("sequence argument must have length equal to input rank")
-    if bin_size > 1:
-        raise NotImplementedError("bin_size > 1 (SP:39-53) is not on the B200 path yet: it depends on "
-                                  "scikit-image block_reduce/resize, which the reference does not pin")
-    if build_manifold:
-        raise NotImplementedError("build_manifold=True (SP:87-165) is a sequential region growing that is "
-                                  "not on the B200 path yet")
+    if bin_size > 1 and method not in _native.METHODS:
+        raise TypeError("exceptions must derive from BaseException")      # SP:53 raises a str
     stack = _as_uint16_stack(image)
     proj, zmap, _ = _native.project_frame_host(stack, int(reference_channel), int(min_z), int(max_z),
-                                               bool(airyscan), int(atoh_shift), mode or DEFAULT_MODE, device)
+                                               bool(airyscan), int(atoh_shift), mode or DEFAULT_MODE, device,
+                                               bin_size=int(bin_size) if bin_size > 1 else 1,
+                                               method=method if bin_size > 1 else "max_averages",
+                                               build_manifold=bool(build_manifold))
     if axes_wo_t.find("C") < 0:                         # unreachable in the reference (see above)
         proj = proj[0]
     if z_map:
@@ -69,12 +71,15 @@ def time_point_surface_projection(time_point, axes, reference_channel, min_z=0, 
     return proj
 
 
-def find_pixel_plane(score, chozen_z, pixel_row, pixel_col, max_row, max_col, max_plane):
-    raise NotImplementedError("continuous-manifold height maps (SP:130-165) are not on the B200 path yet")
-
-
 def build_continues_manifold(score):
-    raise NotImplementedError("continuous-manifold height maps (SP:87-128) are not on the B200 path yet")
+    """SP:87-128 on the GPU: score (Z, Y, X) float32 -> int64 height map grown outwards from the global score
+    maximum (``tsp_build_manifold``; at most 254 planes)."""
+    return _native.build_manifold(np.ascontiguousarray(score, dtype=np.float32))
+
+
+def find_pixel_plane(score, chozen_z, pixel_row, pixel_col, max_row, max_col, max_plane):
+    raise NotImplementedError("find_pixel_plane (SP:130-165) is only available fused inside build_continues_manifold "
+                              "on the B200 path")
 
 
 # ------------------------------------------------------------------------------------------------
