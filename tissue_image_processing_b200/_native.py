@@ -262,12 +262,13 @@ class DeviceProjector:
     """Reusable device-side buffers for one frame shape; everything stays on the current stream."""
 
     def __init__(self, Cn, Z, Y, X, reference_channel=0, min_z=0, max_z=0, airyscan=False, atoh_shift=0,
-                 mode="fast", device=None):
+                 mode="fast", device=None, bin_size=1, method="max_averages", build_manifold=False):
         import torch
         self.lib = load_library()
         self.h = handle(device)
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
-        self.desc = make_desc(Cn, Z, Y, X, reference_channel, min_z, max_z, airyscan, atoh_shift, mode)
+        self.desc = make_desc(Cn, Z, Y, X, reference_channel, min_z, max_z, airyscan, atoh_shift, mode, bin_size,
+                              method, build_manifold)
         self.ws_bytes = int(self.lib.tsp_project_workspace_bytes(C.byref(self.desc)))
         if self.ws_bytes == 0:
             raise TspError(ERR_INVALID, "tsp_project_workspace_bytes")

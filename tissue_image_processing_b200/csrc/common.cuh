@@ -88,6 +88,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done;
     do {
@@ -97,6 +100,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "r"(bar), "r"(parity)
             : "memory");
     } while (!done);
+}
+// 1-D bulk copy global -> shared (bytes a multiple of 16, both sides 16-byte aligned), completing on an mbarrier
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int x, int y, int z, uint32_t bar) {
     asm volatile(
@@ -153,7 +162,7 @@ struct tsp_handle {
     };
     Slot slots[TSP_MAX_SLOTS];
     // per-device one-time setup done (constant memory, function attributes)
-    bool fast_consts = false, band_consts = false, hist_attr = false, ring_attr = false, band3_attr = false, band4_attr = false, xy_attr = false, manifold_attr = false;
+    bool fast_consts = false, band_consts = false, hist_attr = false, ring_attr = false, band3_attr = false, band4_attr = false, xy_attr = false, manifold_attr = false, count_attr = false;
     // optional per-stage timing (tsp_set_profiling): CUDA events recorded on the launching stream
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;       // marks of calls not yet folded into the totals
