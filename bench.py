@@ -227,6 +227,14 @@ def run_gpu(args, rank, world, local_rank):
     stages = nat.stage_times(reset=True, device=local_rank)
     nat.set_profiling(False, local_rank)
 
+    if args.device_only:       # development aid: kernels only, one short line
+        if rank == 0:
+            sm = {k: round(v[0] / max(v[1], 1), 5) for k, v in stages.items() if v[1]}
+            print(json.dumps({"ms_per_step": dev_ms / args.steps, "stage_ms": sm, "status": status}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     # ---- end to end through the public API ----------------------------------------------------------
     host_frames = []
     for f in frames:
@@ -321,6 +329,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--mode", default="fast", choices=["fast", "exact", "bitexact"])
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--device-only", action="store_true", help="development aid: skip the end-to-end and CPU legs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
