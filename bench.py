@@ -228,6 +228,8 @@ def run_gpu(args, rank, world, local_rank):
     nat.set_profiling(False, local_rank)
 
     if args.device_only:       # development aid: kernels only, one short line
+        if sampler:
+            sampler.stop()
         if rank == 0:
             sm = {k: round(v[0] / max(v[1], 1), 5) for k, v in stages.items() if v[1]}
             print(json.dumps({"ms_per_step": dev_ms / args.steps, "stage_ms": sm, "status": status}), flush=True)
@@ -289,6 +291,11 @@ def run_gpu(args, rank, world, local_rank):
                    "prepare": 2 * vox, "band": 2 * vox + Y * X * 8, "interp_argmax": 2 * vox, "coarse": 2 * vox,
                    "argmax": 2 * vox}
     achieved = stage_bytes.get(dom, 2 * vox) / (stage_ms[dom] * 1e-3) / 1e9
+    # dram__bytes_read.sum + dram__bytes_write.sum per frame of each stage's kernels, from the ncu --set full capture
+    # of this very workload (profiles/r1r_ncu_full_summary.txt); only meaningful for the default fast mode
+    ncu_traffic = {"percentile": 16.84e6 + 536.9e6 + 23.28e6 + 0.06e6, "decimate": 555.7e6 + 23.45e6,
+                   "coarse": 2 * 17.45e6, "interp_argmax": 5.57e6, "band": 111.2e6 + 7.14e6 + 0.07e6}
+    traffic = ncu_traffic.get(dom) if args.mode == "fast" else None
     cpu_v, cpu_wall = cpu_baseline((48, 640, 640), procs=1)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -306,7 +313,9 @@ def run_gpu(args, rank, world, local_rank):
                 "single_call_api": "time_point_surface_projection(frame, 'TCZYX', ...) one blocking call per frame"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic,
+                     "traffic_source": "ncu --set full, profiles/r1r_ncu_full_summary.txt (per frame, all kernels of "
+                                       "the stage)", "peak_source": peak_src,
                      "kernel_ms": stage_ms[dom]},
         "frame_roofline": {"achieved": frame_gbs, "peak": peak, "unit": "GB/s", "frac": frame_gbs / peak,
                            "frac_of_nominal_8TBs": frame_gbs / 8000.0,
