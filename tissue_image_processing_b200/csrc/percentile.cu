@@ -14,6 +14,8 @@
 //   3. hist_percentile_kernel, the full-histogram fallback (returns at once when not armed).
 // Small volumes (stride 1) use the full histogram directly.  "Last CTA" = atomic ticket after a fence, so the
 // whole percentile is three launches.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace tsp {
@@ -455,8 +457,11 @@ window_count_kernel(const uint16_t* __restrict__ vol, size_t count, int pedestal
     uint32_t magic = 0x4B000000u;
     asm volatile("" : "+r"(magic));
     float2 acc_nz = make_float2(0.f, 0.f), acc_a = acc_nz, acc_b = acc_nz;
+    uint32_t acc_nzi = 0;                      // pedestal 0: packed 16-bit counters of min(v, 1) (integer pipe)
     uint32_t seen_vec = 0, rounds = 0;
     auto flush = [&]() {
+        nz_total += (unsigned long long)(acc_nzi & 0xffffu) + (unsigned long long)(acc_nzi >> 16);
+        acc_nzi = 0;
         nz_total += (unsigned long long)(acc_nz.x + acc_nz.y);
         below_total += (unsigned long long)seen_vec * 8ull - (unsigned long long)(acc_a.x + acc_a.y);
         acc_nz = acc_a = acc_b = make_float2(0.f, 0.f);
@@ -481,33 +486,43 @@ window_count_kernel(const uint16_t* __restrict__ vol, size_t count, int pedestal
     constexpr size_t kChunkVec = (size_t)kCountThreads * kCountUnroll;
     float2 inwin_prev = make_float2(0.f, 0.f);      // running a - b per half (exact small integers)
     const size_t nfull = nvec / kChunkVec;
-    for (size_t chunk = blockIdx.x; chunk < nfull; chunk += gridDim.x) {
-        const uint4* src = body + chunk * kChunkVec + threadIdx.x;
-        uint4 v[kCountUnroll];
+    // INT_NZ (pedestal 0): the non-zero flags are min(v, 1) on packed pairs (VIMNMX.U16x2) summed by plain integer
+    // adds - the integer pipe carries them while the FP32 pipe does the two window flags
+    auto stream = [&](auto int_nz_tag) {
+        constexpr bool INT_NZ = decltype(int_nz_tag)::value;
+        for (size_t chunk = blockIdx.x; chunk < nfull; chunk += gridDim.x) {
+            const uint4* src = body + chunk * kChunkVec + threadIdx.x;
+            uint4 v[kCountUnroll];
 #pragma unroll
-        for (int j = 0; j < kCountUnroll; ++j) v[j] = __ldg(src + j * kCountThreads);
+            for (int j = 0; j < kCountUnroll; ++j) v[j] = __ldg(src + j * kCountThreads);
 #pragma unroll
-        for (int j = 0; j < kCountUnroll; ++j) {
-            const uint32_t ws[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+            for (int j = 0; j < kCountUnroll; ++j) {
+                const uint32_t ws[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+                if (INT_NZ)
+                    acc_nzi += (__vminu2(ws[0], 0x00010001u) + __vminu2(ws[1], 0x00010001u)) +
+                               (__vminu2(ws[2], 0x00010001u) + __vminu2(ws[3], 0x00010001u));
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float f0 = biased_lo(ws[q], magic), f1 = biased_hi(ws[q], magic);
-                acc_nz = __fadd2_rn(acc_nz, make_float2(sat_add(f0, c_nz), sat_add(f1, c_nz)));
-                acc_a = __fadd2_rn(acc_a, make_float2(sat_add(f0, c_a), sat_add(f1, c_a)));
-                acc_b = __fadd2_rn(acc_b, make_float2(sat_add(f0, c_b), sat_add(f1, c_b)));
+                for (int q = 0; q < 4; ++q) {
+                    const float f0 = biased_lo(ws[q], magic), f1 = biased_hi(ws[q], magic);
+                    if (!INT_NZ) acc_nz = __fadd2_rn(acc_nz, make_float2(sat_add(f0, c_nz), sat_add(f1, c_nz)));
+                    acc_a = __fadd2_rn(acc_a, make_float2(sat_add(f0, c_a), sat_add(f1, c_a)));
+                    acc_b = __fadd2_rn(acc_b, make_float2(sat_add(f0, c_b), sat_add(f1, c_b)));
+                }
+                // a >= b voxel by voxel: the vector touches the window iff a and b advanced differently
+                const float2 inwin = __fadd2_rn(acc_a, make_float2(-acc_b.x, -acc_b.y));
+                if (inwin.x != inwin_prev.x || inwin.y != inwin_prev.y) park(v[j]);
+                inwin_prev = inwin;
             }
-            // a >= b voxel by voxel: the vector touches the window iff a and b advanced differently
-            const float2 inwin = __fadd2_rn(acc_a, make_float2(-acc_b.x, -acc_b.y));
-            if (inwin.x != inwin_prev.x || inwin.y != inwin_prev.y) park(v[j]);
-            inwin_prev = inwin;
+            seen_vec += kCountUnroll;
+            if (++rounds == 2048u) {           // packed 16-bit counters: at most 16 per half and round
+                flush();
+                inwin_prev = zero2;
+                rounds = 0;
+            }
         }
-        seen_vec += kCountUnroll;
-        if (++rounds == 32768u) {          // keep the float counters far below 2^24
-            flush();
-            inwin_prev = zero2;
-            rounds = 0;
-        }
-    }
+    };
+    if (ped == 0) stream(std::true_type{});
+    else stream(std::false_type{});
     if (blockIdx.x == 0) {                 // the vectors after the last full chunk, voxel by voxel
         const uint16_t* rest = reinterpret_cast<const uint16_t*>(body + nfull * kChunkVec);
         const size_t nrest = (nvec - nfull * kChunkVec) * 8;
