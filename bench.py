@@ -181,6 +181,8 @@ def run_gpu(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
+        # stdout carries exactly one JSON line: whatever NCCL has to say (its version banner) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
     import tissue_image_processing_b200 as tsp
     from tissue_image_processing_b200 import _native as nat
