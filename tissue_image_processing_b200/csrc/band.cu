@@ -1,8 +1,8 @@
 // Stages K4-K7: argmax over z (SP:61), band mask (SP:62-71) and weighted max projection (SP:72-81).
 //
 // The reference scatters a one-hot (Z, Y*X) volume at the height map, blurs it with sigma=(1,2,2)
-// and takes max_z(image * mask).  band_project_kernel never materialises either volume: for a
-// 32x64 pixel tile it walks only the planes near the tile's heights, builds the XY-blurred
+// and takes max_z(image * mask).  The band kernels never materialise either volume: for a
+// 32x64 pixel tile they walk only the planes near the tile's heights, builds the XY-blurred
 // one-hot plane A[z''] on the fly from the height-map tile (x pass into shared memory, y pass into
 // registers), keeps a 9-plane window of A per pixel and applies the z taps as the exact
 // edge-replicating 9-band matrix (SURVEY trap T9), multiplying the raw uint16 voxels as they
@@ -143,10 +143,6 @@ __device__ __forceinline__ bool band_index_error(const BandArgs& a) {
     return err != 0;
 }
 
-// b_s column permutation: the two float4 halves of every 8-pixel group live in separate 32-float
-// halves of the row, so that the y pass reads conflict-free 16-byte vectors
-__device__ __forceinline__ int band_col(int xq) { return ((xq >> 2) & 1) * 32 + (xq >> 3) * 4; }
-
 __device__ __forceinline__ uint4 band_load8(const uint16_t* __restrict__ src, int x, int X, bool vec) {
     if (vec && x + 7 < X) return __ldg(reinterpret_cast<const uint4*>(src));
     uint32_t w[4] = {0, 0, 0, 0};
@@ -156,207 +152,8 @@ __device__ __forceinline__ uint4 band_load8(const uint16_t* __restrict__ src, in
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-__global__ void __launch_bounds__(kBandThreads, 2) band_project_kernel(const BandArgs a) {
-    constexpr int CW = kBandTX + 2 * kBandHalo;      // 80
-    constexpr int CH = kBandTY + 2 * kBandHalo;      // 48
-    __shared__ __align__(16) int cz_s[CH][CW];
-    __shared__ __align__(16) float b_s[CH][kBandTX];
-    __shared__ uint32_t present[kBandMaxPlanes / 32];
-    __shared__ int zlo_s, zhi_s;
-
-    if (band_index_error(a)) return;            // the reference raises before projecting
-
-    const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * kBandTX, y0 = blockIdx.y * kBandTY;
-    if (tid == 0) {
-        zlo_s = INT32_MAX;
-        zhi_s = INT32_MIN;
-    }
-    for (int i = tid; i < (a.Z >> 5) + 1 && i < kBandMaxPlanes / 32; i += kBandThreads) present[i] = 0;
-    __syncthreads();
-    {
-        // all height-map loads of the thread are issued before any is used (tile + halo = 15 per thread)
-        constexpr int kPer = (CH * CW + kBandThreads - 1) / kBandThreads;
-        int vals[kPer];
-#pragma unroll
-        for (int k = 0; k < kPer; ++k) {
-            const int i = tid + k * kBandThreads;
-            const int yy = min(max(y0 - kBandHalo + i / CW, 0), a.Y - 1);
-            const int xx = min(max(x0 - kBandHalo + i % CW, 0), a.X - 1);
-            vals[k] = i < CH * CW ? __ldg(a.zmap + (size_t)yy * a.X + xx) : 0;
-        }
-        int lo = INT32_MAX, hi = INT32_MIN;
-#pragma unroll
-        for (int k = 0; k < kPer; ++k) {
-            const int i = tid + k * kBandThreads;
-            if (i < CH * CW) {
-                int v = vals[k];
-                if (a.shift != 0) v = min(max(v + a.shift, 0), a.Z);
-                cz_s[i / CW][i % CW] = v;
-                lo = min(lo, v);
-                hi = max(hi, v);
-                atomicOr(&present[v >> 5], 1u << (v & 31));
-            }
-        }
-        for (int o = 16; o; o >>= 1) {
-            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-        }
-        if ((tid & 31) == 0) {
-            atomicMin(&zlo_s, lo);
-            atomicMax(&zhi_s, hi);
-        }
-    }
-    __syncthreads();
-    const int zlo = zlo_s, zhi = zhi_s;
-
-    const int g = tid & 7, row = tid >> 3;                     // 8 pixels x0+8g .. +7 of row y0+row
-    const int x = x0 + g * kBandPix, y = y0 + row;
-    const bool inside = y < a.Y && x < a.X;
-    const int c0 = blockIdx.z * kBandMaxCh;
-    const int nc = min(kBandMaxCh, a.nch - c0);
-    const size_t plane = (size_t)a.Y * a.X;
-    const uint16_t* src0 = a.stack + (size_t)a.ch[c0] * a.channel_stride + a.z0_offset + (size_t)y * a.X + x;
-    const uint16_t* src1 = a.stack + (size_t)a.ch[c0 + (nc > 1 ? 1 : 0)] * a.channel_stride + a.z0_offset +
-                           (size_t)y * a.X + x;
-    const float ped = (float)a.pedestal + 8388608.0f;
-
-    // pending masks of planes t-4 .. t+4(+2): unrolled by 3 so the window shifts by 3 every 3 steps
-    float win[kBandPix][11];
-    float best[kBandMaxCh][kBandPix];
-#pragma unroll
-    for (int p = 0; p < kBandPix; ++p) {
-#pragma unroll
-        for (int i = 0; i < 11; ++i) win[p][i] = 0.f;
-#pragma unroll
-        for (int c = 0; c < kBandMaxCh; ++c) best[c][p] = 0.f;
-    }
-    int live = 0;                                   // steps during which this thread's window may be non-zero
-
-    uint4 nxt0 = make_uint4(0, 0, 0, 0), nxt1 = nxt0;
-    {
-        const int z = zlo - 4;
-        if (inside && z >= 0 && z < a.Z) {
-            nxt0 = band_load8(src0 + (size_t)z * plane, x, a.X, a.vec != 0);
-            if (nc > 1) nxt1 = band_load8(src1 + (size_t)z * plane, x, a.X, a.vec != 0);
-        }
-    }
-
-    for (int tb = zlo; tb <= zhi + 8; tb += 3) {
-#pragma unroll
-        for (int u = 0; u < 3; ++u) {
-            const int t = tb + u;
-            if (t > zhi + 8) break;                                    // block-uniform
-            const uint4 cur0 = nxt0, cur1 = nxt1;
-            {   // prefetch the voxels of the next output plane while this one is processed
-                const int zn = t - 3;
-                if (inside && zn >= 0 && zn < a.Z && t + 1 <= zhi + 8) {
-                    nxt0 = band_load8(src0 + (size_t)zn * plane, x, a.X, a.vec != 0);
-                    if (nc > 1) nxt1 = band_load8(src1 + (size_t)zn * plane, x, a.X, a.vec != 0);
-                }
-            }
-            const bool have = t <= zhi && ((present[t >> 5] >> (t & 31)) & 1u);
-            if (have) {                                                // block-uniform
-                // x pass: b_s[r][x] = sum_dx w2[dx] * [cz(r, x+dx) == t], 4 outputs per task
-                for (int task = tid; task < CH * (kBandTX / 4); task += kBandThreads) {
-                    const int r = task / (kBandTX / 4), xq = (task % (kBandTX / 4)) * 4;
-                    float oh[20];
-                    const int4* src = reinterpret_cast<const int4*>(&cz_s[r][xq]);
-                    bool any = false;
-#pragma unroll
-                    for (int q = 0; q < 5; ++q) {
-                        const int4 v = src[q];
-                        oh[4 * q + 0] = v.x == t ? 1.f : 0.f;
-                        oh[4 * q + 1] = v.y == t ? 1.f : 0.f;
-                        oh[4 * q + 2] = v.z == t ? 1.f : 0.f;
-                        oh[4 * q + 3] = v.w == t ? 1.f : 0.f;
-                        any |= (v.x == t) | (v.y == t) | (v.z == t) | (v.w == t);
-                    }
-                    float o[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (any) {
-#pragma unroll
-                        for (int k = 0; k < 17; ++k)
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) o[j] = fmaf(c_w2[k], oh[j + k], o[j]);
-                    }
-                    *reinterpret_cast<float4*>(&b_s[r][band_col(xq)]) = make_float4(o[0], o[1], o[2], o[3]);
-                }
-                __syncthreads();
-                // y pass: a_new[p] = sum_dy w2[dy] * b_s[row + dy][x + p]
-                float a_new[kBandPix];
-#pragma unroll
-                for (int p = 0; p < kBandPix; ++p) a_new[p] = 0.f;
-#pragma unroll
-                for (int dy = 0; dy < 17; ++dy) {
-                    const float4 lo4 = *reinterpret_cast<const float4*>(&b_s[row + dy][g * 4]);
-                    const float4 hi4 = *reinterpret_cast<const float4*>(&b_s[row + dy][32 + g * 4]);
-                    const float w = c_w2[dy];
-                    a_new[0] = fmaf(w, lo4.x, a_new[0]); a_new[1] = fmaf(w, lo4.y, a_new[1]);
-                    a_new[2] = fmaf(w, lo4.z, a_new[2]); a_new[3] = fmaf(w, lo4.w, a_new[3]);
-                    a_new[4] = fmaf(w, hi4.x, a_new[4]); a_new[5] = fmaf(w, hi4.y, a_new[5]);
-                    a_new[6] = fmaf(w, hi4.z, a_new[6]); a_new[7] = fmaf(w, hi4.w, a_new[7]);
-                }
-                __syncthreads();
-                bool nzero = false;
-#pragma unroll
-                for (int p = 0; p < kBandPix; ++p) nzero |= a_new[p] != 0.f;
-                if (nzero) {
-                    live = 9;
-                    // plane t feeds the masks of z = t-4+k (window slot u+k) with the (z, t) entry of the
-                    // edge-replicating z matrix: interior rows are the plain sigma=1 taps
-                    const bool edge = t - 4 < 4 || t + 4 > a.Z - 5;
-#pragma unroll
-                    for (int k = 0; k < 9; ++k) {
-                        const int z = t - 4 + k;
-                        float w = c_w1[8 - k];
-                        if (edge) w = (z >= 0 && z < a.Z) ? __ldg(a.wz + z * 9 + (8 - k)) : 0.f;
-#pragma unroll
-                        for (int p = 0; p < kBandPix; ++p) win[p][u + k] = fmaf(w, a_new[p], win[p][u + k]);
-                    }
-                }
-            }
-            const int z = t - 4;
-            if (live > 0 && inside && z >= 0 && z < a.Z) {
-                const uint32_t w0[4] = {cur0.x, cur0.y, cur0.z, cur0.w};
-                const uint32_t w1[4] = {cur1.x, cur1.y, cur1.z, cur1.w};
-#pragma unroll
-                for (int p = 0; p < kBandPix; ++p) {
-                    const float m = win[p][u];
-                    const uint32_t v0 = (p & 1) ? (w0[p >> 1] >> 16) : (w0[p >> 1] & 0xffffu);
-                    const float f0 = fmaxf(__uint_as_float(0x4B000000u | v0) - ped, 0.f);
-                    best[0][p] = fmaxf(best[0][p], __fmul_rn(f0, m));
-                    if (nc > 1) {
-                        const uint32_t v1 = (p & 1) ? (w1[p >> 1] >> 16) : (w1[p >> 1] & 0xffffu);
-                        const float f1 = fmaxf(__uint_as_float(0x4B000000u | v1) - ped, 0.f);
-                        best[1][p] = fmaxf(best[1][p], __fmul_rn(f1, m));
-                    }
-                }
-            }
-            live -= live > 0;
-        }
-        // slide the window by 3 planes
-#pragma unroll
-        for (int p = 0; p < kBandPix; ++p) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) win[p][i] = win[p][i + 3];
-            win[p][8] = win[p][9] = win[p][10] = 0.f;
-        }
-    }
-    if (inside) {
-#pragma unroll
-        for (int c = 0; c < kBandMaxCh; ++c) {
-            if (c < nc) {
-                float* dst = a.proj + ((size_t)a.ch[c0 + c] * a.Y + y) * a.X + x;
-#pragma unroll
-                for (int p = 0; p < kBandPix; ++p)
-                    if (x + p < a.X) dst[p] = best[c][p];
-            }
-        }
-    }
-}
-
 // ---- K5-K7 fused, second generation -------------------------------------------------------------
-// Same tile walk as band_project_kernel, with the per-plane work cut to what the data need:
+// Register-prefetch kernel (no TMA; any alignment): the per-plane work is cut to what the data need:
 //   * the indicator [cz == t] of a tile row is an 80-bit mask (three warp ballots); the 17-tap x blur of a
 //     binary line is a table lookup: window bits 0..8 and 9..16 index two shared tables of partial tap sums
 //     (2 LDS + 1 FADD per pixel instead of 17 FMA and 17 compares); all-zero / all-one windows are free;
@@ -1364,10 +1161,6 @@ static int launch_band_range(tsp_handle* h, const int32_t* d_zmap, int Z, int Y,
 
 // channels are projected two per CTA; an odd channel count ends with a one-channel launch
 static int launch_band_variant(tsp_handle* h, BandArgs a, dim3 grid, int pedestal, int C, cudaStream_t s) {
-    if (getenv("TSP_BAND_V1")) {
-        band_project_kernel<<<grid, kBandThreads, 0, s>>>(a);
-        return TSP_OK;
-    }
     // TMA path: rows 16-byte aligned (the tensor map's stride rule), tile not larger than the image
     const bool tma = a.vec && (a.X % 8 == 0) && a.X >= kBandTX && a.Y >= kBandTY && !getenv("TSP_BAND_V2");
     CUtensorMap tmap;
