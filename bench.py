@@ -167,7 +167,7 @@ def run_reference(args, rank, world):
             "data": "synthetic", "config": {"workload": WORKLOAD},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -264,9 +264,8 @@ def run_gpu(args, rank, world, local_rank):
             sampler.stop()
         if rank == 0:
             sm = {k: round(v[0] / max(v[1], 1), 5) for k, v in stages.items() if v[1]}
-            print(json.dumps({"ms_per_step": dev_ms / args.steps, "frames_in_flight": in_flight,
-                              "single_stream_ms_per_step": serial_ms / args.steps, "stage_ms": sm, "status": status}),
-                  flush=True)
+            emit({"ms_per_step": dev_ms / args.steps, "frames_in_flight": in_flight,
+                  "single_stream_ms_per_step": serial_ms / args.steps, "stage_ms": sm, "status": status})
         if world > 1:
             dist.destroy_process_group()
         return
@@ -369,12 +368,30 @@ def run_gpu(args, rank, world, local_rank):
         "clocks": clocks,
         "frame_status": status,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def emit(line):
+    """The one JSON line goes to the real stdout; everything else any library prints to fd 1 (NCCL's version
+    banner, for instance) was redirected to stderr in main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
