@@ -117,3 +117,35 @@ def test_movie_partition_world_size_2_gloo(tmp_path):
             want_p, want_z = orc.time_point_surface_projection(movie[t:t + 1], "TCZYX", 0, airyscan=False, z_map=True)
             assert np.array_equal(proj[t, :, 0], want_p), (rank, t)
             assert np.array_equal(zmap[t, 0, 0], want_z), (rank, t)
+
+
+def test_cli_flags_and_dispatch(monkeypatch, tmp_path):
+    """SP:329-423: same flags and defaults, same dispatch to the three drivers."""
+    import numpy as np
+    from tissue_image_processing_b200 import surface_projection as sp
+    opts, rest = sp.getOptions([])
+    assert rest == []
+    assert (opts.input, opts.output, opts.position_number, opts.movie_number, opts.reference_channel) == ("", "", 1, 1, 1)
+    assert (opts.chunk_size, opts.method, opts.bin_size, opts.only_position, opts.zmin, opts.zmax) == (
+        0, "max_averages", 1, 0, 0, 0)
+    assert not (opts.fixed_sample or opts.build_manifold or opts.airyscan or opts.separate_files)
+    calls = []
+    monkeypatch.setattr(sp, "movie_surface_projection", lambda *a, **k: calls.append(("movie", a, k)))
+    monkeypatch.setattr(sp, "large_image_projection", lambda *a, **k: calls.append(("large", a, k)))
+    d = str(tmp_path)
+    assert sp.main(["-i", d, "-n", "2", "-m", "3", "-r", "0", "-b", "2", "--method", "max_std", "--manifold",
+                    "--min-z", "1", "--max-z", "9", "--airyscan"]) == 0
+    kind, a, k = calls.pop()
+    assert kind == "movie"
+    assert a[0] == [os.path.join(d, "m%d.czi" % i) for i in (1, 2, 3)]
+    assert a[1:] == (0, [3, 3], 2, d, "max_std", 2, True, 0, 1, 9, True)
+    sp.main(["-i", d, "-n", "2", "-m", "3", "-f", "(2, 3)"])
+    assert calls.pop()[1][2] == [2, 3]
+    sp.main(["-i", d, "-o", d + "/out", "--fixed", "--file", "big.czi", "-c", "2048", "-n", "2"])
+    kind, a, k = calls.pop()
+    assert kind == "large" and a == (d, d + "/out", "big.czi")
+    assert np.array_equal(k["position"], [1, 2]) and k["chunk_size"] == 2048 and k["airyscan"] is False
+    open(os.path.join(d, "a.czi"), "w").close()
+    sp.main(["-i", d, "--separate-files", "--only-position", "1"])
+    kind, a, k = calls.pop()
+    assert kind == "movie" and a[0] == [os.path.join(d, "a.czi")] and a[2] == (1,) and k["output_name"] == "a.czi"

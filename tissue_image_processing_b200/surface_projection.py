@@ -282,3 +282,78 @@ def large_image_projection(input_dir, output_dir, input_file_name, position=1, r
         zmap_filename = os.path.join(output_dir, input_file_name.replace(postfix, pos_addition + "_zmap.npy"))
         save_tiff(projection_file_name, projection, axes="TCYX" if dims.T > 1 else "CYX", data_type="uint16")
         np.save(zmap_filename, zmap)
+
+
+# ------------------------------------------------------------------------------------------------
+# command line (SP:329-423): same flags, same dispatch
+# ------------------------------------------------------------------------------------------------
+CLI_FLAGS = (
+    # flags, dest, type, default, help                                              (SP:334-378)
+    (("-i", "--input"), "input", str, "", "input directory with movies m1, m2, m3, ... [default: current directory]"),
+    (("-o", "--output"), "output", str, "", "output directory [default: the input directory]"),
+    (("-f", "--position-final_movie"), "position_final_movie", str, "",
+     "final movie of each sample, in the order of the initial positions [default: all end in the last movie]"),
+    (("-n", "--position-number"), "position_number", int, 1, "number of initial positions"),
+    (("-m", "--movie-number"), "movie_number", int, 1, "number of movies"),
+    (("-r", "--reference_channel"), "reference_channel", int, 1, "channel the height map is taken from"),
+    (("-c", "--chunk-size"), "chunk_size", int, 0, "tile size of a large fixed-sample projection [default: whole image]"),
+    (("--method",), "method", str, "max_averages", "score method when --bin-size > 1"),
+    (("--file",), "file_name", str, None, "file name (fixed-sample projection)"),
+    (("-b", "--bin-size"), "bin_size", int, 1, "bin size of the block mean / variance"),
+    (("--only-position",), "only_position", int, 0, "project only this position [default: all]"),
+    (("--min-z",), "zmin", int, 0, "first plane considered"),
+    (("--max-z",), "zmax", int, 0, "last plane considered [default: all]"),
+)
+CLI_SWITCHES = (
+    (("--fixed",), "fixed_sample", "fixed-sample (tiled) projection instead of a movie projection"),
+    (("--manifold",), "build_manifold", "grow a continuous manifold instead of the pixel-wise argmax"),
+    (("--airyscan",), "airyscan", "airyscan-processed intensities (pedestal 10000)"),
+    (("--separate-files",), "separate_files", "project every czi file of the input directory on its own"),
+)
+
+
+def getOptions(argv=None):
+    """SP:329-379.  Returns (options, positional_args) like optparse did."""
+    import argparse
+    parser = argparse.ArgumentParser(usage="%(prog)s [options]", allow_abbrev=False)
+    for flags, dest, typ, default, text in CLI_FLAGS:
+        parser.add_argument(*flags, dest=dest, type=typ, default=default, help=text)
+    for flags, dest, text in CLI_SWITCHES:
+        parser.add_argument(*flags, dest=dest, action="store_true", default=False, help=text)
+    return parser.parse_known_args(argv)
+
+
+def main(argv=None):
+    """SP:381-423: dispatch to the fixed-sample, per-file or movie driver exactly as the reference's __main__."""
+    from ast import literal_eval
+    from glob import glob
+    options, _ = getOptions(argv)
+    input_dir = options.input or os.getcwd()
+    output_dir = options.output or input_dir
+    common = dict(method=options.method, bin_size=options.bin_size, build_manifold=options.build_manifold)
+    if options.fixed_sample:
+        position = options.only_position if options.only_position > 0 else \
+            np.arange(start=1, stop=options.position_number + 1)
+        large_image_projection(input_dir, output_dir, options.file_name, position=position,
+                               reference_channel=options.reference_channel, chunk_size=options.chunk_size,
+                               min_z=options.zmin, max_z=options.zmax, airyscan=options.airyscan, **common)
+    elif options.separate_files:
+        for file in glob(os.path.join(input_dir, "*.czi")):
+            movie_surface_projection([file], options.reference_channel, (1,), options.position_number, output_dir,
+                                     options.method, options.bin_size, options.build_manifold, options.only_position,
+                                     options.zmin, options.zmax, options.airyscan,
+                                     output_name=os.path.basename(file))
+    else:
+        if options.position_final_movie:
+            final = list(literal_eval(options.position_final_movie))
+        else:
+            final = [options.movie_number] * options.position_number
+        files = [os.path.join(input_dir, "m%d.czi" % (i + 1)) for i in range(options.movie_number)]
+        movie_surface_projection(files, options.reference_channel, final, options.position_number, output_dir,
+                                 options.method, options.bin_size, options.build_manifold, options.only_position,
+                                 options.zmin, options.zmax, options.airyscan)
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())
