@@ -42,6 +42,26 @@ def test_pipeline_equals_single_calls(tsp, slots):
         assert got[t][2]["has_nonzero"]
 
 
+@pytest.mark.parametrize("extra", [dict(bin_size=2, method="max_std"), dict(build_manifold=True),
+                                   dict(bin_size=3, method="max_averages", build_manifold=True)])
+def test_pipeline_binned_and_manifold_frames(tsp, extra):
+    """bin_size > 1 / build_manifold travel through the frame slots like every other argument."""
+    from tissue_image_processing_b200.movie import FramePipeline
+    movie = _movie(T=3)
+    got = {}
+    pipe = FramePipeline(slots=2, mode="exact")
+    pipe.project_frames(((t, movie[t]) for t in range(len(movie))),
+                        lambda t, p, z, st: got.__setitem__(t, (p.copy(), z.copy())),
+                        reference_channel=0, airyscan=False, **extra)
+    for t in range(len(movie)):
+        p, z = tsp.time_point_surface_projection(movie[t:t + 1], "TCZYX", 0, airyscan=False, z_map=True,
+                                                 mode="exact", **extra)
+        assert np.array_equal(got[t][0], p) and np.array_equal(got[t][1], z)
+    with pytest.raises(TypeError):
+        pipe.project_frames([(0, movie[0])], lambda *a: None, reference_channel=0, airyscan=False, bin_size=2,
+                            method="nope")
+
+
 def test_pipeline_propagates_index_error(tsp):
     from tissue_image_processing_b200.movie import FramePipeline
     movie = _movie(T=2, C=1, Z=20, Y=48, X=48)

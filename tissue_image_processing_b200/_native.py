@@ -234,7 +234,7 @@ MAX_SLOTS = 4
 
 
 def frame_submit(slot, stack, proj, zmap, reference_channel, min_z=0, max_z=0, airyscan=False, atoh_shift=0,
-                 mode="fast", device=None):
+                 mode="fast", device=None, bin_size=1, method="max_averages", build_manifold=False):
     """Enqueue one frame on a slot (asynchronous).  stack (C,Z,Y,X) uint16, proj (C,Y,X) float64 and zmap (Y,X)
     int64 are host arrays that must stay alive (and untouched) until frame_wait(slot)."""
     lib = load_library()
@@ -242,7 +242,8 @@ def frame_submit(slot, stack, proj, zmap, reference_channel, min_z=0, max_z=0, a
     Cn, Z, Y, X = stack.shape
     assert proj.dtype == np.float64 and proj.shape == (Cn, Y, X) and proj.flags.c_contiguous
     assert zmap.dtype == np.int64 and zmap.shape == (Y, X) and zmap.flags.c_contiguous
-    desc = make_desc(Cn, Z, Y, X, reference_channel, min_z, max_z, airyscan, atoh_shift, mode)
+    desc = make_desc(Cn, Z, Y, X, reference_channel, min_z, max_z, airyscan, atoh_shift, mode, bin_size, method,
+                     build_manifold)
     rc = lib.tsp_frame_submit(handle(device), int(slot), C.byref(desc), C.c_void_p(stack.ctypes.data),
                               C.c_void_p(proj.ctypes.data), C.c_void_p(zmap.ctypes.data))
     check(rc, "tsp_frame_submit")

@@ -77,6 +77,13 @@ class FramePipeline:
         kw = dict(reference_channel=int(params.get("reference_channel", 0)), min_z=int(params.get("min_z", 0)),
                   max_z=int(params.get("max_z", 0)), airyscan=bool(params.get("airyscan", True)),
                   atoh_shift=int(params.get("atoh_shift", 0)), mode=mode, device=device)
+        bin_size = int(params.get("bin_size", 1) or 1)
+        if bin_size > 1:
+            if params.get("method") not in _native.METHODS:
+                raise TypeError("exceptions must derive from BaseException")      # SP:53 raises a str
+            kw.update(bin_size=bin_size, method=params["method"])
+        if params.get("build_manifold", False):
+            kw.update(build_manifold=True)
         inflight = [None] * self.slots          # (t, stack, proj, zmap) per slot
         bufs = [None] * self.slots              # pinned output buffers per slot, reused while the shape holds
 
@@ -172,9 +179,7 @@ class FramePipeline:
         rank, world = rank_world()
         if mode is not None:
             params = dict(params, mode=mode)
-        if params.get("bin_size", 1) > 1 or params.get("build_manifold", False):
-            raise NotImplementedError("bin_size > 1 / build_manifold are not on the B200 path yet")
-        for k in ("axes", "z_map", "method", "bin_size", "build_manifold"):
+        for k in ("axes", "z_map"):
             params.pop(k, None)
 
         def frames():
