@@ -97,6 +97,43 @@ def test_percentile_float32_rank_beyond_2_24(nat):
     assert np.float32(st["percentile95"]) == np.float32(want) == np.float32(9.0)
 
 
+@pytest.mark.parametrize("kind", ["white16", "white12", "top", "constant", "airyscan", "gamma", "sparse",
+                                  "odd_offset", "window_edge"])
+def test_percentile_sampled_window_path(nat, kind):
+    """Volumes large enough (> 8 M voxels) for the sample -> value window -> streaming count pass; every
+    distribution must give numpy's float32 percentile exactly (or fall back to the full histogram by itself)."""
+    rng = np.random.default_rng(23)
+    n = 12_000_011
+    airy = kind == "airyscan"
+    if kind == "white16":
+        vol = rng.integers(0, 65536, size=n)
+    elif kind == "white12":
+        vol = rng.integers(0, 4096, size=n)
+    elif kind == "top":
+        vol = rng.integers(65000, 65536, size=n)            # the window saturates at 65535
+    elif kind == "constant":
+        vol = np.full(n, 1234)                              # every voxel lies inside the window
+    elif kind == "airyscan":
+        vol = rng.integers(9000, 14000, size=n)
+    elif kind == "gamma":
+        vol = np.minimum(rng.gamma(2.0, 300.0, size=n), 65535)
+    elif kind == "sparse":
+        vol = np.where(rng.random(n) < 0.02, rng.integers(1, 3000, size=n), 0)
+    elif kind == "window_edge":
+        vol = np.where(rng.random(n) < 0.9497, rng.integers(1000, 1024, size=n), rng.integers(1024, 1100, size=n))
+    else:
+        vol = rng.integers(0, 5000, size=n)
+    vol = vol.astype(np.uint16)
+    if kind == "odd_offset":
+        d = _cuda(np.concatenate([[0], vol]).astype(np.uint16))[1:]                 # 2-byte aligned start
+    else:
+        d = _cuda(vol)
+    st = nat.percentile95_nonzero(d, airyscan=airy)
+    want, cnt = _np_p95(vol, airy)
+    assert st["nonzero_count"] == cnt
+    assert np.float32(st["percentile95"]) == np.float32(want)
+
+
 def test_argmax_first_maximum_wins(nat):
     rng = np.random.default_rng(2)
     score = rng.integers(0, 4, size=(9, 40, 50)).astype(np.float32)       # many exact ties

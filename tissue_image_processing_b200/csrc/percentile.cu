@@ -8,9 +8,9 @@
 // Large volumes therefore take the order statistics in three steps, all exact:
 //   1. sample_window_kernel: coarse histogram of a pseudo-random 1/stride subsample of 16-byte vectors; its
 //      last CTA picks a value window [lo, lo+W) that contains the wanted ranks with overwhelming probability
-//   2. window_count_kernel: one streaming pass that only COUNTS (voxels > pedestal, voxels < lo)
-//      and histograms the few voxels inside the window; its last CTA resolves the ranks inside the window,
-//      or - if the window missed or was too wide - arms
+//   2. window_count_kernel: one streaming pass that only COUNTS (voxels > pedestal, clamp sum -> voxels above
+//      the window) and histograms the few voxels inside the window; its last CTA resolves the ranks inside
+//      the window, or - if the window missed or was too wide - arms
 //   3. hist_percentile_kernel, the full-histogram fallback (returns at once when not armed).
 // Small volumes (stride 1) use the full histogram directly.  "Last CTA" = atomic ticket after a fence, so the
 // whole percentile is three launches.
@@ -314,8 +314,9 @@ __device__ void window_select(const uint32_t* __restrict__ shist, int pedestal, 
         int lo = look.bin[0] << kCoarseShift, hi = (look.bin[1] << kCoarseShift) + (1 << kCoarseShift) - 1;
         if (lo < pedestal + 1) lo = pedestal + 1;
         if (hi > kHistBins - 1) hi = kHistBins - 1;
-        const int w = hi - lo + 1;
-        const bool ok = w <= kWinBins && w > 0;
+        int w = hi - lo + 1;
+        const bool ok = w < kWinBins && w > 0;
+        if (ok) w = (1 << (32 - __clz(w))) - 1;        // widened to 2^k - 1 values (clamp-and-sum count pass), k <= 12
         status[ST_WIN_LO] = lo;
         status[ST_WIN_N] = w;
         status[ST_WIN_OK] = ok ? 1 : 0;
@@ -325,7 +326,12 @@ __device__ void window_select(const uint32_t* __restrict__ shist, int pedestal, 
 
 __global__ void __launch_bounds__(kHistThreads, 1)
 sample_window_kernel(const uint16_t* __restrict__ vol, size_t count, uint32_t stride, int pedestal,
-                     uint32_t* __restrict__ shist, int32_t* __restrict__ status, unsigned int* __restrict__ ticket) {
+                     uint32_t* __restrict__ shist, int32_t* __restrict__ status, unsigned int* __restrict__ ticket,
+                     uint4* __restrict__ zero_ptr, size_t zero_vecs) {
+    // side job: clear the accumulation volume of the score stage.  This kernel is latency bound (it reads 1/32 of the
+    // volume), the stores ride along for free - as a memset node or inside the count pass they cost 4 us
+    for (size_t i = (size_t)blockIdx.x * kHistThreads + threadIdx.x; i < zero_vecs; i += (size_t)gridDim.x * kHistThreads)
+        zero_ptr[i] = make_uint4(0, 0, 0, 0);
     __shared__ uint32_t sh[kCoarseBins];
     for (int i = threadIdx.x; i < kCoarseBins; i += kHistThreads) sh[i] = 0;
     __syncthreads();
@@ -362,82 +368,122 @@ sample_window_kernel(const uint16_t* __restrict__ vol, size_t count, uint32_t st
     window_select(shist, pedestal, status);
 }
 
+// ---- step 2: streaming count pass -----------------------------------------------------------------
+// One pass over the volume that only counts.  The window of step 1 is widened to W = 2^k - 1 values,
+// [lo, lo + W), and every voxel is reduced to
+//     c(v) = clamp(v, lo - 1, lo + W) - (lo - 1)  in [0, 2^k]:   0 below the window, 2^k above it, d + 1 at window bin d
+// so ONE clamped value per voxel carries both facts the pass needs: a 16-byte vector touches the window iff some c
+// has non-zero low k bits (one OR over the vector), and the sum R of all c gives the count above the window once
+// the window's own share sum_d hist[d] (d + 1) is taken out:
+//     above = (R - sum_d hist[d] (d + 1)) >> k,        below = count - in_window - above.
+// Everything runs on packed uint16 pairs: VIMNMX.U16x2 max / min, a plain 32-bit subtract (no borrow: both halves
+// are >= lo - 1), IDP.2A sums both halves into a 32-bit counter - 27 instructions per 16-byte vector.  The
+// ~2 % of vectors that touch the window are parked in a shared queue and histogrammed after the stream.
+// Measured on B200 (config 2, 537 MB): 80 us for the bare read stream of this very loop, +7 us for the counting.
+constexpr int kCountThreads = 512;
+constexpr int kCountUnroll = 4;
+constexpr int kQueueCap = 1536;              // parked 16-byte vectors per CTA (24 KB)
+static_assert(kWinBins == kCountThreads * 8, "window_finalize keeps eight window bins per thread");
+
 // ---- step 3 (run by the last CTA of window_count_kernel) -----------------------------------------------
+// Eight window bins per thread stay in registers: one round of loads gives the window total, its share of the
+// clamp sum, an exclusive scan, and - once the counts below the window are known - both ranks.
 __device__ void window_finalize(const uint32_t* __restrict__ gwin, const unsigned long long* __restrict__ gcounters,
                                 unsigned long long count, int pedestal, int32_t* __restrict__ status) {
+    __shared__ unsigned long long warp_tot[kCountThreads / 32], warp_share[kCountThreads / 32];
+    __shared__ int found[2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned long long n = __ldcg(gcounters);      // voxels > pedestal
+    const unsigned long long clamp_sum = __ldcg(gcounters + 1);
+    const uint4 b0 = __ldcg(reinterpret_cast<const uint4*>(gwin) + 2 * threadIdx.x);
+    const uint4 b1 = __ldcg(reinterpret_cast<const uint4*>(gwin) + 2 * threadIdx.x + 1);
+    const uint32_t bins[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    unsigned long long mine = 0, share = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        mine += bins[i];
+        share += (unsigned long long)bins[i] * (unsigned)(8 * threadIdx.x + i + 1);
+    }
+    unsigned long long incl = mine;
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+    }
+    for (int o = 16; o; o >>= 1) share += __shfl_xor_sync(0xffffffffu, share, o);
+    if (lane == 31) warp_tot[warp] = incl;
+    if (lane == 0) warp_share[warp] = share;
+    if (threadIdx.x < 2) found[threadIdx.x] = -1;
+    __syncthreads();
+    unsigned long long before = 0, in_window = 0, share_all = 0;
+    for (int w = 0; w < kCountThreads / 32; ++w) {
+        if (w < warp) before += warp_tot[w];
+        in_window += warp_tot[w];
+        share_all += warp_share[w];
+    }
     if (n == 0) {
         if (threadIdx.x == 0) write_result(status, 0, 0.f);
         return;
     }
-    const unsigned long long zeros = count - n;     // voxels <= pedestal (they are all below the window)
-    const unsigned long long below_nz = __ldcg(gcounters + 1) - zeros;
+    const uint32_t wn = (uint32_t)status[ST_WIN_N];
+    const int k = 32 - __clz(wn);                        // wn = 2^k - 1
+    const unsigned long long zeros = count - n;          // voxels <= pedestal (they are all below the window)
+    const bool sane = clamp_sum >= share_all && ((clamp_sum - share_all) & ((1ull << k) - 1)) == 0;
+    const unsigned long long above = sane ? (clamp_sum - share_all) >> k : 0;
+    const bool ok = sane && in_window + above + zeros <= count;
+    const unsigned long long below_nz = ok ? count - in_window - above - zeros : 0;
     const RankPair rp = numpy_ranks(n);
-    RankLookup look = block_rank_lookup(gwin, kWinBins, 0, below_nz, rp.prev, rp.next);
-    if (threadIdx.x == 0) {
-        const int lo = status[ST_WIN_LO];
-        if (look.bin[0] < 0 || look.bin[1] < 0 || rp.prev < below_nz) {
-            status[ST_NEED_FULL] = 1;               // the sample window missed: exact fallback
-        } else {
-            write_result(status, n, numpy_lerp((float)(lo + look.bin[0] - pedestal),
-                                               (float)(lo + look.bin[1] - pedestal), rp.gamma));
+    const unsigned long long ranks[2] = {rp.prev, rp.next};
+    const unsigned long long excl = below_nz + before + incl - mine;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        if (ranks[r] >= excl && ranks[r] < excl + mine) {
+            unsigned long long cum = excl;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                cum += bins[i];
+                if (cum > ranks[r]) {
+                    found[r] = 8 * threadIdx.x + i;
+                    break;
+                }
+            }
         }
     }
-}
-
-// ---- step 2: streaming count pass -----------------------------------------------------------------
-// One pass over the volume that only counts.  The integer pipe of an SMSP issues one warp instruction every
-// two cycles, so compare/shift/add per voxel cannot keep up with HBM; the counting is done on the FP32 pipe
-// instead.  PRMT turns a uint16 into the float 2^23 + v (exact), a saturating add against a threshold is the
-// flag [v >= t] as 0.0 or 1.0, and packed FADD2 adds the flags of two voxels at a time:
-//     nz  = #[v >= pedestal + 1]        a = #[v >= lo]        b = #[v >= lo + wn]
-// A 16-byte vector holds a voxel of the value window [lo, lo + wn) exactly when its a and b counts differ;
-// those rare vectors are parked in a shared queue and histogrammed after the stream.
-constexpr int kCountThreads = 512;
-constexpr int kCountUnroll = 4;
-constexpr int kQueueCap = 1536;              // parked 16-byte vectors per CTA (24 KB)
-
-__device__ __forceinline__ float sat_add(float a, float b) {
-    float r;
-    asm("add.sat.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
-    return r;
-}
-__device__ __forceinline__ float biased_lo(uint32_t w, uint32_t magic) {
-    uint32_t r;
-    asm("prmt.b32 %0, %1, %2, 0x7410;" : "=r"(r) : "r"(w), "r"(magic));
-    return __uint_as_float(r);
-}
-__device__ __forceinline__ float biased_hi(uint32_t w, uint32_t magic) {
-    uint32_t r;
-    asm("prmt.b32 %0, %1, %2, 0x7432;" : "=r"(r) : "r"(w), "r"(magic));
-    return __uint_as_float(r);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int lo = status[ST_WIN_LO];
+        if (!ok || found[0] < 0 || found[1] < 0 || rp.prev < below_nz) {
+            status[ST_NEED_FULL] = 1;               // the sample window missed: exact fallback
+        } else {
+            write_result(status, n, numpy_lerp((float)(lo + found[0] - pedestal), (float)(lo + found[1] - pedestal),
+                                               rp.gamma));
+        }
+    }
 }
 
 __global__ void __launch_bounds__(kCountThreads, 2)
 window_count_kernel(const uint16_t* __restrict__ vol, size_t count, int pedestal, int32_t* __restrict__ status,
                     uint32_t* __restrict__ gwin, unsigned long long* __restrict__ gcounters,
-                    unsigned int* __restrict__ ticket, uint4* __restrict__ zero_ptr, size_t zero_vecs) {
-    // side job: clear the accumulation volume of the next stage (saves a separate memset pass between kernels)
-    for (size_t i = (size_t)blockIdx.x * kCountThreads + threadIdx.x; i < zero_vecs; i += (size_t)gridDim.x * kCountThreads)
-        zero_ptr[i] = make_uint4(0, 0, 0, 0);
+                    unsigned int* __restrict__ ticket) {
     if (status[ST_WIN_OK] == 0) return;
     __shared__ uint32_t win[kWinBins];
     __shared__ uint4 queue[kQueueCap];
     __shared__ uint32_t qtail;
     __shared__ unsigned long long blk[2];
-    const uint32_t lo = (uint32_t)status[ST_WIN_LO], wn = (uint32_t)status[ST_WIN_N];
+    const uint32_t lo = (uint32_t)status[ST_WIN_LO], wn = (uint32_t)status[ST_WIN_N];     // wn = 2^k - 1, lo >= 1
     const uint32_t ped = (uint32_t)pedestal;
     for (int i = threadIdx.x; i < kWinBins; i += kCountThreads) win[i] = 0;
     if (threadIdx.x < 2) blk[threadIdx.x] = 0;
     if (threadIdx.x == 0) qtail = 0;
     __syncthreads();
 
-    unsigned long long nz_total = 0, below_total = 0;      // per-thread integer totals (scalar path + flushes)
+    unsigned long long nz_total = 0, clamp_total = 0;      // per-thread totals (scalar path + flushes)
     auto one = [&](uint32_t v) {
         if (v > ped) ++nz_total;
-        if (v < lo) ++below_total;
-        const uint32_t d = v - lo;
-        if (d < wn) atomicAdd(&win[d], 1u);
+        if (v >= lo) {
+            const uint32_t d = v - lo;
+            clamp_total += d < wn ? d + 1 : wn + 1;
+            if (d < wn) atomicAdd(&win[d], 1u);
+        }
     };
     const uintptr_t addr = reinterpret_cast<uintptr_t>(vol);
     size_t head = ((16 - (addr & 15)) & 15) / 2;
@@ -449,25 +495,6 @@ window_count_kernel(const uint16_t* __restrict__ vol, size_t count, int pedestal
         for (size_t i = threadIdx.x; i < head; i += kCountThreads) one(vol[i]);
         for (size_t i = tail0 + threadIdx.x; i < count; i += kCountThreads) one(vol[i]);
     }
-
-    // thresholds in the biased domain: sat(f + c) with c = -(2^23 + t - 1) is [v >= t]; all values are exact
-    const float c_nz = -(8388608.0f + (float)ped);                 // t = ped + 1
-    const float c_a = -(8388608.0f + (float)lo - 1.0f);            // t = lo          (lo >= ped + 1 >= 1)
-    const float c_b = -(8388608.0f + (float)(lo + wn) - 1.0f);     // t = lo + wn
-    uint32_t magic = 0x4B000000u;
-    asm volatile("" : "+r"(magic));
-    float2 acc_nz = make_float2(0.f, 0.f), acc_a = acc_nz, acc_b = acc_nz;
-    uint32_t acc_nzi = 0;                      // pedestal 0: packed 16-bit counters of min(v, 1) (integer pipe)
-    uint32_t seen_vec = 0, rounds = 0;
-    auto flush = [&]() {
-        nz_total += (unsigned long long)(acc_nzi & 0xffffu) + (unsigned long long)(acc_nzi >> 16);
-        acc_nzi = 0;
-        nz_total += (unsigned long long)(acc_nz.x + acc_nz.y);
-        below_total += (unsigned long long)seen_vec * 8ull - (unsigned long long)(acc_a.x + acc_a.y);
-        acc_nz = acc_a = acc_b = make_float2(0.f, 0.f);
-        seen_vec = 0;
-    };
-    const float2 zero2 = make_float2(0.f, 0.f);
     auto park = [&](const uint4& vec) {      // rare: the vector goes to the CTA queue, histogrammed after the stream
         const uint32_t slot = atomicAdd(&qtail, 1u);
         if (slot < kQueueCap) {
@@ -482,14 +509,22 @@ window_count_kernel(const uint16_t* __restrict__ vol, size_t count, int pedestal
             }
         }
     };
+    // packed clamp bounds; the top bound saturates at 65535 (then nothing lies above the window)
+    const uint32_t lo1_2 = (lo - 1) * 0x00010001u;
+    const uint32_t hi_2 = min(lo + wn, 65535u) * 0x00010001u;
+    const uint32_t mask_2 = wn * 0x00010001u;
+    const uint32_t ped1_2 = (ped + 1) * 0x00010001u, ped_2 = ped * 0x00010001u;
+    uint32_t acc_c = 0, acc_nz = 0, rounds = 0;
+    auto flush = [&]() {
+        clamp_total += acc_c;
+        nz_total += acc_nz;
+        acc_c = acc_nz = 0;
+    };
     // chunk c = vectors [c * T * U, (c + 1) * T * U): thread t takes c * T * U + j * T + t, j < U (no bounds checks)
     constexpr size_t kChunkVec = (size_t)kCountThreads * kCountUnroll;
-    float2 inwin_prev = make_float2(0.f, 0.f);      // running a - b per half (exact small integers)
     const size_t nfull = nvec / kChunkVec;
-    // INT_NZ (pedestal 0): the non-zero flags are min(v, 1) on packed pairs (VIMNMX.U16x2) summed by plain integer
-    // adds - the integer pipe carries them while the FP32 pipe does the two window flags
-    auto stream = [&](auto int_nz_tag) {
-        constexpr bool INT_NZ = decltype(int_nz_tag)::value;
+    auto stream = [&](auto zero_pedestal_tag) {
+        constexpr bool ZERO_PED = decltype(zero_pedestal_tag)::value;       // [v > 0] is min(v, 1)
         for (size_t chunk = blockIdx.x; chunk < nfull; chunk += gridDim.x) {
             const uint4* src = body + chunk * kChunkVec + threadIdx.x;
             uint4 v[kCountUnroll];
@@ -498,25 +533,18 @@ window_count_kernel(const uint16_t* __restrict__ vol, size_t count, int pedestal
 #pragma unroll
             for (int j = 0; j < kCountUnroll; ++j) {
                 const uint32_t ws[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
-                if (INT_NZ)
-                    acc_nzi += (__vminu2(ws[0], 0x00010001u) + __vminu2(ws[1], 0x00010001u)) +
-                               (__vminu2(ws[2], 0x00010001u) + __vminu2(ws[3], 0x00010001u));
+                uint32_t c[4], f[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const float f0 = biased_lo(ws[q], magic), f1 = biased_hi(ws[q], magic);
-                    if (!INT_NZ) acc_nz = __fadd2_rn(acc_nz, make_float2(sat_add(f0, c_nz), sat_add(f1, c_nz)));
-                    acc_a = __fadd2_rn(acc_a, make_float2(sat_add(f0, c_a), sat_add(f1, c_a)));
-                    acc_b = __fadd2_rn(acc_b, make_float2(sat_add(f0, c_b), sat_add(f1, c_b)));
+                    c[q] = __vminu2(__vmaxu2(ws[q], lo1_2), hi_2) - lo1_2;
+                    f[q] = ZERO_PED ? __vminu2(ws[q], 0x00010001u) : __vminu2(__vmaxu2(ws[q], ped_2), ped1_2) - ped_2;
                 }
-                // a >= b voxel by voxel: the vector touches the window iff a and b advanced differently
-                const float2 inwin = __fadd2_rn(acc_a, make_float2(-acc_b.x, -acc_b.y));
-                if (inwin.x != inwin_prev.x || inwin.y != inwin_prev.y) park(v[j]);
-                inwin_prev = inwin;
+                acc_c = __dp2a_lo((c[0] + c[1]) + (c[2] + c[3]), 0x0101u, acc_c);      // halves <= 4 * 4096: no carry
+                acc_nz = __dp2a_lo((f[0] + f[1]) + (f[2] + f[3]), 0x0101u, acc_nz);
+                if (((c[0] | c[1]) | (c[2] | c[3])) & mask_2) park(v[j]);
             }
-            seen_vec += kCountUnroll;
-            if (++rounds == 2048u) {           // packed 16-bit counters: at most 16 per half and round
+            if (++rounds == 8192u) {           // 32-bit counters: at most 8 * kCountUnroll * 4096 per round
                 flush();
-                inwin_prev = zero2;
                 rounds = 0;
             }
         }
@@ -543,21 +571,21 @@ window_count_kernel(const uint16_t* __restrict__ vol, size_t count, int pedestal
             }
         }
     }
-    unsigned long long nz = nz_total, below = below_total;
+    unsigned long long nz = nz_total, cs = clamp_total;
     for (int o = 16; o; o >>= 1) {
         nz += __shfl_xor_sync(0xffffffffu, nz, o);
-        below += __shfl_xor_sync(0xffffffffu, below, o);
+        cs += __shfl_xor_sync(0xffffffffu, cs, o);
     }
     if ((threadIdx.x & 31) == 0) {
         atomicAdd(&blk[0], nz);
-        atomicAdd(&blk[1], below);
+        atomicAdd(&blk[1], cs);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         atomicAdd(&gcounters[0], blk[0]);
         atomicAdd(&gcounters[1], blk[1]);
     }
-    for (int i = threadIdx.x; i < kWinBins; i += kCountThreads)
+    for (int i = threadIdx.x; i <= (int)wn && i < kWinBins; i += kCountThreads)
         if (win[i]) atomicAdd(&gwin[i], win[i]);
     if (!is_last_block(ticket)) return;
     window_finalize(gwin, gcounters, (unsigned long long)count, pedestal, status);
@@ -616,11 +644,11 @@ int launch_percentile(tsp_handle* h, const uint16_t* d_vol, size_t count, int pe
         TSP_LAUNCH_CHECK(h);
         return TSP_OK;
     }
-    sample_window_kernel<<<hist_grid(h, count, stride), kHistThreads, 0, s>>>(d_vol, count, stride, pedestal,
-                                                                             hist_sample, d_status, tickets + 1);
+    sample_window_kernel<<<hist_grid(h, count, stride), kHistThreads, 0, s>>>(
+        d_vol, count, stride, pedestal, hist_sample, d_status, tickets + 1, (uint4*)zero_ptr, zero_bytes / 16);
     TSP_LAUNCH_CHECK(h);
     window_count_kernel<<<h->sm_count * 2, kCountThreads, 0, s>>>(d_vol, count, pedestal, d_status, win, counters,
-                                                                  tickets + 2, (uint4*)zero_ptr, zero_bytes / 16);
+                                                                  tickets + 2);
     TSP_LAUNCH_CHECK(h);
     // exact fallback, armed by ST_NEED_FULL (returns at once otherwise)
     hist_percentile_kernel<<<hist_grid(h, count, 1), kHistThreads, kHistSmemBytes, s>>>(
