@@ -48,15 +48,16 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def synth_frame_device(torch, seed, device):
+def synth_frame_device(torch, seed, device, shape=None):
     """Same construction as oracle/synth.py (bright sheet on a smooth surface, sparse texture, noise),
     generated on the device because the numpy generator needs minutes at this size."""
+    Zs, Ys, Xs = shape or (Z, Y, X)
     g = torch.Generator(device=device).manual_seed(1000 + seed)
-    zz = torch.arange(Z, device=device, dtype=torch.float32)[:, None, None]
-    yy = torch.arange(Y, device=device, dtype=torch.float32)[None, :, None]
-    xx = torch.arange(X, device=device, dtype=torch.float32)[None, None, :]
-    h = Z / 2 + 0.15 * Z * torch.sin(2 * np.pi * 1.5 * yy / Y + 0.1 * seed) + 0.10 * Z * torch.cos(2 * np.pi * xx / X)
-    tex = 0.5 + 0.5 * (torch.rand((1, Y, X), device=device, generator=g) < 0.15)
+    zz = torch.arange(Zs, device=device, dtype=torch.float32)[:, None, None]
+    yy = torch.arange(Ys, device=device, dtype=torch.float32)[None, :, None]
+    xx = torch.arange(Xs, device=device, dtype=torch.float32)[None, None, :]
+    h = Zs / 2 + 0.15 * Zs * torch.sin(2 * np.pi * 1.5 * yy / Ys + 0.1 * seed) + 0.10 * Zs * torch.cos(2 * np.pi * xx / Xs)
+    tex = 0.5 + 0.5 * (torch.rand((1, Ys, Xs), device=device, generator=g) < 0.15)
     sig = 300.0 + 2500.0 * torch.exp(-(zz - h) ** 2 / 8.0) * tex
     sig += torch.sqrt(8.0 * sig) * torch.randn(sig.shape, device=device, generator=g)      # ~ 8*Poisson(sig/8)
     sig += 20.0 * torch.randn(sig.shape, device=device, generator=g)
@@ -173,6 +174,72 @@ def run_reference(args, rank, world):
 # --------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------
+MOVIE_SHAPE = (48, 1024, 1024)          # BASELINE configs[2]: 200-frame 1024x1024x48 time-lapse, frame-parallel
+
+
+def run_movie_leg(args, torch, nat, pipe, device, local_rank, rank, barrier, max_over_ranks, world):
+    """BASELINE configs[2] next to the headline: `--movie-frames` frames of 1024x1024x48 per GPU (frames are dealt
+    round-robin to the ranks, so N GPUs project N times as many in the same time), device-resident with 3 frames
+    in flight and end to end through movie.FramePipeline from pinned host frames."""
+    n = args.movie_frames
+    if n <= 0:
+        return None
+    Zm, Ym, Xm = MOVIE_SHAPE
+    dframes = [synth_frame_device(torch, 50 + 10 * rank + i, device, MOVIE_SHAPE) for i in range(4)]
+    projs = [nat.DeviceProjector(1, Zm, Ym, Xm, reference_channel=0, airyscan=False, mode=args.mode,
+                                 device=local_rank) for _ in range(3)]
+    strs = [torch.cuda.Stream(device=device) for _ in range(3)]
+
+    def resident(k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for st in strs:
+            st.wait_event(e0)
+        for i in range(k):
+            with torch.cuda.stream(strs[i % 3]):
+                projs[i % 3].run(dframes[i % 4])
+        for st in strs:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            torch.cuda.current_stream().wait_event(ev)
+        e1.record()
+        return e0, e1
+
+    resident(6)
+    barrier()
+    e0, e1 = resident(n)
+    barrier()
+    dev_ms = max_over_ranks(e0.elapsed_time(e1))
+    hframes = []
+    for f in dframes:
+        hbuf = nat.pinned_empty((1, Zm, Ym, Xm), np.uint16)
+        torch.from_numpy(hbuf).copy_(f)
+        hframes.append(hbuf)
+    torch.cuda.synchronize()
+    seen = [0]
+
+    def sink(t, proj, zmap, status):
+        seen[0] += int(zmap[0, 0] >= 0)
+
+    def gen(k):
+        for i in range(k):
+            yield i, hframes[i % 4]
+
+    pipe.project_frames(gen(4), sink, reference_channel=0, airyscan=False)
+    barrier()
+    t0 = time.perf_counter()
+    pipe.project_frames(gen(n), sink, reference_channel=0, airyscan=False)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    return {"workload": "1024x1024x48 uint16 time-lapse frames (BASELINE configs[2]), %d frames per GPU, frames "
+                        "partitioned over the ranks, no collective" % n,
+            "frames": n * world, "frames_per_s": n * world / (dev_ms * 1e-3),
+            "frames_per_s_e2e": n * world / e2e_s, "ms_per_frame": dev_ms / n, "ms_per_frame_e2e": e2e_s * 1e3 / n,
+            "voxels_per_s": n * world * Zm * Ym * Xm / (dev_ms * 1e-3),
+            "note": "frames_per_s: device-resident, 3 frames in flight per GPU; frames_per_s_e2e: pinned host frame in, "
+                    "float64 projection + int64 height map out (PCIe-bound)"}
+
+
 def run_gpu(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -304,6 +371,7 @@ def run_gpu(args, rank, world, local_rank):
     pipe.project_frames(frames(args.steps), sink, reference_channel=0, airyscan=False)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
+    movie = run_movie_leg(args, torch, nat, pipe, device, local_rank, rank, barrier, max_over_ranks, world)
     clocks = sampler.stop() if sampler else None
 
     if rank != 0:
@@ -320,17 +388,22 @@ def run_gpu(args, rank, world, local_rank):
     dom = max(stage_ms, key=stage_ms.get)
     # algorithmic bytes of each stage of the fast path (per frame): every score-path stage is charged the one
     # uint16 read of the reference channel it exists for; band = one uint16 read + both outputs
-    stage_bytes = {"percentile": 2 * vox, "decimate": 2 * vox, "blur_score": 2 * vox, "blur_pre": 2 * vox,
+    stage_bytes = {"percentile": 2 * vox, "percentile_count": 2 * vox, "percentile_sample": 2 * vox // 32,
+                   "decimate": 2 * vox, "blur_score": 2 * vox, "blur_pre": 2 * vox,
                    "prepare": 2 * vox, "band": 2 * vox + Y * X * 8, "interp_argmax": 2 * vox, "coarse": 2 * vox,
                    "argmax": 2 * vox}
+    stage_kernel = {"decimate": "decimate_ring_kernel", "percentile_count": "window_count_kernel",
+                    "percentile_sample": "sample_window_kernel", "band": "band_project4_kernel",
+                    "interp_argmax": "interp_argmax_kernel", "coarse": "coarse_xy_kernel + coarse_zmix_kernel"}
     achieved = stage_bytes.get(dom, 2 * vox) / (stage_ms[dom] * 1e-3) / 1e9
     # dram__bytes_read.sum + dram__bytes_write.sum per frame of each stage's kernels, from the ncu --set full capture
-    # of this very workload (profiles/r1r_ncu_full_summary.txt); only meaningful for the default fast mode
-    ncu_traffic = {"percentile": 16.84e6 + 536.9e6 + 23.28e6 + 0.06e6, "decimate": 555.7e6 + 23.45e6,
-                   "coarse": 2 * 17.45e6, "interp_argmax": 5.57e6, "band": 111.2e6 + 7.14e6 + 0.07e6}
+    # of this very workload (profiles/r1v_ncu_full_summary.txt); only meaningful for the default fast mode
+    ncu_traffic = {"percentile_sample": 16.84e6, "percentile_count": 537.0e6 + 5.69e6, "percentile": 0.06e6,
+                   "decimate": 555.8e6 + 19.76e6, "coarse": 2 * 17.45e6, "interp_argmax": 5.57e6,
+                   "band": 111.2e6 + 7.82e6 + 0.07e6}
     traffic = ncu_traffic.get(dom) if args.mode == "fast" else None
     # the CPU leg runs on rank 0 at N=1 only (at N>1 it would only add minutes next to seven idle ranks)
-    cpu_v, cpu_wall = cpu_baseline((48, 640, 640), procs=1) if world == 1 else (None, 0.0)
+    cpu_v, cpu_wall = cpu_baseline((48, 1024, 1024), procs=1) if world == 1 else (None, 0.0)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
@@ -349,9 +422,9 @@ def run_gpu(args, rank, world, local_rank):
                 "single_call_ms": single_s * 1e3 / args.steps,
                 "single_call_api": "time_point_surface_projection(frame, 'TCZYX', ...) one blocking call per frame"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": stage_kernel.get(dom, dom), "stage": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic,
-                     "traffic_source": "ncu --set full, profiles/r1r_ncu_full_summary.txt (per frame, all kernels of "
+                     "traffic_source": "ncu --set full, profiles/r1v_ncu_full_summary.txt (per frame, all kernels of "
                                        "the stage)", "peak_source": peak_src,
                      "kernel_ms": stage_ms[dom]},
         "frame_roofline": {"achieved": frame_gbs, "peak": peak, "unit": "GB/s", "frac": frame_gbs / peak,
@@ -362,8 +435,9 @@ def run_gpu(args, rank, world, local_rank):
                           "frac_of_measured_peak": frame_bytes * args.steps / (serial_ms * 1e-3) / 1e9 / peak,
                           "note": "one frame at a time on one stream = the latency of a single stack"},
         "stage_ms": stage_ms,
+        "movie": movie,
         "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": 1, "kind": "port",
-                         "sample": ("one 640x640x48 crop of the workload frame, %.1f s" % cpu_wall) if world == 1
+                         "sample": ("one 1024x1024x48 crop of the workload frame, %.1f s" % cpu_wall) if world == 1
                          else "not measured at N>1 (see the N=1 line)"},
         "clocks": clocks,
         "frame_status": status,
@@ -399,6 +473,8 @@ def main():
     ap.add_argument("--mode", default="fast", choices=["fast", "exact", "bitexact"])
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--device-only", action="store_true", help="development aid: skip the end-to-end and CPU legs")
+    ap.add_argument("--movie-frames", type=int, default=48,
+                    help="frames per GPU of the 1024x1024x48 movie leg (BASELINE configs[2]); 0 skips it")
     ap.add_argument("--streams", type=int, default=3, help="independent frames in flight per GPU (CUDA streams)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -47,7 +47,8 @@ int get_tensor_map_encoder(EncodeTiledFn* out) {
 }
 
 static const char* kStageNames[STG_COUNT] = {"percentile", "decimate", "coarse", "interp_argmax", "prepare",
-                                             "blur_pre", "blur_score", "argmax", "band", "widen"};
+                                             "blur_pre", "blur_score", "argmax", "band", "widen",
+                                             "percentile_sample", "percentile_count"};
 
 struct Crop {
     int z0;        // first plane of the cropped stack inside the full stack

@@ -42,7 +42,7 @@ void set_error(const char* fmt, ...);
 
 enum Stage {
     STG_PERCENTILE = 0, STG_DECIMATE, STG_COARSE, STG_INTERP_ARGMAX, STG_PREPARE, STG_BLUR_PRE, STG_BLUR_SCORE,
-    STG_ARGMAX, STG_BAND, STG_WIDEN, STG_COUNT
+    STG_ARGMAX, STG_BAND, STG_WIDEN, STG_PCT_SAMPLE, STG_PCT_COUNT, STG_COUNT
 };
 
 #define TSP_CUDA(expr)                                                                       \

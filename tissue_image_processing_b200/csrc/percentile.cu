@@ -647,9 +647,11 @@ int launch_percentile(tsp_handle* h, const uint16_t* d_vol, size_t count, int pe
     sample_window_kernel<<<hist_grid(h, count, stride), kHistThreads, 0, s>>>(
         d_vol, count, stride, pedestal, hist_sample, d_status, tickets + 1, (uint4*)zero_ptr, zero_bytes / 16);
     TSP_LAUNCH_CHECK(h);
+    prof_mark(h, s, STG_PCT_SAMPLE);
     window_count_kernel<<<h->sm_count * 2, kCountThreads, 0, s>>>(d_vol, count, pedestal, d_status, win, counters,
                                                                   tickets + 2);
     TSP_LAUNCH_CHECK(h);
+    prof_mark(h, s, STG_PCT_COUNT);      // what follows (the gated fallback) is booked on the caller's STG_PERCENTILE
     // exact fallback, armed by ST_NEED_FULL (returns at once otherwise)
     hist_percentile_kernel<<<hist_grid(h, count, 1), kHistThreads, kHistSmemBytes, s>>>(
         d_vol, count, hist_full, pedestal, d_status, tickets, d_status + ST_NEED_FULL, 0);
