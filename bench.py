@@ -187,7 +187,7 @@ def run_movie_leg(args, torch, nat, pipe, device, local_rank, rank, barrier, max
     Zm, Ym, Xm = MOVIE_SHAPE
     dframes = [synth_frame_device(torch, 50 + 10 * rank + i, device, MOVIE_SHAPE) for i in range(4)]
     projs = [nat.DeviceProjector(1, Zm, Ym, Xm, reference_channel=0, airyscan=False, mode=args.mode,
-                                 device=local_rank) for _ in range(3)]
+                                 device=local_rank, concurrent=True) for _ in range(3)]
     strs = [torch.cuda.Stream(device=device) for _ in range(3)]
 
     def resident(k):
@@ -290,8 +290,8 @@ def run_gpu(args, rank, world, local_rank):
     # movie.FramePipeline's frame slots run): the issue-bound stages of one frame overlap the HBM-bound ones of another
     dev_ms, in_flight = serial_ms, 1
     if args.streams > 1:
-        projs = [proj] + [nat.DeviceProjector(1, Z, Y, X, reference_channel=0, airyscan=False, mode=args.mode,
-                                              device=local_rank) for _ in range(args.streams - 1)]
+        projs = [nat.DeviceProjector(1, Z, Y, X, reference_channel=0, airyscan=False, mode=args.mode,
+                                     device=local_rank, concurrent=True) for _ in range(args.streams)]
         strs = [torch.cuda.Stream(device=device) for _ in range(args.streams)]
 
         def pipelined(nsteps):

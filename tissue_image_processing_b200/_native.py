@@ -25,7 +25,7 @@ class FrameDesc(C.Structure):
                 ("reference_channel", C.c_int32), ("min_z", C.c_int32), ("max_z", C.c_int32),
                 ("airyscan", C.c_int32), ("atoh_shift", C.c_int32), ("mode", C.c_int32),
                 ("bin_size", C.c_int32), ("method", C.c_int32), ("build_manifold", C.c_int32),
-                ("reserved", C.c_int32 * 3)]
+                ("flags", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
 class FrameStatus(C.Structure):
@@ -171,9 +171,13 @@ def stage_times(reset=True, device=None):
 METHODS = {"max_averages": 0, "max_std": 1, "multi_channel": 2}
 
 
+FRAME_CONCURRENT = 1        # desc.flags: frames of other streams are in flight on this GPU (no chained launches)
+
+
 def make_desc(C_, Z, Y, X, reference_channel=0, min_z=0, max_z=0, airyscan=False, atoh_shift=0, mode="fast",
-              bin_size=1, method="max_averages", build_manifold=False):
+              bin_size=1, method="max_averages", build_manifold=False, concurrent=False):
     d = FrameDesc()
+    d.flags = FRAME_CONCURRENT if concurrent else 0
     d.bin_size = int(bin_size)
     d.method = METHODS[method] if isinstance(method, str) else int(method)
     d.build_manifold = 1 if build_manifold else 0
@@ -263,13 +267,16 @@ class DeviceProjector:
     """Reusable device-side buffers for one frame shape; everything stays on the current stream."""
 
     def __init__(self, Cn, Z, Y, X, reference_channel=0, min_z=0, max_z=0, airyscan=False, atoh_shift=0,
-                 mode="fast", device=None, bin_size=1, method="max_averages", build_manifold=False):
+                 mode="fast", device=None, bin_size=1, method="max_averages", build_manifold=False,
+                 concurrent=False):
+        """concurrent=True: several projectors of this GPU run frames on different streams at the same time
+        (throughput mode, plain launches); False chains the kernels for the lowest single-frame latency."""
         import torch
         self.lib = load_library()
         self.h = handle(device)
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
         self.desc = make_desc(Cn, Z, Y, X, reference_channel, min_z, max_z, airyscan, atoh_shift, mode, bin_size,
-                              method, build_manifold)
+                              method, build_manifold, concurrent)
         self.ws_bytes = int(self.lib.tsp_project_workspace_bytes(C.byref(self.desc)))
         if self.ws_bytes == 0:
             raise TspError(ERR_INVALID, "tsp_project_workspace_bytes")

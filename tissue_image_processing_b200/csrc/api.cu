@@ -14,6 +14,8 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+thread_local bool tl_chain_launches = true;
+
 void prof_mark(tsp_handle* h, cudaStream_t s, int stage) {
     if (!h->profiling) return;
     cudaEvent_t ev;
@@ -233,6 +235,10 @@ int tsp_project_frame(tsp_handle* h, const tsp_frame_desc* desc, const uint16_t*
     }
     TSP_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = (cudaStream_t)cuda_stream;
+    struct ChainScope {          // launches happen on this thread: the flag covers exactly this frame's kernels
+        explicit ChainScope(bool on) { tl_chain_launches = on; }
+        ~ChainScope() { tl_chain_launches = true; }
+    } chain_scope((desc->flags & TSP_FRAME_CONCURRENT) == 0);
     const int Y = desc->rows, X = desc->cols, C = desc->channels;
     const size_t plane = (size_t)Y * X;
     const size_t chan_stride = (size_t)desc->planes * plane;
@@ -486,6 +492,10 @@ int tsp_frame_submit(tsp_handle* h, int slot, const tsp_frame_desc* desc, const 
     char* base = (char*)sl.d_mem;
     cudaStream_t s = sl.stream;
     TSP_CUDA(cudaMemcpyAsync(base + o_stack, h_stack, nstack * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
+    tsp_frame_desc d2 = *desc;
+    for (int k = 0; k < TSP_MAX_SLOTS; ++k)
+        if (k != slot && h->slots[k].busy) d2.flags |= TSP_FRAME_CONCURRENT;      // other frames are in flight
+    desc = &d2;
     rc = tsp_project_frame(h, desc, (const uint16_t*)(base + o_stack), (float*)(base + o_proj),
                            (int32_t*)(base + o_zmap), base + o_ws, ws, s);
     if (rc) return rc;

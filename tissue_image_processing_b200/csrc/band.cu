@@ -189,6 +189,8 @@ __global__ void __launch_bounds__(kB2Threads, 2) band_project2_kernel(const Band
     __shared__ uint32_t present[kBandMaxPlanes / 32];
     __shared__ int zlo_s, zhi_s;
 
+    chain_release();
+    chain_wait();
     if (band_index_error(a)) return;            // the reference raises before projecting
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -480,6 +482,8 @@ __global__ void __launch_bounds__(kB2Threads, 2) band_project3_kernel(const __gr
     __shared__ float lut_lo[512], lut_hi[256];
     __shared__ int zlo_s, zhi_s;
 
+    chain_release();
+    chain_wait();
     if (band_index_error(a)) return;            // the reference raises before projecting
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -815,6 +819,8 @@ __global__ void __launch_bounds__(kB2Threads, 3) band_project4_kernel(const __gr
     __shared__ int zlo_s, zhi_s;
     uint16_t (*cz_s)[kB2CW] = reinterpret_cast<uint16_t (*)[kB2CW]>(&r_s[0][0]);
 
+    chain_release();
+    chain_wait();
     if (band_index_error(a)) return;            // the reference raises before projecting
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1187,8 +1193,8 @@ static int launch_band_variant(tsp_handle* h, BandArgs a, dim3 grid, int pedesta
             }
         }
         dim3 g4(grid.x, grid.y, a.nch);
-        if (pedestal) band_project4_kernel<true><<<g4, kB2Threads, kB4Smem, s>>>(tmap, a);
-        else band_project4_kernel<false><<<g4, kB2Threads, kB4Smem, s>>>(tmap, a);
+        if (pedestal) TSP_CUDA(launch_chained(band_project4_kernel<true>, g4, kB2Threads, kB4Smem, s, tmap, a));
+        else TSP_CUDA(launch_chained(band_project4_kernel<false>, g4, kB2Threads, kB4Smem, s, tmap, a));
         TSP_LAUNCH_CHECK(h);
         a.use_list = 1;
     }
@@ -1203,8 +1209,8 @@ static int launch_band_variant(tsp_handle* h, BandArgs a, dim3 grid, int pedesta
         b.nch = 2 * pairs;
         dim3 g2(grid.x, grid.y, pairs);
         if (tma) {
-            if (pedestal) band_project3_kernel<true, true><<<g2, kB2Threads, kB3Smem2, s>>>(tmap, b);
-            else band_project3_kernel<false, true><<<g2, kB2Threads, kB3Smem2, s>>>(tmap, b);
+            if (pedestal) TSP_CUDA(launch_chained(band_project3_kernel<true, true>, g2, kB2Threads, kB3Smem2, s, tmap, b));
+            else TSP_CUDA(launch_chained(band_project3_kernel<false, true>, g2, kB2Threads, kB3Smem2, s, tmap, b));
         } else {
             if (pedestal) band_project2_kernel<true, true><<<g2, kB2Threads, 0, s>>>(b);
             else band_project2_kernel<false, true><<<g2, kB2Threads, 0, s>>>(b);
@@ -1216,8 +1222,8 @@ static int launch_band_variant(tsp_handle* h, BandArgs a, dim3 grid, int pedesta
         b.nch = 1;
         dim3 g1(grid.x, grid.y, 1);
         if (tma) {
-            if (pedestal) band_project3_kernel<true, false><<<g1, kB2Threads, kB3Smem1, s>>>(tmap, b);
-            else band_project3_kernel<false, false><<<g1, kB2Threads, kB3Smem1, s>>>(tmap, b);
+            if (pedestal) TSP_CUDA(launch_chained(band_project3_kernel<true, false>, g1, kB2Threads, kB3Smem1, s, tmap, b));
+            else TSP_CUDA(launch_chained(band_project3_kernel<false, false>, g1, kB2Threads, kB3Smem1, s, tmap, b));
         } else {
             if (pedestal) band_project2_kernel<true, false><<<g1, kB2Threads, 0, s>>>(b);
             else band_project2_kernel<false, false><<<g1, kB2Threads, 0, s>>>(b);

@@ -10,6 +10,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <cstdlib>
 #include <vector>
 
 #include "../../include/tsp_b200.h"
@@ -77,6 +78,36 @@ struct DeviceTaps {          // one uploaded FIR: w64[0..2r], w32 padded with `p
     const float* w32 = nullptr;    // points at the first real tap; w32[-pad..-1] and [2r+1..2r+pad] are 0
 };
 constexpr int kTapPad = 8;
+
+// ---- programmatic dependent launch (the kernels of one frame form a chain on one stream) ----------------
+// A kernel launched with launch_chained() may be scheduled while its predecessor on the stream is still draining:
+// its CTAs take the SM slots the predecessor's last CTAs free, run whatever does not touch global memory (shared
+// memory clears, mbarrier setup, index arithmetic) and then block in chain_wait() until the predecessor grid has
+// completed and its writes are visible.  Every kernel calls chain_release() first thing so that its own successor
+// may start queueing.  Launched the ordinary way (<<<>>>) both calls do nothing.  What this buys is the ~2 us of
+// launch latency and ramp at each of the frame's ten kernel boundaries.
+extern thread_local bool tl_chain_launches;      // false while a TSP_FRAME_CONCURRENT frame is being enqueued
+#ifdef __CUDACC__
+__device__ __forceinline__ void chain_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void chain_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                  Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static const bool allowed = getenv("TSP_NO_CHAIN") == nullptr;       // A/B switch for measurements
+    cfg.attrs = attr;
+    cfg.numAttrs = allowed && tl_chain_launches ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
 
 // ---- TMA / mbarrier primitives (sm_100a) ----------------------------------------------------------
 #ifdef __CUDACC__

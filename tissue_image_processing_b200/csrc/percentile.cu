@@ -278,6 +278,8 @@ __global__ void __launch_bounds__(kHistThreads, 1)
 hist_percentile_kernel(const uint16_t* __restrict__ vol, size_t count, uint32_t* __restrict__ ghist, int pedestal,
                        int32_t* __restrict__ status, unsigned int* __restrict__ ticket, const int32_t* __restrict__ gate,
                        int all_voxels) {
+    chain_release();
+    chain_wait();
     if (gate && *gate == 0) return;
     extern __shared__ uint32_t sh[];
     hist_full_body(vol, count, ghist, sh);
@@ -328,6 +330,8 @@ __global__ void __launch_bounds__(kHistThreads, 1)
 sample_window_kernel(const uint16_t* __restrict__ vol, size_t count, uint32_t stride, int pedestal,
                      uint32_t* __restrict__ shist, int32_t* __restrict__ status, unsigned int* __restrict__ ticket,
                      uint4* __restrict__ zero_ptr, size_t zero_vecs) {
+    chain_release();
+    chain_wait();
     // side job: clear the accumulation volume of the score stage.  This kernel is latency bound (it reads 1/32 of the
     // volume), the stores ride along for free - as a memset node or inside the count pass they cost 4 us
     for (size_t i = (size_t)blockIdx.x * kHistThreads + threadIdx.x; i < zero_vecs; i += (size_t)gridDim.x * kHistThreads)
@@ -464,6 +468,8 @@ __global__ void __launch_bounds__(kCountThreads, 2)
 window_count_kernel(const uint16_t* __restrict__ vol, size_t count, int pedestal, int32_t* __restrict__ status,
                     uint32_t* __restrict__ gwin, unsigned long long* __restrict__ gcounters,
                     unsigned int* __restrict__ ticket) {
+    chain_release();
+    chain_wait();
     if (status[ST_WIN_OK] == 0) return;
     __shared__ uint32_t win[kWinBins];
     __shared__ uint4 queue[kQueueCap];
@@ -644,17 +650,17 @@ int launch_percentile(tsp_handle* h, const uint16_t* d_vol, size_t count, int pe
         TSP_LAUNCH_CHECK(h);
         return TSP_OK;
     }
-    sample_window_kernel<<<hist_grid(h, count, stride), kHistThreads, 0, s>>>(
-        d_vol, count, stride, pedestal, hist_sample, d_status, tickets + 1, (uint4*)zero_ptr, zero_bytes / 16);
+    TSP_CUDA(launch_chained(sample_window_kernel, hist_grid(h, count, stride), kHistThreads, 0, s, d_vol, count, stride,
+                            pedestal, hist_sample, d_status, tickets + 1, (uint4*)zero_ptr, zero_bytes / 16));
     TSP_LAUNCH_CHECK(h);
     prof_mark(h, s, STG_PCT_SAMPLE);
-    window_count_kernel<<<h->sm_count * 2, kCountThreads, 0, s>>>(d_vol, count, pedestal, d_status, win, counters,
-                                                                  tickets + 2);
+    TSP_CUDA(launch_chained(window_count_kernel, h->sm_count * 2, kCountThreads, 0, s, d_vol, count, pedestal, d_status,
+                            win, counters, tickets + 2));
     TSP_LAUNCH_CHECK(h);
     prof_mark(h, s, STG_PCT_COUNT);      // what follows (the gated fallback) is booked on the caller's STG_PERCENTILE
     // exact fallback, armed by ST_NEED_FULL (returns at once otherwise)
-    hist_percentile_kernel<<<hist_grid(h, count, 1), kHistThreads, kHistSmemBytes, s>>>(
-        d_vol, count, hist_full, pedestal, d_status, tickets, d_status + ST_NEED_FULL, 0);
+    TSP_CUDA(launch_chained(hist_percentile_kernel, hist_grid(h, count, 1), kHistThreads, kHistSmemBytes, s, d_vol, count,
+                            hist_full, pedestal, d_status, tickets, d_status + ST_NEED_FULL, 0));
     TSP_LAUNCH_CHECK(h);
     return TSP_OK;
 }
