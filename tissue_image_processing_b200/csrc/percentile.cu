@@ -296,9 +296,33 @@ hist_percentile_kernel(const uint16_t* __restrict__ vol, size_t count, uint32_t*
 constexpr int kCoarseShift = 3;
 constexpr int kCoarseBins = kHistBins >> kCoarseShift;      // 8192
 
+// Run by the last CTA (kHistThreads threads): eight coarse bins per thread stay in registers - one round of loads
+// gives the sample size, an exclusive scan and, once the rank interval is known, both of its ends.
+static_assert(kCoarseBins == kHistThreads * 8, "window_select keeps eight coarse bins per thread");
+
 __device__ void window_select(const uint32_t* __restrict__ shist, int pedestal, int32_t* __restrict__ status) {
-    RankLookup first = block_rank_lookup(shist, kCoarseBins, 0, 0, ~0ull, ~0ull);
-    const unsigned long long ns = first.total;
+    __shared__ unsigned long long warp_tot[kHistThreads / 32];
+    __shared__ int found[2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint4 b0 = __ldcg(reinterpret_cast<const uint4*>(shist) + 2 * threadIdx.x);
+    const uint4 b1 = __ldcg(reinterpret_cast<const uint4*>(shist) + 2 * threadIdx.x + 1);
+    const uint32_t bins[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    unsigned long long mine = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) mine += bins[i];
+    unsigned long long incl = mine;
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    if (threadIdx.x < 2) found[threadIdx.x] = -1;
+    __syncthreads();
+    unsigned long long before = 0, ns = 0;
+    for (int w = 0; w < kHistThreads / 32; ++w) {
+        if (w < warp) before += warp_tot[w];
+        ns += warp_tot[w];
+    }
     if (ns < 1024) {                  // sample too thin to trust: go straight to the full histogram
         if (threadIdx.x == 0) {
             status[ST_WIN_OK] = 0;
@@ -309,15 +333,30 @@ __device__ void window_select(const uint32_t* __restrict__ shist, int pedestal, 
     const double centre = 0.95 * (double)(ns - 1);
     const double margin = 4.0 + 9.0 * sqrt((double)ns * 0.0475);
     const double lo_r = centre - margin, hi_r = centre + margin + 1.0;
-    const unsigned long long r_lo = lo_r < 0.0 ? 0ull : (unsigned long long)lo_r;
-    const unsigned long long r_hi = hi_r > (double)(ns - 1) ? ns - 1 : (unsigned long long)hi_r;
-    RankLookup look = block_rank_lookup(shist, kCoarseBins, 0, 0, r_lo, r_hi);
+    const unsigned long long ranks[2] = {lo_r < 0.0 ? 0ull : (unsigned long long)lo_r,
+                                         hi_r > (double)(ns - 1) ? ns - 1 : (unsigned long long)hi_r};
+    const unsigned long long excl = before + incl - mine;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        if (ranks[r] >= excl && ranks[r] < excl + mine) {
+            unsigned long long cum = excl;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                cum += bins[i];
+                if (cum > ranks[r]) {
+                    found[r] = 8 * threadIdx.x + i;
+                    break;
+                }
+            }
+        }
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
-        int lo = look.bin[0] << kCoarseShift, hi = (look.bin[1] << kCoarseShift) + (1 << kCoarseShift) - 1;
+        int lo = found[0] << kCoarseShift, hi = (found[1] << kCoarseShift) + (1 << kCoarseShift) - 1;
         if (lo < pedestal + 1) lo = pedestal + 1;
         if (hi > kHistBins - 1) hi = kHistBins - 1;
         int w = hi - lo + 1;
-        const bool ok = w < kWinBins && w > 0;
+        const bool ok = found[0] >= 0 && found[1] >= 0 && w < kWinBins && w > 0;
         if (ok) w = (1 << (32 - __clz(w))) - 1;        // widened to 2^k - 1 values (clamp-and-sum count pass), k <= 12
         status[ST_WIN_LO] = lo;
         status[ST_WIN_N] = w;
@@ -331,13 +370,13 @@ sample_window_kernel(const uint16_t* __restrict__ vol, size_t count, uint32_t st
                      uint32_t* __restrict__ shist, int32_t* __restrict__ status, unsigned int* __restrict__ ticket,
                      uint4* __restrict__ zero_ptr, size_t zero_vecs) {
     chain_release();
-    chain_wait();
+    __shared__ uint32_t sh[kCoarseBins];
+    for (int i = threadIdx.x; i < kCoarseBins; i += kHistThreads) sh[i] = 0;
+    chain_wait();                // everything above overlaps the previous kernel's tail
     // side job: clear the accumulation volume of the score stage.  This kernel is latency bound (it reads 1/32 of the
     // volume), the stores ride along for free - as a memset node or inside the count pass they cost 4 us
     for (size_t i = (size_t)blockIdx.x * kHistThreads + threadIdx.x; i < zero_vecs; i += (size_t)gridDim.x * kHistThreads)
         zero_ptr[i] = make_uint4(0, 0, 0, 0);
-    __shared__ uint32_t sh[kCoarseBins];
-    for (int i = threadIdx.x; i < kCoarseBins; i += kHistThreads) sh[i] = 0;
     __syncthreads();
     const uintptr_t addr = reinterpret_cast<uintptr_t>(vol);
     size_t head = ((16 - (addr & 15)) & 15) / 2;
@@ -469,17 +508,17 @@ window_count_kernel(const uint16_t* __restrict__ vol, size_t count, int pedestal
                     uint32_t* __restrict__ gwin, unsigned long long* __restrict__ gcounters,
                     unsigned int* __restrict__ ticket) {
     chain_release();
-    chain_wait();
-    if (status[ST_WIN_OK] == 0) return;
     __shared__ uint32_t win[kWinBins];
     __shared__ uint4 queue[kQueueCap];
     __shared__ uint32_t qtail;
     __shared__ unsigned long long blk[2];
-    const uint32_t lo = (uint32_t)status[ST_WIN_LO], wn = (uint32_t)status[ST_WIN_N];     // wn = 2^k - 1, lo >= 1
-    const uint32_t ped = (uint32_t)pedestal;
     for (int i = threadIdx.x; i < kWinBins; i += kCountThreads) win[i] = 0;
     if (threadIdx.x < 2) blk[threadIdx.x] = 0;
     if (threadIdx.x == 0) qtail = 0;
+    chain_wait();                // the shared-memory clears above overlap the sample kernel's last CTA
+    if (status[ST_WIN_OK] == 0) return;
+    const uint32_t lo = (uint32_t)status[ST_WIN_LO], wn = (uint32_t)status[ST_WIN_N];     // wn = 2^k - 1, lo >= 1
+    const uint32_t ped = (uint32_t)pedestal;
     __syncthreads();
 
     unsigned long long nz_total = 0, clamp_total = 0;      // per-thread totals (scalar path + flushes)
