@@ -221,14 +221,17 @@ def run_movie_leg(args, torch, nat, pipe, device, local_rank, rank, barrier, max
     def sink(t, proj, zmap, status):
         seen[0] += int(zmap[0, 0] >= 0)
 
-    def gen(k):
-        for i in range(k):
+    from tissue_image_processing_b200.movie import SharedFrameCounter
+
+    def gen(counter, total):
+        for i in counter.claims(total):
             yield i, hframes[i % 4]
 
-    pipe.project_frames(gen(4), sink, reference_channel=0, airyscan=False)
+    warm_counter, movie_counter = SharedFrameCounter("movie_warm"), SharedFrameCounter("movie")
+    pipe.project_frames(gen(warm_counter, 4 * world), sink, reference_channel=0, airyscan=False)
     barrier()
     t0 = time.perf_counter()
-    pipe.project_frames(gen(n), sink, reference_channel=0, airyscan=False)
+    pipe.project_frames(gen(movie_counter, n * world), sink, reference_channel=0, airyscan=False)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     return {"workload": "1024x1024x48 uint16 time-lapse frames (BASELINE configs[2]), %d frames per GPU, frames "
@@ -253,6 +256,7 @@ def run_gpu(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=device)
     import tissue_image_processing_b200 as tsp
     from tissue_image_processing_b200 import _native as nat
+    host_cpus = nat.bind_host_thread_to_gpu(local_rank)      # pinned frames on the GPU's own NUMA node
 
     def barrier():
         if world > 1:
@@ -354,21 +358,24 @@ def run_gpu(args, rank, world, local_rank):
     barrier()
     single_s = max_over_ranks(time.perf_counter() - t0)
     # the movie API: same frames through the slot pipeline (copy-in of frame t+1 overlaps the kernels of frame t)
-    from tissue_image_processing_b200.movie import FramePipeline
+    from tissue_image_processing_b200.movie import FramePipeline, SharedFrameCounter
     pipe = FramePipeline(devices=[local_rank], slots=3, mode=args.mode)
     checksum = [0.0]
 
     def sink(t, proj, zmap, status):
         checksum[0] += float(proj[0, 0, 0]) + float(zmap[0, 0])        # the result is read on the host
 
-    def frames(n):
-        for i in range(n):
+    # the job's world * K frames are claimed from a counter shared by the ranks (movie.SharedFrameCounter): the host
+    # links of a multi-GPU box are not equally fast, a rank on a faster link takes more frames; one rank = plain count
+    def frames(counter, total):
+        for i in counter.claims(total):
             yield i, host_frames[i % nframes][0]
 
-    pipe.project_frames(frames(min(args.warmup, 3)), sink, reference_channel=0, airyscan=False)
+    warm_counter, e2e_counter = SharedFrameCounter("e2e_warm"), SharedFrameCounter("e2e")
+    pipe.project_frames(frames(warm_counter, world * min(args.warmup, 3)), sink, reference_channel=0, airyscan=False)
     barrier()
     t0 = time.perf_counter()
-    pipe.project_frames(frames(args.steps), sink, reference_channel=0, airyscan=False)
+    pipe.project_frames(frames(e2e_counter, world * args.steps), sink, reference_channel=0, airyscan=False)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     movie = run_movie_leg(args, torch, nat, pipe, device, local_rank, rank, barrier, max_over_ranks, world)
@@ -419,6 +426,8 @@ def run_gpu(args, rank, world, local_rank):
                 "ms_per_step": e2e_s * 1e3 / args.steps,
                 "api": "movie.FramePipeline.project_frames(pinned host uint16 frames) -> float64 projection, int64 "
                        "height map per frame on the host (3 frame slots: copy-in overlaps kernels)",
+                "frame_assignment": "the job's N*K frames are claimed by the ranks from a shared counter (the host "
+                                    "links of a multi-GPU box differ in speed); bytes are per frame",
                 "single_call_ms": single_s * 1e3 / args.steps,
                 "single_call_api": "time_point_surface_projection(frame, 'TCZYX', ...) one blocking call per frame"},
         "gpu_launches": int(launches),
@@ -440,6 +449,7 @@ def run_gpu(args, rank, world, local_rank):
                          "sample": ("one 1024x1024x48 crop of the workload frame, %.1f s" % cpu_wall) if world == 1
                          else "not measured at N>1 (see the N=1 line)"},
         "clocks": clocks,
+        "host_cpus": ("%d CPUs next to the GPU (NVML affinity)" % len(host_cpus)) if host_cpus else "not bound",
         "frame_status": status,
     }
     emit(line)

@@ -98,18 +98,23 @@ def _gloo_worker(rank, world, port, tmp):
     zmap = np.zeros((5, 1, 1, 24, 28))
     pipe = FramePipeline(operator=orc.time_point_surface_projection)           # host-logic seam, no GPU here
     pipe.project_movie("m", 0, proj, zmap, reference_channel=0, airyscan=False, atoh_shift=0, min_z=0, max_z=0)
+    from tissue_image_processing_b200.movie import SharedFrameCounter
+    mine = list(SharedFrameCounter("test").claims(37))                         # every index exactly once across ranks
+    np.save(os.path.join(tmp, "claims%d.npy" % rank), np.array(mine, dtype=np.int64))
     np.save(os.path.join(tmp, "proj%d.npy" % rank), proj)
     np.save(os.path.join(tmp, "zmap%d.npy" % rank), zmap)
     dist.destroy_process_group()
 
 
 def test_movie_partition_world_size_2_gloo(tmp_path):
-    """Two ranks each project their own time points (t % 2 == rank); assembling the arrays is the only
-    exchange.  The operator is the oracle here - this checks the host logic, not the kernels."""
+    """Two ranks each project the time points they claim from the shared counter; assembling the arrays is the
+    only exchange.  The operator is the oracle here - this checks the host logic, not the kernels."""
     import torch.multiprocessing as mp
     port = 29500 + os.getpid() % 2000
     mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     movie = np.stack([synth.synth_stack(6, 24, 28, C=2, seed=3, t=t) for t in range(5)])
+    claims = np.concatenate([np.load(tmp_path / ("claims%d.npy" % r)) for r in range(2)])
+    assert sorted(claims.tolist()) == list(range(37))
     for rank in range(2):
         proj = np.load(tmp_path / ("proj%d.npy" % rank))
         zmap = np.load(tmp_path / ("zmap%d.npy" % rank))
