@@ -404,10 +404,10 @@ def run_gpu(args, rank, world, local_rank):
                     "interp_argmax": "interp_argmax_kernel", "coarse": "coarse_xy_kernel + coarse_zmix_kernel"}
     achieved = stage_bytes.get(dom, 2 * vox) / (stage_ms[dom] * 1e-3) / 1e9
     # dram__bytes_read.sum + dram__bytes_write.sum per frame of each stage's kernels, from the ncu --set full capture
-    # of this very workload (profiles/r1x_ncu_full_summary.txt); only meaningful for the default fast mode
-    ncu_traffic = {"percentile_sample": 16.83e6, "percentile_count": 536.9e6 + 4.02e6, "percentile": 0.05e6,
-                   "decimate": 555.8e6 + 20.12e6, "coarse": 2 * 17.45e6, "interp_argmax": 5.57e6,
-                   "band": 111.2e6 + 9.37e6 + 0.07e6}
+    # of this very workload (profiles/r1f_ncu_full_summary.txt); only meaningful for the default fast mode
+    ncu_traffic = {"percentile_sample": 16.83e6, "percentile_count": 536.9e6 + 6.41e6, "percentile": 0.05e6,
+                   "decimate": 555.8e6 + 19.64e6, "coarse": 2 * 17.45e6, "interp_argmax": 5.57e6,
+                   "band": 111.2e6 + 7.89e6 + 0.07e6}
     traffic = ncu_traffic.get(dom) if args.mode == "fast" else None
     # the CPU leg runs on rank 0 at N=1 only (at N>1 it would only add minutes next to seven idle ranks)
     cpu_v, cpu_wall = cpu_baseline((48, 1024, 1024), procs=1) if world == 1 else (None, 0.0)
@@ -433,7 +433,7 @@ def run_gpu(args, rank, world, local_rank):
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": stage_kernel.get(dom, dom), "stage": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic,
-                     "traffic_source": "ncu --set full, profiles/r1x_ncu_full_summary.txt (per frame, all kernels of "
+                     "traffic_source": "ncu --set full, profiles/r1f_ncu_full_summary.txt (per frame, all kernels of "
                                        "the stage)", "peak_source": peak_src,
                      "kernel_ms": stage_ms[dom]},
         "frame_roofline": {"achieved": frame_gbs, "peak": peak, "unit": "GB/s", "frac": frame_gbs / peak,
