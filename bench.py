@@ -186,9 +186,10 @@ def run_movie_leg(args, torch, nat, pipe, device, local_rank, rank, barrier, max
         return None
     Zm, Ym, Xm = MOVIE_SHAPE
     dframes = [synth_frame_device(torch, 50 + 10 * rank + i, device, MOVIE_SHAPE) for i in range(4)]
+    ns = max(1, args.movie_streams)
     projs = [nat.DeviceProjector(1, Zm, Ym, Xm, reference_channel=0, airyscan=False, mode=args.mode,
-                                 device=local_rank, concurrent=True) for _ in range(3)]
-    strs = [torch.cuda.Stream(device=device) for _ in range(3)]
+                                 device=local_rank, concurrent=ns > 1) for _ in range(ns)]
+    strs = [torch.cuda.Stream(device=device) for _ in range(ns)]
 
     def resident(k):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -196,8 +197,8 @@ def run_movie_leg(args, torch, nat, pipe, device, local_rank, rank, barrier, max
         for st in strs:
             st.wait_event(e0)
         for i in range(k):
-            with torch.cuda.stream(strs[i % 3]):
-                projs[i % 3].run(dframes[i % 4])
+            with torch.cuda.stream(strs[i % ns]):
+                projs[i % ns].run(dframes[i % 4])
         for st in strs:
             ev = torch.cuda.Event()
             ev.record(st)
@@ -205,7 +206,7 @@ def run_movie_leg(args, torch, nat, pipe, device, local_rank, rank, barrier, max
         e1.record()
         return e0, e1
 
-    resident(6)
+    resident(2 * ns)
     barrier()
     e0, e1 = resident(n)
     barrier()
@@ -239,7 +240,8 @@ def run_movie_leg(args, torch, nat, pipe, device, local_rank, rank, barrier, max
             "frames": n * world, "frames_per_s": n * world / (dev_ms * 1e-3),
             "frames_per_s_e2e": n * world / e2e_s, "ms_per_frame": dev_ms / n, "ms_per_frame_e2e": e2e_s * 1e3 / n,
             "voxels_per_s": n * world * Zm * Ym * Xm / (dev_ms * 1e-3),
-            "note": "frames_per_s: device-resident, 3 frames in flight per GPU; frames_per_s_e2e: pinned host frame in, "
+            "frames_in_flight": ns,
+            "note": "frames_per_s: device-resident, frames_in_flight frames in flight per GPU; frames_per_s_e2e: pinned host frame in, "
                     "float64 projection + int64 height map out (PCIe-bound)"}
 
 
@@ -485,6 +487,7 @@ def main():
     ap.add_argument("--device-only", action="store_true", help="development aid: skip the end-to-end and CPU legs")
     ap.add_argument("--movie-frames", type=int, default=48,
                     help="frames per GPU of the 1024x1024x48 movie leg (BASELINE configs[2]); 0 skips it")
+    ap.add_argument("--movie-streams", type=int, default=4, help="frames in flight per GPU in the movie leg")
     ap.add_argument("--streams", type=int, default=3, help="independent frames in flight per GPU (CUDA streams)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
