@@ -72,3 +72,21 @@ def test_no_cpu_fallback_without_gpu(native):
     import tissue_image_processing_b200 as pkg
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         pkg.time_point_surface_projection(np.zeros((1, 1, 4, 8, 8), np.uint16), "TCZYX", 0)
+
+
+def test_descriptor_flags(native):
+    """desc.flags took over the first reserved word: 0 and TSP_FRAME_CONCURRENT are valid, anything else (or a
+    non-zero reserved word) is refused, and the flag does not change the workspace."""
+    lib = native.load_library()
+    plain = native.make_desc(1, 16, 128, 128, mode="fast")
+    conc = native.make_desc(1, 16, 128, 128, mode="fast", concurrent=True)
+    assert plain.flags == 0 and conc.flags == native.FRAME_CONCURRENT == 1
+    assert ctypes.sizeof(plain) == 16 * 4
+    n0 = lib.tsp_project_workspace_bytes(ctypes.byref(plain))
+    assert n0 > 0 and lib.tsp_project_workspace_bytes(ctypes.byref(conc)) == n0
+    bad = native.make_desc(1, 16, 128, 128, mode="fast")
+    bad.flags = 6
+    assert lib.tsp_project_workspace_bytes(ctypes.byref(bad)) == 0 and b"flags" in lib.tsp_last_error()
+    bad.flags = 0
+    bad.reserved[1] = 1
+    assert lib.tsp_project_workspace_bytes(ctypes.byref(bad)) == 0

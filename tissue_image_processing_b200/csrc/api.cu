@@ -79,6 +79,10 @@ static int resolve_crop(const tsp_frame_desc* d, Crop* c) {
         set_error("unknown method %d", d->method);
         return TSP_ERR_INVALID;
     }
+    if ((d->flags & ~TSP_FRAME_CONCURRENT) != 0 || d->reserved[0] != 0 || d->reserved[1] != 0) {
+        set_error("unknown flags 0x%x (or non-zero reserved words) in the frame descriptor", (unsigned)d->flags);
+        return TSP_ERR_INVALID;
+    }
     c->z_offset = d->min_z;
     if (d->max_z > 0) {
         const int hi = d->max_z < d->planes ? d->max_z : d->planes;
