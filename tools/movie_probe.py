@@ -13,6 +13,18 @@ Z, Y, X = (int(v) for v in sys.argv[1:4])
 streams = [int(v) for v in sys.argv[4:]] or [1, 2, 3, 4, 6, 8]
 dev = torch.device("cuda", 0)
 frames = [bench.synth_frame_device(torch, 70 + i, dev, (Z, Y, X)) for i in range(4)]
+p0 = nat.DeviceProjector(1, Z, Y, X, airyscan=False, mode="fast", device=0)
+for i in range(4):
+    p0.run(frames[i % 4])
+torch.cuda.synchronize()
+nat.set_profiling(True, 0)
+nat.stage_times(reset=True, device=0)
+for i in range(20):
+    p0.run(frames[i % 4])
+torch.cuda.synchronize()
+st = nat.stage_times(reset=True, device=0)
+nat.set_profiling(False, 0)
+print("stage us (events between the stages):", {k: round(1e3 * v[0] / max(v[1], 1), 1) for k, v in st.items()}, flush=True)
 for ns in streams:
     projs = [nat.DeviceProjector(1, Z, Y, X, airyscan=False, mode="fast", device=0, concurrent=ns > 1) for _ in range(ns)]
     strs = [torch.cuda.Stream(device=dev) for _ in range(ns)]
