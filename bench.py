@@ -361,7 +361,7 @@ def run_gpu(args, rank, world, local_rank):
     single_s = max_over_ranks(time.perf_counter() - t0)
     # the movie API: same frames through the slot pipeline (copy-in of frame t+1 overlaps the kernels of frame t)
     from tissue_image_processing_b200.movie import FramePipeline, SharedFrameCounter
-    pipe = FramePipeline(devices=[local_rank], slots=3, mode=args.mode)
+    pipe = FramePipeline(devices=[local_rank], slots=args.slots, mode=args.mode)
     checksum = [0.0]
 
     def sink(t, proj, zmap, status):
@@ -427,7 +427,7 @@ def run_gpu(args, rank, world, local_rank):
                 "h2d_bytes_per_step": int(vox * 2), "d2h_bytes_per_step": int(Y * X * 16 + 256),
                 "ms_per_step": e2e_s * 1e3 / args.steps,
                 "api": "movie.FramePipeline.project_frames(pinned host uint16 frames) -> float64 projection, int64 "
-                       "height map per frame on the host (3 frame slots: copy-in overlaps kernels)",
+                       "height map per frame on the host (%d frame slots: copy-in overlaps kernels)" % args.slots,
                 "frame_assignment": "the job's N*K frames are claimed by the ranks from a shared counter (the host "
                                     "links of a multi-GPU box differ in speed); bytes are per frame",
                 "single_call_ms": single_s * 1e3 / args.steps,
@@ -487,6 +487,7 @@ def main():
     ap.add_argument("--device-only", action="store_true", help="development aid: skip the end-to-end and CPU legs")
     ap.add_argument("--movie-frames", type=int, default=48,
                     help="frames per GPU of the 1024x1024x48 movie leg (BASELINE configs[2]); 0 skips it")
+    ap.add_argument("--slots", type=int, default=2, help="frame slots of the end-to-end pipeline (frames a rank holds)")
     ap.add_argument("--movie-streams", type=int, default=4, help="frames in flight per GPU in the movie leg")
     ap.add_argument("--streams", type=int, default=3, help="independent frames in flight per GPU (CUDA streams)")
     args = ap.parse_args()
