@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TSP_ABI_VERSION 2
+#define TSP_ABI_VERSION 3
 
 /* error codes */
 #define TSP_OK 0
@@ -56,6 +56,24 @@ typedef struct tsp_handle tsp_handle; /* per-GPU context: tables, status words, 
  * GPU the early-queued CTAs only take SM slots from them: set TSP_FRAME_CONCURRENT and the kernels launch the
  * ordinary way (tsp_frame_submit sets it by itself while another slot is busy). */
 #define TSP_FRAME_CONCURRENT 1
+/* Host-buffer calls only (tsp_frame_submit / tsp_project_frame_host): the outputs are converted on the device to what
+ * the movie driver stores - projection and height map as uint16, the C cast numpy's astype("uint16") performs
+ * (BIM:481, SP:229-231) - so a frame returns 2 + 2 bytes per pixel instead of 8 + 8.  h_proj / h_zmap then point at
+ * uint16 arrays. */
+#define TSP_FRAME_OUT_U16 2
+
+/* The constants the reference hard-codes (SP:28, SP:35, SP:37, SP:55, SP:70-71).  tsp_default_params() fills the
+ * reference's values; a frame descriptor with has_params == 0 uses them too.  Non-default sigmas leave the
+ * fast-mode tables (built for sigma 1 / 30 / (1,2,2)): the score then runs through the direct FIR (TSP_MODE_FAST
+ * behaves like TSP_MODE_EXACT) and a non-default sigma_mask through the materialised band mask. */
+typedef struct tsp_params {
+    float percentile;       /* SP:35   95: clip at this percentile of the non-zero reference voxels, [0, 100]   */
+    int32_t pedestal;       /* SP:28   10000: subtracted (and clamped at 0) when desc.airyscan != 0             */
+    float sigma_pre[3];     /* SP:37   (0.5, 1, 1)   z, y, x                                                    */
+    float sigma_score[3];   /* SP:55   (0.5, 30, 30)                                                            */
+    float sigma_mask[3];    /* SP:70   (1, 2, 2): the band whose weighted maximum is projected                  */
+    int32_t reserved[5];    /* must be 0                                                                        */
+} tsp_params;
 
 /* Frame descriptor = the arguments of time_point_surface_projection (SP:17-19) that reach the
  * arithmetic.  bin_size <= 1 and build_manifold == 0 (the zeroed defaults) select the plain
@@ -73,8 +91,10 @@ typedef struct tsp_frame_desc {
     int32_t bin_size;                     /* SP:39: <= 1 none                                    */
     int32_t method;                       /* TSP_METHOD_* (only read when bin_size > 1)          */
     int32_t build_manifold;               /* SP:56-57                                            */
-    int32_t flags;                        /* TSP_FRAME_* (0 = defaults; was reserved, must-be-0)  */
-    int32_t reserved[2];                  /* must be 0                                           */
+    int32_t flags;                        /* TSP_FRAME_* (0 = defaults)                           */
+    int32_t has_params;                   /* 0: reference constants; 1: `params` below            */
+    int32_t reserved;                     /* must be 0                                           */
+    tsp_params params;                    /* read only when has_params != 0                      */
 } tsp_frame_desc;
 
 /* What the operator learned about the frame (filled by the *_host calls and tsp_get_frame_status) */
@@ -90,6 +110,8 @@ typedef struct tsp_frame_status {
 
 int tsp_abi_version(void);
 const char* tsp_last_error(void);
+
+void tsp_default_params(tsp_params* out);
 
 int tsp_create(int device, tsp_handle** out);
 int tsp_destroy(tsp_handle* h);
@@ -114,10 +136,12 @@ int tsp_get_frame_status(tsp_handle* h, const void* d_workspace, void* cuda_stre
 
 /* Host-buffer call = the plugin boundary `result = apply_function(chunk, **params)` of BIM:129.
  * h_stack (C,Z,Y,X) uint16 in host memory; h_proj (C,Y,X) float64 and h_zmap (Y,X) int64 are
- * the dtypes the reference returns (SP:73, SP:61).  Copies in, runs, copies out, synchronises.
- * Device scratch is owned (and reused) by the handle. */
+ * the dtypes the reference returns (SP:73, SP:61) - uint16 both with TSP_FRAME_OUT_U16.  Copies in, runs,
+ * copies out, synchronises.  Device scratch is owned (and reused) by the handle; the call has a frame slot
+ * of its own, so it may be issued from any thread, also while a slot pipeline is running (calls from several
+ * threads take turns). */
 int tsp_project_frame_host(tsp_handle* h, const tsp_frame_desc* desc, const uint16_t* h_stack,
-                           double* h_proj, int64_t* h_zmap, tsp_frame_status* status);
+                           void* h_proj, void* h_zmap, tsp_frame_status* status);
 
 /* Pipelined form of the same call for movies (SP:205-212 projects the time points of a movie one by
  * one; they are independent).  A handle owns TSP_MAX_SLOTS frame slots, each with its own stream
@@ -127,7 +151,7 @@ int tsp_project_frame_host(tsp_handle* h, const tsp_frame_desc* desc, const uint
  * tsp_project_frame_host == submit + wait on slot 0. */
 #define TSP_MAX_SLOTS 4
 int tsp_frame_submit(tsp_handle* h, int slot, const tsp_frame_desc* desc, const uint16_t* h_stack,
-                     double* h_proj, int64_t* h_zmap);
+                     void* h_proj, void* h_zmap);
 int tsp_frame_wait(tsp_handle* h, int slot, tsp_frame_status* status);
 
 /* ---- building blocks (also used one by one by the parity tests) --------------------------- */
@@ -149,6 +173,9 @@ int tsp_gaussian_blur_u16(tsp_handle* h, const uint16_t* d_in, uint16_t* d_out, 
  * > 0 after the optional airyscan pedestal.  Synchronises; results through `out`. */
 int tsp_percentile95_nonzero_u16(tsp_handle* h, const uint16_t* d_volume, size_t count,
                                  int airyscan, void* cuda_stream, tsp_frame_status* out);
+/* The same for any percentile in [0, 100] and pedestal (0 = none). */
+int tsp_percentile_nonzero_u16(tsp_handle* h, const uint16_t* d_volume, size_t count, float percentile,
+                               int pedestal, void* cuda_stream, tsp_frame_status* out);
 
 /* SP:26-37 + SP:55: the focus score volume (planes,rows,cols) float32 of one channel, in the
  * exact / bit-exact variants (the fast variant never materialises it).  d_tmp: same size. */
@@ -207,6 +234,13 @@ int tsp_project_m(tsp_handle* h, const uint16_t* d_channel, uint16_t* d_out, int
 int tsp_debug_coarse_taps(double* out, int capacity);
 /* Number of CUDA kernels launched through this handle so far (bench.py reports it). */
 int64_t tsp_launch_count(const tsp_handle* h);
+/* Kernel-variant switches for tests and A/B measurements (the product path never needs them; they replace the
+ * environment variables of ABI 2, which were read on every launch).  Keys: "no_ring" (strip decimation instead of
+ * the TMA ring), "band_variant" (0 auto, 2 register-prefetch kernel, 3 TMA ring kernel for every tile), "no_chain"
+ * (plain launches everywhere), "interp_rows" (2, 4 or 8 image rows per thread of the interpolation stage).  The same
+ * keys are read ONCE at tsp_create from the environment as TSP_NO_RING, TSP_BAND_VARIANT, TSP_NO_CHAIN,
+ * TSP_INTERP_ROWS. */
+int tsp_debug_set(tsp_handle* h, const char* key, int value);
 
 /* Optional per-stage device timing: when enabled, tsp_project_frame records CUDA events on the
  * launching stream between its stages.  tsp_get_stage_times synchronises the device, folds the

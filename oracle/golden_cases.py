@@ -57,6 +57,11 @@ CASES = [
      dict(reference_channel=0, airyscan=False, z_map=True, atoh_shift=-3)),
     ("zcrop_min0", lambda: _structured(20, 64, 72, seed=10), "TCZYX",
      dict(reference_channel=0, airyscan=False, z_map=True, min_z=0, max_z=14)),
+    # trap T4 without the IndexError: chosen_z carries +min_z but indexes the CROPPED stack (band min_z planes too deep)
+    ("zcrop_min3_band_deeper", lambda: _structured(20, 64, 72, seed=20), "TCZYX",
+     dict(reference_channel=0, airyscan=False, z_map=True, min_z=3, max_z=20)),
+    ("zcrop_min2_two_channels_shift", lambda: _structured(22, 56, 64, C=2, seed=24), "TCZYX",
+     dict(reference_channel=0, airyscan=False, z_map=True, min_z=2, max_z=21, atoh_shift=1)),
     ("saturated_ties", lambda: _saturated(9, 64, 64), "TCZYX",
      dict(reference_channel=0, airyscan=False, z_map=True)),
     ("no_zmap_return", lambda: _structured(8, 48, 48, seed=12), "TCZYX",

@@ -63,3 +63,21 @@ def sparse_spike_stack(Z, Y, X, C=1, seed=0, density=0.01, amp=4000):
     mask = rng.random((C, Z, Y, X)) < density
     vals = rng.integers(amp // 4, amp, size=(C, Z, Y, X))
     return np.where(mask, vals, 0).astype(np.uint16)
+
+
+def synth_tile(Z, tile, full, origin, seed=0, C=1):
+    """One ``tile x tile`` XY tile of a ``full x full`` frame (BASELINE configs[4]: the 4096x4096x128 stack is
+    projected in independent ``chunk_size`` tiles, reference surface_projection.py:294-301).  The sheet follows
+    the height field of the WHOLE frame evaluated at the tile's global coordinates; texture and noise come from
+    a generator seeded per tile, so a tile is reproducible without building the multi-GB frame around it."""
+    y0, x0 = origin
+    rng = np.random.default_rng(seed + 7919 * (1 + (y0 // tile) * (-(-full // tile)) + x0 // tile))
+    h = height_field(Z, full, full)[y0:y0 + tile, x0:x0 + tile]
+    z = np.arange(Z, dtype=np.float64)[:, None, None]
+    out = np.empty((C, Z) + h.shape, dtype=np.uint16)
+    for c in range(C):
+        tex = 0.5 + 0.5 * (rng.random(h.shape) < 0.15) if c == 0 else _blob_texture(rng, *h.shape)
+        sig = 300.0 + (2500.0 if c == 0 else 1500.0) * np.exp(-(z - (h + c)[None]) ** 2 / 8.0) * tex[None]
+        img = 8.0 * rng.poisson(sig / 8.0) + rng.normal(0.0, 20.0, size=sig.shape)
+        out[c] = np.clip(np.rint(img), 0, 65535).astype(np.uint16)
+    return out

@@ -103,6 +103,22 @@ def _gloo_worker(rank, world, port, tmp):
     np.save(os.path.join(tmp, "claims%d.npy" % rank), np.array(mine, dtype=np.int64))
     np.save(os.path.join(tmp, "proj%d.npy" % rank), proj)
     np.save(os.path.join(tmp, "zmap%d.npy" % rank), zmap)
+    # the movie driver itself under two ranks: only rank 0 may touch the output directory (resume files, TIFF, zmap,
+    # pickle, the final os.remove loop); the other rank only projects the time points it claims
+    from tissue_image_processing_b200 import surface_projection as sp
+    m2 = np.stack([synth.synth_stack(6, 24, 28, C=2, seed=4, t=t) for t in range(3)])
+    install(bim, {"m1.czi": FakeAICSImage([movie, movie[::-1]]), "m2.czi": FakeAICSImage([m2])})
+    written = {}
+    sp.tiff_writer = lambda path, image, axes, metadata: written.update({path: (image, axes)})
+    out = os.path.join(tmp, "driver")
+    os.makedirs(out, exist_ok=True)
+    pipe16 = FramePipeline(operator=orc.time_point_surface_projection, out_dtype="uint16")
+    sp.movie_surface_projection(["m1.czi", "m2.czi"], 0, [2, 1], 2, out, "max_averages", 1, False, 0, 0, 0, False,
+                                frame_pipeline=pipe16)
+    np.save(os.path.join(tmp, "wrote%d.npy" % rank), np.array(sorted(os.path.basename(k) for k in written)))
+    if rank == 0:
+        np.save(os.path.join(tmp, "tif1.npy"), written[os.path.join(out, "position1.tif")][0])
+        np.save(os.path.join(tmp, "tif2.npy"), written[os.path.join(out, "position2.tif")][0])
     dist.destroy_process_group()
 
 
@@ -122,6 +138,22 @@ def test_movie_partition_world_size_2_gloo(tmp_path):
             want_p, want_z = orc.time_point_surface_projection(movie[t:t + 1], "TCZYX", 0, airyscan=False, z_map=True)
             assert np.array_equal(proj[t, :, 0], want_p), (rank, t)
             assert np.array_equal(zmap[t, 0, 0], want_z), (rank, t)
+    # driver: position 1 lives in m1 (5 frames) and m2 (3 frames), position 2 only in m1 (series 1: the frames reversed)
+    assert np.load(tmp_path / "wrote0.npy").tolist() == ["position1.tif", "position2.tif"]
+    assert np.load(tmp_path / "wrote1.npy").size == 0
+    m2 = np.stack([synth.synth_stack(6, 24, 28, C=2, seed=4, t=t) for t in range(3)])
+    want1 = [orc.time_point_surface_projection(f[None], "TCZYX", 0, airyscan=False).astype("uint16")
+             for f in list(movie) + list(m2)]
+    want2 = [orc.time_point_surface_projection(f[None], "TCZYX", 0, airyscan=False).astype("uint16") for f in movie[::-1]]
+    assert np.array_equal(np.load(tmp_path / "tif1.npy"), np.stack(want1))
+    assert np.array_equal(np.load(tmp_path / "tif2.npy"), np.stack(want2))
+    left = sorted(os.listdir(tmp_path / "driver"))
+    assert left == ["stage_locations_position1.pkl", "stage_locations_position2.pkl", "zmap_position1.npy",
+                    "zmap_position2.npy"], left
+    import pickle
+    with open(tmp_path / "driver" / "stage_locations_position1.pkl", "rb") as f:
+        assert len(pickle.load(f)["x"]) == 8
+    assert np.load(tmp_path / "driver" / "zmap_position1.npy").shape == (8, 1, 1, 24, 28)
 
 
 def test_cli_flags_and_dispatch(monkeypatch, tmp_path):

@@ -212,9 +212,127 @@ def test_chained_and_concurrent_launches_agree(tsp, shape, C, shift):
             got.append((p.clone(), z.clone()))
     torch.cuda.synchronize()
     for (p0, z0), (p1, z1) in zip(want, got):
-        # the coarse volume is accumulated with float atomics: two runs may differ in the last bit of a score and so
-        # in a handful of exact near-ties, never more (a broken dependency would scramble whole tiles)
-        dz = int((z0 != z1).sum())
-        assert dz <= 4, dz
-        assert int((p0 != p1).sum()) <= dz * 17 * 17 * C
+        # the coarse volume is accumulated in fixed point (integer atomics): the result does not depend on the order
+        # in which the warps arrive, so the two launch forms - and any two runs - agree bit for bit
+        assert torch.equal(z0, z1) and torch.equal(p0, p1)
     assert chained.status()["has_nonzero"]
+
+
+def test_pipeline_uint16_outputs_and_pageable_frames(tsp):
+    """out_dtype="uint16": the device converts (BIM:481 / SP:229-231 semantics); frames that are not in pinned memory
+    (what a dask .compute() returns, also non-contiguous views and uint8) go through the pinned staging ring; other
+    dtypes are refused like the single-frame operator refuses them."""
+    from tissue_image_processing_b200.movie import FramePipeline
+    movie = _movie(T=6, C=2, Z=9, Y=72, X=264)
+    want = [tsp.time_point_surface_projection(movie[t:t + 1], "TCZYX", 0, airyscan=False, z_map=True, mode="fast")
+            for t in range(6)]
+    got = {}
+    pipe = FramePipeline(slots=2, mode="fast", out_dtype="uint16", copy_threads=3)
+    padded = np.zeros((6, 2, 9, 72, 270), dtype=np.uint16)
+    padded[..., :264] = movie
+    pipe.project_frames(((t, padded[t][..., :264]) for t in range(6)),            # non-contiguous, pageable
+                        lambda t, p, z, st: got.__setitem__(t, (p.copy(), z.copy())),
+                        reference_channel=0, airyscan=False)
+    for t in range(6):
+        assert got[t][0].dtype == np.uint16 and got[t][1].dtype == np.uint16
+        assert np.array_equal(got[t][0], want[t][0].astype("uint16"))
+        assert np.array_equal(got[t][1], want[t][1].astype("uint16"))
+    assert pipe.h2d_bytes == 6 * movie[0].nbytes
+    small = (movie[:2] >> 4).astype(np.uint8)
+    got8 = {}
+    FramePipeline(slots=2, mode="exact").project_frames(((t, small[t]) for t in range(2)),
+                                                        lambda t, p, z, st: got8.__setitem__(t, (p.copy(), z.copy())),
+                                                        reference_channel=0, airyscan=False)
+    for t in range(2):
+        p, z = tsp.time_point_surface_projection(small[t:t + 1].astype(np.uint16), "TCZYX", 0, airyscan=False,
+                                                 z_map=True, mode="exact")
+        assert np.array_equal(got8[t][0], p) and np.array_equal(got8[t][1], z)
+    with pytest.raises(TypeError):
+        pipe.project_frames([(0, movie[0].astype(np.int32))], lambda *a: None, reference_channel=0, airyscan=False)
+    with pytest.raises(TypeError):
+        tsp.time_point_surface_projection(movie[:1].astype(np.float32), "TCZYX", 0, airyscan=False)
+
+
+def test_pipeline_params_travel_through_the_slots(tsp):
+    from tissue_image_processing_b200.movie import FramePipeline
+    movie = _movie(T=3, C=1, Z=24, Y=64, X=96)
+    extra = dict(percentile=90, sigma_mask=(2.5, 2, 2))
+    got = {}
+    FramePipeline(slots=2, mode="fast").project_frames(((t, movie[t]) for t in range(3)),
+                                                       lambda t, p, z, st: got.__setitem__(t, (p.copy(), z.copy())),
+                                                       reference_channel=0, airyscan=False, **extra)
+    for t in range(3):
+        p, z = tsp.time_point_surface_projection(movie[t:t + 1], "TCZYX", 0, airyscan=False, z_map=True, mode="fast",
+                                                 **extra)
+        assert np.array_equal(got[t][0], p) and np.array_equal(got[t][1], z)
+
+
+def test_pipeline_several_workers_share_one_queue(tsp):
+    """One worker thread per GPU, all taking frames from one queue (dynamic claiming): every frame is projected
+    exactly once whichever worker takes it; results equal the single-call results.  With one visible GPU this runs
+    the single-worker form."""
+    from tissue_image_processing_b200.movie import FramePipeline
+    movie = _movie(T=9, C=1, Z=8, Y=64, X=72)
+    import torch
+    devices = [0, 1] if torch.cuda.device_count() > 1 else [0]
+    got = {}
+    FramePipeline(devices=devices, slots=2, mode="fast").project_frames(
+        ((t, movie[t]) for t in range(9)), lambda t, p, z, st: got.__setitem__(t, (p.copy(), z.copy())),
+        reference_channel=0, airyscan=False)
+    assert sorted(got) == list(range(9))
+    for t in range(9):
+        p, z = tsp.time_point_surface_projection(movie[t:t + 1], "TCZYX", 0, airyscan=False, z_map=True, mode="fast")
+        assert np.array_equal(got[t][0], p) and np.array_equal(got[t][1], z)
+
+
+def _nccl_rank(rank, world, port, tmp):
+    """One rank of a torchrun-style job whose DEFAULT process group is NCCL (what bench.py and a GPU job create):
+    project_movie must assemble its arrays over a gloo group of its own."""
+    import sys
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dev = rank % torch.cuda.device_count()
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", rank=rank, world_size=world)
+    from tests.fake_image import FakeAICSImage, install
+    from tissue_image_processing_b200 import basic_image_manipulations as bim
+    from tissue_image_processing_b200 import surface_projection as sp
+    from tissue_image_processing_b200.movie import FramePipeline
+    movie = _movie(T=7, C=2, Z=8, Y=40, X=72, seed=11)
+    install(bim, {"m1.czi": FakeAICSImage([movie])})
+    proj = np.zeros((7, 2, 1, 40, 72), dtype=np.uint16)
+    zmap = np.zeros((7, 1, 1, 40, 72), dtype=np.uint16)
+    pipe = FramePipeline(devices=[dev], slots=2, mode="bitexact", out_dtype="uint16")
+    owned = pipe.project_movie("m1.czi", 0, proj, zmap, reference_channel=0, airyscan=False, atoh_shift=0, min_z=0,
+                               max_z=0, gather="all")
+    np.save(os.path.join(tmp, "owned%d.npy" % rank), np.array(owned, dtype=np.int64))
+    np.save(os.path.join(tmp, "proj%d.npy" % rank), proj)
+    # the whole driver, rank-guarded writes (only rank 0 touches the output directory)
+    written = {}
+    sp.tiff_writer = lambda path, image, axes, metadata: written.update({path: image})
+    out = os.path.join(tmp, "driver")
+    os.makedirs(out, exist_ok=True)
+    sp.movie_surface_projection(["m1.czi"], 0, [1], 1, out, "max_averages", 1, False, 0, 0, 0, False, mode="bitexact",
+                                frame_pipeline=pipe)
+    np.save(os.path.join(tmp, "wrote%d.npy" % rank), np.array(len(written)))
+    if rank == 0:
+        np.save(os.path.join(tmp, "tif.npy"), written[os.path.join(out, "position1.tif")])
+    dist.destroy_process_group()
+
+
+def test_project_movie_under_an_nccl_default_group(tsp, tmp_path):
+    import torch.multiprocessing as mp
+    port = 29500 + (os.getpid() * 7) % 2000
+    mp.spawn(_nccl_rank, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    movie = _movie(T=7, C=2, Z=8, Y=40, X=72, seed=11)
+    owned = [np.load(tmp_path / ("owned%d.npy" % r)).tolist() for r in range(2)]
+    assert sorted(owned[0] + owned[1]) == list(range(7))
+    want = np.stack([orc.time_point_surface_projection(movie[t:t + 1], "TCZYX", 0, airyscan=False).astype("uint16")
+                     for t in range(7)])
+    for r in range(2):
+        assert np.array_equal(np.load(tmp_path / ("proj%d.npy" % r))[:, :, 0], want), r
+    assert np.load(tmp_path / "wrote0.npy") == 1 and np.load(tmp_path / "wrote1.npy") == 0
+    assert np.array_equal(np.load(tmp_path / "tif.npy"), want)
+    assert sorted(os.listdir(tmp_path / "driver")) == ["stage_locations_position1.pkl", "zmap_position1.npy"]

@@ -109,9 +109,10 @@ def test_white_noise_tolerance_rule(mode, tsp):
 
 @pytest.mark.parametrize("shape,airy", [((12, 264, 520), True), ((9, 300, 1000), False), ((6, 131, 256), False),
                                         ((5, 77, 2056), True)])
-def test_fast_mode_tma_ring_shapes(shape, airy, tsp, monkeypatch):
+def test_fast_mode_tma_ring_shapes(shape, airy, tsp):
     """The TMA-ring decimation (X >= 256, X % 8 == 0) at ragged chunk widths, short images and with the
-    airyscan pedestal, against the oracle; the strip kernel (TSP_NO_RING=1) must satisfy the same rules."""
+    airyscan pedestal, against the oracle; the strip kernel (tsp_debug_set "no_ring") must satisfy the same rules."""
+    from tissue_image_processing_b200 import _native
     Z, Y, X = shape
     img = synth.synth_stack(Z, Y, X, seed=sum(shape), airyscan=airy)[None]
     kw = dict(reference_channel=0, airyscan=airy, z_map=True)
@@ -119,7 +120,10 @@ def test_fast_mode_tma_ring_shapes(shape, airy, tsp, monkeypatch):
     gap = orc.top2_relative_gap(score)
     got_proj, got_zmap = tsp.time_point_surface_projection(img, "TCZYX", mode="fast", **kw)
     print("ring", shape, compare_frame(got_proj, got_zmap, want_proj, want_zmap, gap))
-    monkeypatch.setenv("TSP_NO_RING", "1")
-    alt_proj, alt_zmap = tsp.time_point_surface_projection(img, "TCZYX", mode="fast", **kw)
+    _native.debug_set("no_ring", 1)
+    try:
+        alt_proj, alt_zmap = tsp.time_point_surface_projection(img, "TCZYX", mode="fast", **kw)
+    finally:
+        _native.debug_set("no_ring", 0)
     print("strip", shape, compare_frame(alt_proj, alt_zmap, want_proj, want_zmap, gap))
     assert (alt_zmap != got_zmap).mean() < 1e-3

@@ -162,11 +162,11 @@ def test_band_projection_from_oracle_height_map(nat, shift, ref):
                                                  ((44, 160, 192), 1, 0, "gappy"), ((35, 96, 136), 2, 0, "gappy"),
                                                  ((26, 160, 256), 2, 0, "mixed"), ((19, 96, 192), 3, -1, "mixed"),
                                                  ((6, 64, 128), 1, 0, "mixed"), ((64, 256, 320), 1, 0, False)])
-def test_band_projection_tma_ring(nat, shape, C, shift, noisy, monkeypatch):
+def test_band_projection_tma_ring(nat, shape, C, shift, noisy):
     """TMA path of the band stage (X % 8 == 0, tile inside the image): shallow tiles in the register kernel, plane
     ranges deeper than the ring (a noisy height map walks every plane, refilling the ring) through the worklist, one /
     two / three channels, shifted masks; against the oracle and bit for bit against the older kernels
-    (TSP_BAND_V3=1, TSP_BAND_V2=1), which do the same arithmetic in the same order."""
+    (tsp_debug_set "band_variant" 3 and 2), which do the same arithmetic in the same order."""
     Z, Y, X = shape
     img = synth.synth_stack(Z, Y, X, C=C, seed=sum(shape))
     if img.ndim == 3:
@@ -193,10 +193,14 @@ def test_band_projection_tma_ring(nat, shape, C, shift, noisy, monkeypatch):
     want = orc.project_channels(image, 0, orc.band_mask(zmap, Z), orc.band_mask(z_other, Z))
     got = nat.band_project(_cuda(img), _cuda(zmap.astype(np.int32)), reference_channel=0, atoh_shift=shift).cpu().numpy()
     np.testing.assert_allclose(got, want, rtol=1e-5, atol=0)
-    for variant in ("TSP_BAND_V3", "TSP_BAND_V2"):      # generic TMA kernel alone; register-prefetch kernel
-        monkeypatch.setenv(variant, "1")
-        alt = nat.band_project(_cuda(img), _cuda(zmap.astype(np.int32)), reference_channel=0, atoh_shift=shift).cpu().numpy()
-        assert np.array_equal(got, alt), variant
+    try:
+        for variant in (3, 2):                          # generic TMA kernel alone; register-prefetch kernel
+            nat.debug_set("band_variant", variant)
+            alt = nat.band_project(_cuda(img), _cuda(zmap.astype(np.int32)), reference_channel=0,
+                                   atoh_shift=shift).cpu().numpy()
+            assert np.array_equal(got, alt), variant
+    finally:
+        nat.debug_set("band_variant", 0)
 
 
 def test_band_projection_index_error(nat):

@@ -97,3 +97,39 @@ def test_percentile_restatement_small_counts():
     for n in (1, 2, 3, 20, 21, 1000, 4097):
         v = np.sort(rng.integers(1, 50, size=n).astype(np.float32))
         assert np.percentile(v, 95) == _percentile_f32_restated(v), n
+
+
+def test_large_golden_fixtures_are_complete():
+    """Every case of oracle/large_cases.py has its frozen reference output (digests, height map, near-tie mask, rows)."""
+    import json
+    import os
+    from oracle import large_cases
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "large")
+    for name, _, kw in large_cases.LARGE_CASES:
+        with open(os.path.join(root, name + ".json")) as f:
+            meta = json.load(f)
+        arr = np.load(os.path.join(root, name + ".npz"))
+        Y, X = arr["zmap"].shape
+        assert meta["shape"][-2:] == [Y, X] and meta["kwargs"] == kw
+        assert arr["near_tie_bits"].size == (Y * X + 7) // 8
+        assert arr["proj_rows"].shape == (meta["shape"][1], arr["proj_row_index"].size, X)
+        assert len(meta["zmap_sha256"]) == 64 and len(meta["proj_sha256"]) == 64
+
+
+@pytest.mark.parametrize("name", ["cfg1_512x512x32", "zcrop_min3_768x768x24"])
+def test_oracle_matches_large_reference_golden(name):
+    """The oracle against the frozen reference run at BASELINE configs[0] and on the min_z > 0 corner (trap T4: the
+    band sits min_z planes too deep, no IndexError)."""
+    import hashlib
+    import json
+    import os
+    from oracle import large_cases
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "large")
+    case = {c[0]: c for c in large_cases.LARGE_CASES}[name]
+    with open(os.path.join(root, name + ".json")) as f:
+        meta = json.load(f)
+    chunk = case[1]()
+    assert hashlib.sha256(chunk.tobytes()).hexdigest() == meta["input_sha256"]
+    proj, zmap = orc.time_point_surface_projection(chunk, "TCZYX", **case[2])
+    assert hashlib.sha256(zmap.tobytes()).hexdigest() == meta["zmap_sha256"]
+    assert hashlib.sha256(proj.astype(np.float32).tobytes()).hexdigest() == meta["proj_sha256"]

@@ -20,12 +20,21 @@ MODES = {"fast": MODE_FAST, "exact": MODE_EXACT, "bitexact": MODE_BITEXACT}
 ERR_INVALID, ERR_CUDA, ERR_WORKSPACE, ERR_BAND_INDEX, ERR_CHOOSE_LIMIT = -1, -2, -3, -4, -5
 
 
+ABI_VERSION = 3
+
+
+class Params(C.Structure):
+    """tsp_params: the constants the reference hard-codes (SP:28, SP:35, SP:37, SP:55, SP:70-71)."""
+    _fields_ = [("percentile", C.c_float), ("pedestal", C.c_int32), ("sigma_pre", C.c_float * 3),
+                ("sigma_score", C.c_float * 3), ("sigma_mask", C.c_float * 3), ("reserved", C.c_int32 * 5)]
+
+
 class FrameDesc(C.Structure):
     _fields_ = [("channels", C.c_int32), ("planes", C.c_int32), ("rows", C.c_int32), ("cols", C.c_int32),
                 ("reference_channel", C.c_int32), ("min_z", C.c_int32), ("max_z", C.c_int32),
                 ("airyscan", C.c_int32), ("atoh_shift", C.c_int32), ("mode", C.c_int32),
                 ("bin_size", C.c_int32), ("method", C.c_int32), ("build_manifold", C.c_int32),
-                ("flags", C.c_int32), ("reserved", C.c_int32 * 2)]
+                ("flags", C.c_int32), ("has_params", C.c_int32), ("reserved", C.c_int32), ("params", Params)]
 
 
 class FrameStatus(C.Structure):
@@ -38,6 +47,10 @@ EXPORTS = {
     # name: (restype, argtypes)
     "tsp_abi_version": (C.c_int, []),
     "tsp_last_error": (C.c_char_p, []),
+    "tsp_default_params": (None, [C.POINTER(Params)]),
+    "tsp_debug_set": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
+    "tsp_percentile_nonzero_u16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_float, C.c_int, C.c_void_p,
+                                             C.POINTER(FrameStatus)]),
     "tsp_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "tsp_destroy": (C.c_int, [C.c_void_p]),
     "tsp_project_workspace_bytes": (C.c_size_t, [C.POINTER(FrameDesc)]),
@@ -105,6 +118,9 @@ def load_library():
             fn = getattr(lib, name)          # AttributeError here = header and library disagree
             fn.restype = restype
             fn.argtypes = argtypes
+        if lib.tsp_abi_version() != ABI_VERSION:
+            raise NativeLibraryMissing("%s has ABI %d, this binding needs %d - rebuild it"
+                                       % (LIB_PATH, lib.tsp_abi_version(), ABI_VERSION))
         _lib = lib
         return lib
 
@@ -172,12 +188,45 @@ METHODS = {"max_averages": 0, "max_std": 1, "multi_channel": 2}
 
 
 FRAME_CONCURRENT = 1        # desc.flags: frames of other streams are in flight on this GPU (no chained launches)
+FRAME_OUT_U16 = 2           # host-buffer calls: uint16 projection / height map (the movie driver's on-disk dtype)
+
+PARAM_KEYS = ("percentile", "pedestal", "sigma_pre", "sigma_score", "sigma_mask")
+
+
+def default_params():
+    """The reference's constants as a dict (from the library: tsp_default_params)."""
+    p = Params()
+    load_library().tsp_default_params(C.byref(p))
+    return {"percentile": float(p.percentile), "pedestal": int(p.pedestal), "sigma_pre": tuple(p.sigma_pre),
+            "sigma_score": tuple(p.sigma_score), "sigma_mask": tuple(p.sigma_mask)}
+
+
+def debug_set(key, value, device=None):
+    """Kernel-variant switch for tests / A-B measurements (tsp_debug_set)."""
+    check(load_library().tsp_debug_set(handle(device), key.encode(), int(value)), "tsp_debug_set")
 
 
 def make_desc(C_, Z, Y, X, reference_channel=0, min_z=0, max_z=0, airyscan=False, atoh_shift=0, mode="fast",
-              bin_size=1, method="max_averages", build_manifold=False, concurrent=False):
+              bin_size=1, method="max_averages", build_manifold=False, concurrent=False, out_u16=False,
+              params=None):
+    """params: dict with any of PARAM_KEYS (None values = the reference's constant)."""
     d = FrameDesc()
-    d.flags = FRAME_CONCURRENT if concurrent else 0
+    d.flags = (FRAME_CONCURRENT if concurrent else 0) | (FRAME_OUT_U16 if out_u16 else 0)
+    if params and set(params) - set(PARAM_KEYS):
+        raise TypeError("unknown projection parameters: %s" % sorted(set(params) - set(PARAM_KEYS)))
+    if params and any(params.get(k) is not None for k in PARAM_KEYS):
+        d.has_params = 1
+        load_library().tsp_default_params(C.byref(d.params))
+        if params.get("percentile") is not None:
+            d.params.percentile = float(params["percentile"])
+        if params.get("pedestal") is not None:
+            d.params.pedestal = int(params["pedestal"])
+        for key in ("sigma_pre", "sigma_score", "sigma_mask"):
+            if params.get(key) is not None:
+                vals = tuple(float(v) for v in params[key])
+                if len(vals) != 3:
+                    raise RuntimeError("sequence argument must have length equal to input rank")
+                setattr(d.params, key, (C.c_float * 3)(*vals))
     d.bin_size = int(bin_size)
     d.method = METHODS[method] if isinstance(method, str) else int(method)
     d.build_manifold = 1 if build_manifold else 0
@@ -241,17 +290,19 @@ def bind_host_thread_to_gpu(device=None):
 
 def project_frame_host(stack, reference_channel, min_z=0, max_z=0, airyscan=False, atoh_shift=0, mode="fast",
                        device=None, out_proj=None, out_zmap=None, bin_size=1, method="max_averages",
-                       build_manifold=False):
+                       build_manifold=False, params=None, out_u16=False):
     """stack: C-contiguous uint16 ndarray (C,Z,Y,X) in host memory.  Returns (projection float64 (C,Y,X),
-    zmap int64 (Y,X), status dict)."""
+    zmap int64 (Y,X), status dict); uint16 both with ``out_u16`` (the movie driver's on-disk dtype)."""
     lib = load_library()
     h = handle(device)
     assert stack.dtype == np.uint16 and stack.ndim == 4 and stack.flags.c_contiguous
     Cn, Z, Y, X = stack.shape
     desc = make_desc(Cn, Z, Y, X, reference_channel, min_z, max_z, airyscan, atoh_shift, mode, bin_size, method,
-                     build_manifold)
-    proj = out_proj if out_proj is not None else pinned_empty((Cn, Y, X), np.float64)
-    zmap = out_zmap if out_zmap is not None else pinned_empty((Y, X), np.int64)
+                     build_manifold, out_u16=out_u16, params=params)
+    pdt, zdt = (np.uint16, np.uint16) if out_u16 else (np.float64, np.int64)
+    proj = out_proj if out_proj is not None else pinned_empty((Cn, Y, X), pdt)
+    zmap = out_zmap if out_zmap is not None else pinned_empty((Y, X), zdt)
+    assert proj.dtype == pdt and zmap.dtype == zdt and proj.flags.c_contiguous and zmap.flags.c_contiguous
     st = FrameStatus()
     rc = lib.tsp_project_frame_host(h, C.byref(desc), C.c_void_p(stack.ctypes.data), C.c_void_p(proj.ctypes.data),
                                     C.c_void_p(zmap.ctypes.data), C.byref(st))
@@ -263,16 +314,19 @@ MAX_SLOTS = 4
 
 
 def frame_submit(slot, stack, proj, zmap, reference_channel, min_z=0, max_z=0, airyscan=False, atoh_shift=0,
-                 mode="fast", device=None, bin_size=1, method="max_averages", build_manifold=False):
-    """Enqueue one frame on a slot (asynchronous).  stack (C,Z,Y,X) uint16, proj (C,Y,X) float64 and zmap (Y,X)
-    int64 are host arrays that must stay alive (and untouched) until frame_wait(slot)."""
+                 mode="fast", device=None, bin_size=1, method="max_averages", build_manifold=False, params=None):
+    """Enqueue one frame on a slot (asynchronous).  stack (C,Z,Y,X) uint16, proj (C,Y,X) and zmap (Y,X) are host
+    arrays that must stay alive (and untouched) until frame_wait(slot); float64 / int64 outputs are the reference's
+    dtypes, uint16 / uint16 selects the on-device conversion (TSP_FRAME_OUT_U16)."""
     lib = load_library()
     assert stack.dtype == np.uint16 and stack.ndim == 4 and stack.flags.c_contiguous
     Cn, Z, Y, X = stack.shape
-    assert proj.dtype == np.float64 and proj.shape == (Cn, Y, X) and proj.flags.c_contiguous
-    assert zmap.dtype == np.int64 and zmap.shape == (Y, X) and zmap.flags.c_contiguous
+    out_u16 = proj.dtype == np.uint16
+    assert (proj.dtype, zmap.dtype) in ((np.float64, np.int64), (np.uint16, np.uint16))
+    assert proj.shape == (Cn, Y, X) and proj.flags.c_contiguous
+    assert zmap.shape == (Y, X) and zmap.flags.c_contiguous
     desc = make_desc(Cn, Z, Y, X, reference_channel, min_z, max_z, airyscan, atoh_shift, mode, bin_size, method,
-                     build_manifold)
+                     build_manifold, out_u16=out_u16, params=params)
     rc = lib.tsp_frame_submit(handle(device), int(slot), C.byref(desc), C.c_void_p(stack.ctypes.data),
                               C.c_void_p(proj.ctypes.data), C.c_void_p(zmap.ctypes.data))
     check(rc, "tsp_frame_submit")
@@ -293,7 +347,7 @@ class DeviceProjector:
 
     def __init__(self, Cn, Z, Y, X, reference_channel=0, min_z=0, max_z=0, airyscan=False, atoh_shift=0,
                  mode="fast", device=None, bin_size=1, method="max_averages", build_manifold=False,
-                 concurrent=False):
+                 concurrent=False, params=None):
         """concurrent=True: several projectors of this GPU run frames on different streams at the same time
         (throughput mode, plain launches); False chains the kernels for the lowest single-frame latency."""
         import torch
@@ -301,7 +355,7 @@ class DeviceProjector:
         self.h = handle(device)
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
         self.desc = make_desc(Cn, Z, Y, X, reference_channel, min_z, max_z, airyscan, atoh_shift, mode, bin_size,
-                              method, build_manifold, concurrent)
+                              method, build_manifold, concurrent, params=params)
         self.ws_bytes = int(self.lib.tsp_project_workspace_bytes(C.byref(self.desc)))
         if self.ws_bytes == 0:
             raise TspError(ERR_INVALID, "tsp_project_workspace_bytes")
@@ -360,6 +414,17 @@ def percentile95_nonzero(d_vol, airyscan=False, stream=None):
     rc = lib.tsp_percentile95_nonzero_u16(h, C.c_void_p(d_vol.data_ptr()), d_vol.numel(), 1 if airyscan else 0,
                                           _stream_ptr(stream), C.byref(st))
     check(rc, "tsp_percentile95_nonzero_u16")
+    return status_dict(st)
+
+
+def percentile_nonzero(d_vol, percentile, pedestal=0, stream=None):
+    """np.percentile(v[v > pedestal] - pedestal, percentile) of a uint16 CUDA tensor, numpy's float32 arithmetic."""
+    lib, h = load_library(), handle(d_vol.device.index)
+    assert d_vol.is_cuda and d_vol.is_contiguous() and d_vol.element_size() == 2
+    st = FrameStatus()
+    rc = lib.tsp_percentile_nonzero_u16(h, C.c_void_p(d_vol.data_ptr()), d_vol.numel(), float(percentile),
+                                        int(pedestal), _stream_ptr(stream), C.byref(st))
+    check(rc, "tsp_percentile_nonzero_u16")
     return status_dict(st)
 
 

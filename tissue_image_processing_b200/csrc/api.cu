@@ -15,6 +15,11 @@ void set_error(const char* fmt, ...) {
 }
 
 thread_local bool tl_chain_launches = true;
+std::atomic<bool> g_no_chain{false};
+
+static const char* kStageNames[STG_COUNT] = {"percentile", "decimate", "coarse", "interp_argmax", "prepare",
+                                             "blur_pre", "blur_score", "argmax", "band", "widen",
+                                             "percentile_sample", "percentile_count"};
 
 void prof_mark(tsp_handle* h, cudaStream_t s, int stage) {
     if (!h->profiling) return;
@@ -48,10 +53,6 @@ int get_tensor_map_encoder(EncodeTiledFn* out) {
     return TSP_OK;
 }
 
-static const char* kStageNames[STG_COUNT] = {"percentile", "decimate", "coarse", "interp_argmax", "prepare",
-                                             "blur_pre", "blur_score", "argmax", "band", "widen",
-                                             "percentile_sample", "percentile_count"};
-
 struct Crop {
     int z0;        // first plane of the cropped stack inside the full stack
     int zc;        // planes after SP:30-31
@@ -79,7 +80,8 @@ static int resolve_crop(const tsp_frame_desc* d, Crop* c) {
         set_error("unknown method %d", d->method);
         return TSP_ERR_INVALID;
     }
-    if ((d->flags & ~TSP_FRAME_CONCURRENT) != 0 || d->reserved[0] != 0 || d->reserved[1] != 0) {
+    if ((d->flags & ~(TSP_FRAME_CONCURRENT | TSP_FRAME_OUT_U16)) != 0 || d->reserved != 0 ||
+        (d->has_params != 0 && d->has_params != 1)) {
         set_error("unknown flags 0x%x (or non-zero reserved words) in the frame descriptor", (unsigned)d->flags);
         return TSP_ERR_INVALID;
     }
@@ -95,6 +97,47 @@ static int resolve_crop(const tsp_frame_desc* d, Crop* c) {
     } else {
         c->z0 = 0;
         c->zc = d->planes;
+    }
+    return TSP_OK;
+}
+
+static const tsp_params kReferenceParams = {95.0f, kAiryscanPedestal, {0.5f, 1.0f, 1.0f}, {0.5f, 30.0f, 30.0f},
+                                            {1.0f, 2.0f, 2.0f}, {0, 0, 0, 0, 0}};
+
+// desc.params (or the reference constants) -> what the stages take, and whether the fast-mode tables / fused band
+// kernels (built for the reference's sigmas) apply
+static int resolve_params(const tsp_frame_desc* d, Params* out) {
+    const tsp_params& p = d->has_params ? d->params : kReferenceParams;
+    if (!(p.percentile >= 0.0f && p.percentile <= 100.0f)) {
+        set_error("percentile %g outside [0, 100]", (double)p.percentile);        // numpy: "Percentiles must be in the range [0, 100]"
+        return TSP_ERR_INVALID;
+    }
+    if (p.pedestal < 0 || p.pedestal > 65535) {
+        set_error("pedestal %d outside [0, 65535]", p.pedestal);
+        return TSP_ERR_INVALID;
+    }
+    for (int i = 0; i < 5; ++i)
+        if (p.reserved[i] != 0) {
+            set_error("non-zero reserved words in tsp_params");
+            return TSP_ERR_INVALID;
+        }
+    out->q = p.percentile / 100.0f;            // float32 division, as numpy forms q for float32 data
+    out->q64 = (double)p.percentile / 100.0;
+    out->pedestal = d->airyscan ? p.pedestal : 0;
+    out->default_score = true;
+    out->default_mask = true;
+    for (int i = 0; i < 3; ++i) {
+        if (!(p.sigma_pre[i] >= 0.0f) || !(p.sigma_score[i] >= 0.0f) || !(p.sigma_mask[i] >= 0.0f) ||
+            p.sigma_pre[i] > 512.0f || p.sigma_score[i] > 512.0f || p.sigma_mask[i] > 512.0f) {
+            set_error("sigmas must lie in [0, 512]");
+            return TSP_ERR_INVALID;
+        }
+        out->sigma_pre[i] = (double)p.sigma_pre[i];
+        out->sigma_score[i] = (double)p.sigma_score[i];
+        out->sigma_mask[i] = (double)p.sigma_mask[i];
+        if (p.sigma_pre[i] != kReferenceParams.sigma_pre[i] || p.sigma_score[i] != kReferenceParams.sigma_score[i])
+            out->default_score = false;
+        if (p.sigma_mask[i] != kReferenceParams.sigma_mask[i]) out->default_mask = false;
     }
     return TSP_OK;
 }
@@ -116,8 +159,15 @@ struct Workspace {
 };
 
 static bool general_path(const tsp_frame_desc* d) { return d->bin_size > 1 || d->build_manifold != 0; }
+static bool fast_score(const tsp_frame_desc* d, const Params& pr) {
+    return d->mode == TSP_MODE_FAST && !general_path(d) && pr.default_score;
+}
+// the fused band kernels carry the reference's (1, 2, 2) mask and fp32 arithmetic; everything else materialises it
+static bool fused_band(const tsp_frame_desc* d, const Params& pr) {
+    return d->mode != TSP_MODE_BITEXACT && pr.default_mask;
+}
 
-static Workspace carve(const tsp_frame_desc* d, const Crop& c, void* base) {
+static Workspace carve(const tsp_frame_desc* d, const Crop& c, const Params& pr, void* base) {
     Workspace w{};
     char* p = (char*)base;
     size_t off = 0;
@@ -145,14 +195,17 @@ static Workspace carve(const tsp_frame_desc* d, const Crop& c, void* base) {
         off += align_up((size_t)d->rows * d->cols * sizeof(int32_t), 256);
         w.mf_scratch = p + off;
         off += align_up(manifold_scratch_bytes(), 256);
-    } else if (d->mode == TSP_MODE_FAST) {
-        w.fast = p + off;
-        off += fast_workspace_bytes(c.zc, d->rows, d->cols);
     } else {
-        w.volA = (float*)(p + off);
-        off += vol;
-        w.volB = (float*)(p + off);
-        off += vol;
+        if (fast_score(d, pr)) {
+            w.fast = p + off;
+            off += fast_workspace_bytes(c.zc, d->rows, d->cols);
+        }
+        if (!fast_score(d, pr) || !fused_band(d, pr)) {
+            w.volA = (float*)(p + off);
+            off += vol;
+            w.volB = (float*)(p + off);
+            off += vol;
+        }
     }
     w.total = off;
     return w;
@@ -188,7 +241,33 @@ int tsp_create(int device, tsp_handle** out) {
     h->sm_count = prop.multiProcessorCount;
     TSP_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     TSP_CUDA(cudaMallocHost((void**)&h->h_status, kStatusWords * sizeof(int32_t)));
+    // kernel-variant switches: the environment is read here, once (tsp_debug_set changes them later)
+    auto env_int = [](const char* name, int dflt) {
+        const char* v = getenv(name);
+        return v && *v ? atoi(v) : dflt;
+    };
+    h->dbg.no_ring = env_int("TSP_NO_RING", 0);
+    h->dbg.band_variant = env_int("TSP_BAND_VARIANT", 0);
+    h->dbg.interp_rows = env_int("TSP_INTERP_ROWS", 4);
+    if (env_int("TSP_NO_CHAIN", 0)) g_no_chain.store(true);
     *out = h;
+    return TSP_OK;
+}
+
+void tsp_default_params(tsp_params* out) {
+    if (out) *out = kReferenceParams;
+}
+
+int tsp_debug_set(tsp_handle* h, const char* key, int value) {
+    if (!h || !key) return TSP_ERR_INVALID;
+    if (!strcmp(key, "no_ring")) h->dbg.no_ring = value;
+    else if (!strcmp(key, "band_variant") && (value == 0 || value == 2 || value == 3)) h->dbg.band_variant = value;
+    else if (!strcmp(key, "interp_rows") && (value == 2 || value == 4 || value == 8)) h->dbg.interp_rows = value;
+    else if (!strcmp(key, "no_chain")) g_no_chain.store(value != 0);
+    else {
+        set_error("unknown debug switch %s = %d", key, value);
+        return TSP_ERR_INVALID;
+    }
     return TSP_OK;
 }
 
@@ -219,8 +298,9 @@ int64_t tsp_launch_count(const tsp_handle* h) { return h ? h->launches : 0; }
 
 size_t tsp_project_workspace_bytes(const tsp_frame_desc* desc) {
     Crop c;
-    if (!desc || resolve_crop(desc, &c)) return 0;
-    return carve(desc, c, nullptr).total;
+    Params pr;
+    if (!desc || resolve_crop(desc, &c) || resolve_params(desc, &pr)) return 0;
+    return carve(desc, c, pr, nullptr).total;
 }
 
 int tsp_project_frame(tsp_handle* h, const tsp_frame_desc* desc, const uint16_t* d_stack, float* d_proj,
@@ -230,9 +310,12 @@ int tsp_project_frame(tsp_handle* h, const tsp_frame_desc* desc, const uint16_t*
         return TSP_ERR_INVALID;
     }
     Crop c;
+    Params pr;
     int rc = resolve_crop(desc, &c);
     if (rc) return rc;
-    Workspace w = carve(desc, c, d_workspace);
+    rc = resolve_params(desc, &pr);
+    if (rc) return rc;
+    Workspace w = carve(desc, c, pr, d_workspace);
     if (workspace_bytes < w.total) {
         set_error("workspace %zu bytes < required %zu", workspace_bytes, w.total);
         return TSP_ERR_WORKSPACE;
@@ -248,10 +331,14 @@ int tsp_project_frame(tsp_handle* h, const tsp_frame_desc* desc, const uint16_t*
     const size_t chan_stride = (size_t)desc->planes * plane;
     const size_t z0_off = (size_t)c.z0 * plane;
     const size_t nvox = (size_t)c.zc * plane;
-    const int ped = desc->airyscan ? kAiryscanPedestal : 0;
+    const int ped = pr.pedestal;
     const uint16_t* ref = d_stack + (size_t)desc->reference_channel * chan_stride + z0_off;
+    const double* sig_pre = pr.sigma_pre;          // SP:37
+    const double* sig_score = pr.sigma_score;      // SP:55
+    const bool band_fused = fused_band(desc, pr);
 
     int* worklist = w.worklist;
+    NvtxRange frame_range("tsp/frame");
     prof_mark(h, s, -1);
     if (general_path(desc)) {
         // SP:39-65 with bin_size > 1 and / or build_manifold: direct-FIR score volumes, binned, then either the
@@ -260,11 +347,10 @@ int tsp_project_frame(tsp_handle* h, const tsp_frame_desc* desc, const uint16_t*
         const int bin = desc->bin_size > 1 ? desc->bin_size : 1;
         const bool binned = bin > 1, manifold = desc->build_manifold != 0;
         const int cy = (Y + bin - 1) / bin, cx = (X + bin - 1) / bin;
-        const double sig_pre[3] = {0.5, 1.0, 1.0};       // SP:37
-        const double sig_score[3] = {0.5, 30.0, 30.0};   // SP:55
-        rc = launch_percentile(h, ref, nvox, ped, w.status, w.hist, s);
+        rc = launch_percentile(h, ref, nvox, ped, w.status, w.hist, s, nullptr, 0, pr.q, pr.q64);
         if (rc) return rc;
         prof_mark(h, s, STG_PERCENTILE);
+        NvtxRange general_range("tsp/general_score");
         rc = launch_prepare(h, ref, w.volA, nvox, ped, w.status, s);
         if (rc) return rc;
         rc = gaussian_blur<float>(h, w.volA, w.volB, w.volA, c.zc, Y, X, sig_pre, fp64, s);     // volB = pc
@@ -286,7 +372,7 @@ int tsp_project_frame(tsp_handle* h, const tsp_frame_desc* desc, const uint16_t*
             if (desc->method == TSP_METHOD_MULTI_CHANNEL) {                                     // SP:44-51
                 const int oc = (desc->reference_channel + 1) % C;
                 const uint16_t* other = d_stack + (size_t)oc * chan_stride + z0_off;
-                rc = launch_percentile_all(h, other, nvox, ped, w.status2, w.hist, s);
+                rc = launch_percentile_all(h, other, nvox, ped, w.status2, w.hist, s, pr.q);
                 if (rc) return rc;
                 rc = launch_prepare(h, other, w.volA, nvox, ped, w.status2, s);
                 if (rc) return rc;
@@ -320,10 +406,11 @@ int tsp_project_frame(tsp_handle* h, const tsp_frame_desc* desc, const uint16_t*
             }
         }
         prof_mark(h, s, STG_ARGMAX);
-        if (fp64)
+        NvtxRange band_range("tsp/band");
+        if (!band_fused)
             rc = launch_band_project_bitexact_ex(h, d_stack, chan_stride, z0_off, d_zmap, d_proj, C, c.zc, Y, X,
                                                  desc->reference_channel, desc->atoh_shift, ped, w.volA, w.volB,
-                                                 w.status, range_known, s, zmap_other);
+                                                 w.status, range_known, s, zmap_other, pr.sigma_mask, fp64);
         else
             rc = launch_band_project_ex(h, d_stack, chan_stride, z0_off, d_zmap, d_proj, C, c.zc, Y, X,
                                         desc->reference_channel, desc->atoh_shift, ped, w.status, range_known, s,
@@ -331,39 +418,38 @@ int tsp_project_frame(tsp_handle* h, const tsp_frame_desc* desc, const uint16_t*
         prof_mark(h, s, STG_BAND);
         return rc;
     }
-    const bool fast = desc->mode == TSP_MODE_FAST;
-    rc = launch_percentile(h, ref, nvox, ped, w.status, w.hist, s, fast ? w.fast : nullptr,
-                           fast ? fast_accum_bytes(c.zc, Y, X) : 0);
-    if (rc) return rc;
-    prof_mark(h, s, STG_PERCENTILE);
-
+    const bool fast = fast_score(desc, pr);
+    const bool fp64 = desc->mode == TSP_MODE_BITEXACT;
+    {
+        NvtxRange r("tsp/percentile");
+        rc = launch_percentile(h, ref, nvox, ped, w.status, w.hist, s, fast ? w.fast : nullptr,
+                               fast ? fast_accum_bytes(c.zc, Y, X) : 0, pr.q, pr.q64);
+        if (rc) return rc;
+        prof_mark(h, s, STG_PERCENTILE);
+    }
     if (fast) {
         rc = launch_fast_score_argmax(h, ref, d_zmap, c.zc, Y, X, ped, c.z_offset, w.status, w.fast, s, true);
         if (rc) return rc;
-        rc = launch_band_project_ex(h, d_stack, chan_stride, z0_off, d_zmap, d_proj, C, c.zc, Y, X,
-                                    desc->reference_channel, desc->atoh_shift, ped, w.status, true, s, worklist);
-        prof_mark(h, s, STG_BAND);
-        return rc;
+    } else {
+        NvtxRange r("tsp/score_fir");
+        rc = launch_prepare(h, ref, w.volA, nvox, ped, w.status, s);
+        if (rc) return rc;
+        prof_mark(h, s, STG_PREPARE);
+        rc = gaussian_blur<float>(h, w.volA, w.volB, w.volA, c.zc, Y, X, sig_pre, fp64, s);
+        if (rc) return rc;
+        prof_mark(h, s, STG_BLUR_PRE);
+        rc = gaussian_blur<float>(h, w.volB, w.volA, w.volB, c.zc, Y, X, sig_score, fp64, s);
+        if (rc) return rc;
+        prof_mark(h, s, STG_BLUR_SCORE);
+        rc = launch_argmax(h, w.volA, d_zmap, c.zc, Y, X, c.z_offset, w.status, s);
+        if (rc) return rc;
+        prof_mark(h, s, STG_ARGMAX);
     }
-    const bool fp64 = desc->mode == TSP_MODE_BITEXACT;
-    const double sig_pre[3] = {0.5, 1.0, 1.0};       // SP:37
-    const double sig_score[3] = {0.5, 30.0, 30.0};   // SP:55
-    rc = launch_prepare(h, ref, w.volA, nvox, ped, w.status, s);
-    if (rc) return rc;
-    prof_mark(h, s, STG_PREPARE);
-    rc = gaussian_blur<float>(h, w.volA, w.volB, w.volA, c.zc, Y, X, sig_pre, fp64, s);
-    if (rc) return rc;
-    prof_mark(h, s, STG_BLUR_PRE);
-    rc = gaussian_blur<float>(h, w.volB, w.volA, w.volB, c.zc, Y, X, sig_score, fp64, s);
-    if (rc) return rc;
-    prof_mark(h, s, STG_BLUR_SCORE);
-    rc = launch_argmax(h, w.volA, d_zmap, c.zc, Y, X, c.z_offset, w.status, s);
-    if (rc) return rc;
-    prof_mark(h, s, STG_ARGMAX);
-    if (fp64)
+    NvtxRange band_range("tsp/band");
+    if (!band_fused)
         rc = launch_band_project_bitexact_ex(h, d_stack, chan_stride, z0_off, d_zmap, d_proj, C, c.zc, Y, X,
                                              desc->reference_channel, desc->atoh_shift, ped, w.volA, w.volB,
-                                             w.status, true, s);
+                                             w.status, true, s, nullptr, pr.sigma_mask, fp64);
     else
         rc = launch_band_project_ex(h, d_stack, chan_stride, z0_off, d_zmap, d_proj, C, c.zc, Y, X,
                                     desc->reference_channel, desc->atoh_shift, ped, w.status, true, s, worklist);
@@ -464,71 +550,93 @@ static int ensure_slot(tsp_handle* h, int slot, size_t bytes) {
     return TSP_OK;
 }
 
-int tsp_frame_submit(tsp_handle* h, int slot, const tsp_frame_desc* desc, const uint16_t* h_stack, double* h_proj,
-                     int64_t* h_zmap) {
-    if (!h || !desc || !h_stack || !h_proj || !h_zmap || slot < 0 || slot >= TSP_MAX_SLOTS) {
-        set_error("bad argument to tsp_frame_submit");
-        return TSP_ERR_INVALID;
-    }
+// copy-in, operator, conversion, copy-out of one frame on slot `slot` (< TSP_MAX_SLOTS: the caller's slots; the last
+// one belongs to tsp_project_frame_host)
+static int submit_on_slot(tsp_handle* h, int slot, const tsp_frame_desc* desc, const uint16_t* h_stack, void* h_proj,
+                          void* h_zmap) {
     Crop c;
     int rc = resolve_crop(desc, &c);
     if (rc) return rc;
     TSP_CUDA(cudaSetDevice(h->device));
     std::lock_guard<std::mutex> lock(h->host_mu);
-    if (h->slots[slot].busy) {
+    tsp_handle::Slot& sl = h->slots[slot];
+    if (sl.busy.load()) {
         set_error("slot %d still has a frame in flight: call tsp_frame_wait first", slot);
         return TSP_ERR_INVALID;
     }
+    const bool out16 = (desc->flags & TSP_FRAME_OUT_U16) != 0;
     const size_t plane = (size_t)desc->rows * desc->cols;
     const size_t nstack = (size_t)desc->channels * desc->planes * plane;
     const size_t nproj = (size_t)desc->channels * plane;
     const size_t ws = tsp_project_workspace_bytes(desc);
+    if (ws == 0) return TSP_ERR_INVALID;
+    const size_t proj_out = nproj * (out16 ? sizeof(uint16_t) : sizeof(double));
+    const size_t zmap_out = plane * (out16 ? sizeof(uint16_t) : sizeof(int64_t));
     size_t off = 0;
     const size_t o_stack = off;  off += align_up(nstack * sizeof(uint16_t), 256);
     const size_t o_proj = off;   off += align_up(nproj * sizeof(float), 256);
     const size_t o_zmap = off;   off += align_up(plane * sizeof(int32_t), 256);
-    const size_t o_proj64 = off; off += align_up(nproj * sizeof(double), 256);
-    const size_t o_zmap64 = off; off += align_up(plane * sizeof(int64_t), 256);
+    const size_t o_projx = off;  off += align_up(proj_out, 256);
+    const size_t o_zmapx = off;  off += align_up(zmap_out, 256);
     const size_t o_ws = off;     off += ws;
     rc = ensure_slot(h, slot, off);
     if (rc) return rc;
-    tsp_handle::Slot& sl = h->slots[slot];
     char* base = (char*)sl.d_mem;
     cudaStream_t s = sl.stream;
-    TSP_CUDA(cudaMemcpyAsync(base + o_stack, h_stack, nstack * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
     tsp_frame_desc d2 = *desc;
-    for (int k = 0; k < TSP_MAX_SLOTS; ++k)
-        if (k != slot && h->slots[k].busy) d2.flags |= TSP_FRAME_CONCURRENT;      // other frames are in flight
-    desc = &d2;
-    rc = tsp_project_frame(h, desc, (const uint16_t*)(base + o_stack), (float*)(base + o_proj),
+    d2.flags &= ~TSP_FRAME_OUT_U16;
+    for (int k = 0; k <= TSP_MAX_SLOTS; ++k)
+        if (k != slot && h->slots[k].busy.load()) d2.flags |= TSP_FRAME_CONCURRENT;      // other frames are in flight
+    // From the first enqueued copy on, a failure must not return while the stream may still read the caller's
+    // buffers: drain the slot's stream first.
+    auto fail = [&](int code) {
+        cudaStreamSynchronize(s);
+        return code;
+    };
+    cudaError_t e = cudaMemcpyAsync(base + o_stack, h_stack, nstack * sizeof(uint16_t), cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) {
+        set_error("copy-in failed: %s", cudaGetErrorString(e));
+        return fail(TSP_ERR_CUDA);
+    }
+    rc = tsp_project_frame(h, &d2, (const uint16_t*)(base + o_stack), (float*)(base + o_proj),
                            (int32_t*)(base + o_zmap), base + o_ws, ws, s);
-    if (rc) return rc;
-    rc = launch_widen_outputs(h, (const float*)(base + o_proj), (const int32_t*)(base + o_zmap),
-                              (double*)(base + o_proj64), (int64_t*)(base + o_zmap64), nproj, plane, s);
-    if (rc) return rc;
-    TSP_CUDA(cudaMemcpyAsync(sl.h_status, base + o_ws, kStatusWords * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-    TSP_CUDA(cudaMemcpyAsync(h_proj, base + o_proj64, nproj * sizeof(double), cudaMemcpyDeviceToHost, s));
-    TSP_CUDA(cudaMemcpyAsync(h_zmap, base + o_zmap64, plane * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-    sl.busy = true;
+    if (rc) return fail(rc);
+    {
+        NvtxRange r("tsp/convert_copy_out");
+        if (out16)
+            rc = launch_narrow_outputs(h, (const float*)(base + o_proj), (const int32_t*)(base + o_zmap),
+                                       (uint16_t*)(base + o_projx), (uint16_t*)(base + o_zmapx), nproj, plane, s);
+        else
+            rc = launch_widen_outputs(h, (const float*)(base + o_proj), (const int32_t*)(base + o_zmap),
+                                      (double*)(base + o_projx), (int64_t*)(base + o_zmapx), nproj, plane, s);
+        if (rc) return fail(rc);
+        e = cudaMemcpyAsync(sl.h_status, base + o_ws, kStatusWords * sizeof(int32_t), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h_proj, base + o_projx, proj_out, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h_zmap, base + o_zmapx, zmap_out, cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) {
+            set_error("copy-out failed: %s", cudaGetErrorString(e));
+            return fail(TSP_ERR_CUDA);
+        }
+    }
+    sl.busy.store(true);
     return TSP_OK;
 }
 
-int tsp_frame_wait(tsp_handle* h, int slot, tsp_frame_status* status) {
-    if (!h || slot < 0 || slot >= TSP_MAX_SLOTS) return TSP_ERR_INVALID;
+static int wait_on_slot(tsp_handle* h, int slot, tsp_frame_status* status) {
     tsp_handle::Slot& sl = h->slots[slot];
-    if (!sl.busy) {
+    if (!sl.busy.load()) {
         set_error("slot %d has no frame in flight", slot);
         return TSP_ERR_INVALID;
     }
     TSP_CUDA(cudaSetDevice(h->device));
     cudaError_t e = cudaStreamSynchronize(sl.stream);
-    sl.busy = false;
+    tsp_frame_status st;
+    if (e == cudaSuccess) fill_status(sl.h_status, &st);
+    sl.busy.store(false);
     if (e != cudaSuccess) {
         set_error("cudaStreamSynchronize failed: %s", cudaGetErrorString(e));
         return TSP_ERR_CUDA;
     }
-    tsp_frame_status st;
-    fill_status(sl.h_status, &st);
     if (status) *status = st;
     if (st.band_index_error) {
         set_error("height map indexes past the cropped stack (reference raises IndexError)");
@@ -537,11 +645,32 @@ int tsp_frame_wait(tsp_handle* h, int slot, tsp_frame_status* status) {
     return TSP_OK;
 }
 
-int tsp_project_frame_host(tsp_handle* h, const tsp_frame_desc* desc, const uint16_t* h_stack, double* h_proj,
-                           int64_t* h_zmap, tsp_frame_status* status) {
-    int rc = tsp_frame_submit(h, 0, desc, h_stack, h_proj, h_zmap);
+int tsp_frame_submit(tsp_handle* h, int slot, const tsp_frame_desc* desc, const uint16_t* h_stack, void* h_proj,
+                     void* h_zmap) {
+    if (!h || !desc || !h_stack || !h_proj || !h_zmap || slot < 0 || slot >= TSP_MAX_SLOTS) {
+        set_error("bad argument to tsp_frame_submit");
+        return TSP_ERR_INVALID;
+    }
+    return submit_on_slot(h, slot, desc, h_stack, h_proj, h_zmap);
+}
+
+int tsp_frame_wait(tsp_handle* h, int slot, tsp_frame_status* status) {
+    if (!h || slot < 0 || slot >= TSP_MAX_SLOTS) return TSP_ERR_INVALID;
+    return wait_on_slot(h, slot, status);
+}
+
+// One blocking call = submit + wait on the handle's own slot; single_mu makes calls from several host threads take
+// turns (a slot pipeline running on the same handle is not disturbed: its slots are different ones).
+int tsp_project_frame_host(tsp_handle* h, const tsp_frame_desc* desc, const uint16_t* h_stack, void* h_proj,
+                           void* h_zmap, tsp_frame_status* status) {
+    if (!h || !desc || !h_stack || !h_proj || !h_zmap) {
+        set_error("bad argument to tsp_project_frame_host");
+        return TSP_ERR_INVALID;
+    }
+    std::lock_guard<std::mutex> turn(h->single_mu);
+    int rc = submit_on_slot(h, TSP_MAX_SLOTS, desc, h_stack, h_proj, h_zmap);
     if (rc) return rc;
-    return tsp_frame_wait(h, 0, status);
+    return wait_on_slot(h, TSP_MAX_SLOTS, status);
 }
 
 int tsp_gaussian_blur_f32(tsp_handle* h, const float* d_in, float* d_out, float* d_tmp, int planes, int rows,
@@ -562,7 +691,16 @@ int tsp_gaussian_blur_u16(tsp_handle* h, const uint16_t* d_in, uint16_t* d_out, 
 
 int tsp_percentile95_nonzero_u16(tsp_handle* h, const uint16_t* d_volume, size_t count, int airyscan,
                                  void* cuda_stream, tsp_frame_status* out) {
+    return tsp_percentile_nonzero_u16(h, d_volume, count, 95.0f, airyscan ? kAiryscanPedestal : 0, cuda_stream, out);
+}
+
+int tsp_percentile_nonzero_u16(tsp_handle* h, const uint16_t* d_volume, size_t count, float percentile, int pedestal,
+                               void* cuda_stream, tsp_frame_status* out) {
     if (!h || !d_volume || !out) return TSP_ERR_INVALID;
+    if (!(percentile >= 0.0f && percentile <= 100.0f) || pedestal < 0 || pedestal > 65535) {
+        set_error("percentile %g / pedestal %d out of range", (double)percentile, pedestal);
+        return TSP_ERR_INVALID;
+    }
     TSP_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = (cudaStream_t)cuda_stream;
     const size_t bytes = align_up(kStatusWords * sizeof(int32_t), 256) + percentile_scratch_bytes();
@@ -571,7 +709,8 @@ int tsp_percentile95_nonzero_u16(tsp_handle* h, const uint16_t* d_volume, size_t
     if (rc) return rc;
     int32_t* st = (int32_t*)h->d_scratch;
     uint32_t* hist = (uint32_t*)((char*)h->d_scratch + align_up(kStatusWords * sizeof(int32_t), 256));
-    rc = launch_percentile(h, d_volume, count, airyscan ? kAiryscanPedestal : 0, st, hist, s);
+    rc = launch_percentile(h, d_volume, count, pedestal, st, hist, s, nullptr, 0, percentile / 100.0f,
+                           (double)percentile / 100.0);
     if (rc) return rc;
     TSP_CUDA(cudaMemcpyAsync(h->h_status, st, kStatusWords * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     TSP_CUDA(cudaStreamSynchronize(s));

@@ -1170,7 +1170,7 @@ static int launch_band_range(tsp_handle* h, const int32_t* d_zmap, int Z, int Y,
 // channels are projected two per CTA; an odd channel count ends with a one-channel launch
 static int launch_band_variant(tsp_handle* h, BandArgs a, dim3 grid, int pedestal, int C, cudaStream_t s) {
     // TMA path: rows 16-byte aligned (the tensor map's stride rule), tile not larger than the image
-    const bool tma = a.vec && (a.X % 8 == 0) && a.X >= kBandTX && a.Y >= kBandTY && !getenv("TSP_BAND_V2");
+    const bool tma = a.vec && (a.X % 8 == 0) && a.X >= kBandTX && a.Y >= kBandTY && h->dbg.band_variant != 2;
     CUtensorMap tmap;
     if (tma) {
         int rc = make_band_tensor_map(a.stack + a.z0_offset, a.channel_stride, C, a.Z, a.Y, a.X, &tmap);
@@ -1185,7 +1185,7 @@ static int launch_band_variant(tsp_handle* h, BandArgs a, dim3 grid, int pedesta
         }
     }
     // shallow tiles first, one channel per CTA; the deep ones come back through the worklist
-    if (tma && a.worklist && !getenv("TSP_BAND_V3")) {
+    if (tma && a.worklist && h->dbg.band_variant != 3) {
         {
             std::lock_guard<std::mutex> lock(h->mu);
             if (!h->band4_attr) {
@@ -1345,7 +1345,9 @@ int launch_band_project_bitexact_ex(tsp_handle* h, const uint16_t* d_stack, size
                                     size_t z0_offset, const int32_t* d_zmap, float* d_proj, int C, int Z,
                                     int Y, int X, int ref_c, int shift, int pedestal, float* d_volA,
                                     float* d_volB, int32_t* d_status, bool range_known, cudaStream_t s,
-                                    const int32_t* d_zmap_other) {
+                                    const int32_t* d_zmap_other, const double* sigma_mask, bool fp64) {
+    // Also the general form of the band stage: any sigma_mask (tsp_params), fp64 = scipy's summation order
+    // (bit-exact), otherwise fp32 FMA accumulation.
     if (d_zmap_other) {
         range_known = false;
         shift = 0;
@@ -1355,7 +1357,8 @@ int launch_band_project_bitexact_ex(tsp_handle* h, const uint16_t* d_stack, size
     const size_t plane = (size_t)Y * X;
     size_t blocks = (plane + 255) / 256;
     if (blocks > (size_t)h->sm_count * 32) blocks = (size_t)h->sm_count * 32;
-    const double sig[3] = {1.0, 2.0, 2.0};
+    const double sig_ref[3] = {1.0, 2.0, 2.0};       // SP:70-71
+    const double* sig = sigma_mask ? sigma_mask : sig_ref;
     for (int pass = 0; pass < 2; ++pass) {
         const int sh = pass == 0 ? 0 : shift;
         const bool two_maps = shift != 0 || d_zmap_other;
@@ -1363,7 +1366,7 @@ int launch_band_project_bitexact_ex(tsp_handle* h, const uint16_t* d_stack, size
         onehot_kernel<<<(int)blocks, 256, 0, s>>>(pass == 1 && d_zmap_other ? d_zmap_other : d_zmap, d_volA, Z, plane, sh,
                                                   d_status);
         TSP_LAUNCH_CHECK(h);
-        rc = gaussian_blur<float>(h, d_volA, d_volB, d_volA, Z, Y, X, sig, true, s);
+        rc = gaussian_blur<float>(h, d_volA, d_volB, d_volA, Z, Y, X, sig, fp64, s);
         if (rc) return rc;
         for (int c = 0; c < C; ++c) {
             const bool uses = !two_maps ? (pass == 0) : ((c == ref_c) == (pass == 0));
@@ -1391,6 +1394,27 @@ int launch_widen_outputs(tsp_handle* h, const float* d_proj, const int32_t* d_zm
     if (blocks > (size_t)h->sm_count * 16) blocks = (size_t)h->sm_count * 16;
     if (blocks == 0) blocks = 1;
     widen_kernel<<<(int)blocks, 256, 0, s>>>(d_proj, d_zmap, d_proj64, (long long*)d_zmap64, nproj, nz);
+    TSP_LAUNCH_CHECK(h);
+    return TSP_OK;
+}
+
+// ---- output narrowing for the movie driver: numpy's astype("uint16") of the float64 projection (BIM:481) and of the
+// height map (SP:229-231) is a C cast: truncation toward zero (the values are non-negative and below 65536)
+__global__ void narrow_kernel(const float* __restrict__ p32, const int32_t* __restrict__ z32,
+                              uint16_t* __restrict__ p16, uint16_t* __restrict__ z16, size_t np, size_t nz) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < np; i += stride)
+        p16[i] = (uint16_t)(long long)p32[i];
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nz; i += stride) z16[i] = (uint16_t)z32[i];
+}
+
+int launch_narrow_outputs(tsp_handle* h, const float* d_proj, const int32_t* d_zmap, uint16_t* d_proj16,
+                          uint16_t* d_zmap16, size_t nproj, size_t nz, cudaStream_t s) {
+    size_t n = nproj > nz ? nproj : nz;
+    size_t blocks = (n + 255) / 256;
+    if (blocks > (size_t)h->sm_count * 16) blocks = (size_t)h->sm_count * 16;
+    if (blocks == 0) blocks = 1;
+    narrow_kernel<<<(int)blocks, 256, 0, s>>>(d_proj, d_zmap, d_proj16, d_zmap16, nproj, nz);
     TSP_LAUNCH_CHECK(h);
     return TSP_OK;
 }

@@ -7,11 +7,14 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <string>
 #include <cstdlib>
 #include <vector>
+
+#include <nvtx3/nvToolsExt.h>
 
 #include "../../include/tsp_b200.h"
 
@@ -41,6 +44,16 @@ enum StatusWord {
 
 void set_error(const char* fmt, ...);
 
+// tsp_params with the defaults applied and the routing decisions taken (api.cu: resolve_params)
+struct Params {
+    float q;                  // percentile / 100 in float32, the way numpy forms it for float32 data (SP:35)
+    double q64;               // the same fraction for the sample-window statistics
+    int pedestal;             // 0 when the frame is not airyscan
+    double sigma_pre[3], sigma_score[3], sigma_mask[3];
+    bool default_score;       // sigma_pre / sigma_score are the reference's: the fast-mode tables apply
+    bool default_mask;        // sigma_mask is the reference's: the fused band kernels apply
+};
+
 enum Stage {
     STG_PERCENTILE = 0, STG_DECIMATE, STG_COARSE, STG_INTERP_ARGMAX, STG_PREPARE, STG_BLUR_PRE, STG_BLUR_SCORE,
     STG_ARGMAX, STG_BAND, STG_WIDEN, STG_PCT_SAMPLE, STG_PCT_COUNT, STG_COUNT
@@ -69,6 +82,17 @@ enum Stage {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// NVTX range on the launching thread around the launches of one stage ("tsp/decimate", ...): a timeline shows which
+// kernels belong to which stage of which frame.  Costs nothing without a profiler attached.
+struct NvtxRange {
+    bool open = true;
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    void end() { if (open) { nvtxRangePop(); open = false; } }
+    ~NvtxRange() { end(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+
 // scipy.ndimage Gaussian weights: radius int(4*sigma+0.5), exp(-k^2/(2 sigma^2)) / sum, float64
 std::vector<double> gaussian_taps(double sigma);
 
@@ -87,6 +111,7 @@ constexpr int kTapPad = 8;
 // may start queueing.  Launched the ordinary way (<<<>>>) both calls do nothing.  What this buys is the ~2 us of
 // launch latency and ramp at each of the frame's ten kernel boundaries.
 extern thread_local bool tl_chain_launches;      // false while a TSP_FRAME_CONCURRENT frame is being enqueued
+extern std::atomic<bool> g_no_chain;             // A/B switch (TSP_NO_CHAIN at tsp_create, tsp_debug_set "no_chain")
 #ifdef __CUDACC__
 __device__ __forceinline__ void chain_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void chain_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
@@ -102,9 +127,8 @@ inline cudaError_t launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 bloc
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    static const bool allowed = getenv("TSP_NO_CHAIN") == nullptr;       // A/B switch for measurements
     cfg.attrs = attr;
-    cfg.numAttrs = allowed && tl_chain_launches ? 1 : 0;
+    cfg.numAttrs = !g_no_chain.load(std::memory_order_relaxed) && tl_chain_launches ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 #endif
@@ -172,8 +196,15 @@ struct tsp_handle {
     int device = 0;
     int sm_count = 148;
     int64_t launches = 0;
+    // kernel-variant switches for tests / A-B measurements: environment read once at tsp_create, tsp_debug_set later
+    struct Debug {
+        int no_ring = 0;         // strip decimation kernel instead of the TMA ring
+        int band_variant = 0;    // 0 auto, 2 register-prefetch kernel, 3 TMA ring kernel for every tile
+        int interp_rows = 4;     // image rows per thread of the interpolation + argmax stage
+    } dbg;
     std::mutex mu;        // guards taps / tables
-    std::mutex host_mu;   // serialises the host-buffer entry points (they share d_scratch)
+    std::mutex host_mu;   // guards d_scratch and the slot table (held only while a call is being enqueued)
+    std::mutex single_mu; // tsp_project_frame_host: one blocking call at a time on the handle's own slot
     // small device arena for FIR taps and fast-mode tables, keyed by a text key
     std::map<std::string, tsp::DeviceTaps> taps;
     std::map<std::string, void*> tables;
@@ -189,9 +220,9 @@ struct tsp_handle {
         void* d_mem = nullptr;
         size_t bytes = 0;
         int32_t* h_status = nullptr;
-        bool busy = false;
+        std::atomic<bool> busy{false};
     };
-    Slot slots[TSP_MAX_SLOTS];
+    Slot slots[TSP_MAX_SLOTS + 1];       // the last one belongs to tsp_project_frame_host
     // per-device one-time setup done (constant memory, function attributes)
     bool fast_consts = false, band_consts = false, hist_attr = false, ring_attr = false, band3_attr = false, band4_attr = false, xy_attr = false, manifold_attr = false, count_attr = false;
     // optional per-stage timing (tsp_set_profiling): CUDA events recorded on the launching stream
@@ -211,7 +242,8 @@ void prof_mark(tsp_handle* h, cudaStream_t s, int stage);   // stage -1 opens a 
 // stage launchers (each returns TSP_OK or an error code)
 size_t percentile_scratch_bytes();
 int launch_percentile(tsp_handle* h, const uint16_t* d_vol, size_t count, int pedestal, int32_t* d_status,
-                      void* d_scratch, cudaStream_t s, void* zero_ptr = nullptr, size_t zero_bytes = 0);
+                      void* d_scratch, cudaStream_t s, void* zero_ptr = nullptr, size_t zero_bytes = 0,
+                      float q = 0.95f, double q64 = 0.95);
 int launch_prepare(tsp_handle* h, const uint16_t* d_in, float* d_out, size_t count, int pedestal,
                    const int32_t* d_status, cudaStream_t s);
 int launch_convert_u16_f32(tsp_handle* h, const uint16_t* d_in, float* d_out, size_t count,
@@ -231,7 +263,7 @@ int launch_band_project_ex(tsp_handle* h, const uint16_t* d_stack, size_t channe
 size_t band_worklist_bytes(int Y, int X);
 // binned scores, their resampling and the continuous manifold (binned.cu)
 int launch_percentile_all(tsp_handle* h, const uint16_t* d_vol, size_t count, int pedestal, int32_t* d_status,
-                          void* d_scratch, cudaStream_t s);
+                          void* d_scratch, cudaStream_t s, float q = 0.95f);
 int launch_block_reduce(tsp_handle* h, const float* d_vol, float* d_out, int Z, int Y, int X, int bin,
                         bool variance, bool multiply, cudaStream_t s);
 int launch_resize_argmax(tsp_handle* h, const float* d_score, int32_t* d_zmap, int Z, int Y, int X, int cy, int cx,
@@ -245,11 +277,14 @@ int launch_band_project_bitexact_ex(tsp_handle* h, const uint16_t* d_stack, size
                                     size_t z0_offset, const int32_t* d_zmap, float* d_proj, int C, int Z,
                                     int Y, int X, int ref_c, int shift, int pedestal, float* d_volA,
                                     float* d_volB, int32_t* d_status, bool range_known, cudaStream_t s,
-                                    const int32_t* d_zmap_other = nullptr);
+                                    const int32_t* d_zmap_other = nullptr, const double* sigma_mask = nullptr,
+                                    bool fp64 = true);
 int launch_project_m(tsp_handle* h, const uint16_t* d_channel, uint16_t* d_out, int Z, int Y, int X,
                      int method, int bin, void* d_ws, cudaStream_t s);
 int launch_widen_outputs(tsp_handle* h, const float* d_proj, const int32_t* d_zmap, double* d_proj64,
                          int64_t* d_zmap64, size_t nproj, size_t nz, cudaStream_t s);
+int launch_narrow_outputs(tsp_handle* h, const float* d_proj, const int32_t* d_zmap, uint16_t* d_proj16,
+                          uint16_t* d_zmap16, size_t nproj, size_t nz, cudaStream_t s);
 
 // fast (multirate) score stage
 size_t fast_workspace_bytes(int Z, int Y, int X);

@@ -12,6 +12,7 @@
 namespace tsp {
 
 std::vector<double> gaussian_taps(double sigma) {
+    if (sigma <= 1e-15) return std::vector<double>(1, 1.0);      // scipy skips such an axis: identity
     const int radius = (int)(4.0 * sigma + 0.5);
     std::vector<double> w(2 * radius + 1);
     double sum = 0.0;

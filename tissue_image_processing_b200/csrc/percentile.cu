@@ -199,8 +199,7 @@ struct RankPair {
     float gamma;
 };
 
-__device__ RankPair numpy_ranks(unsigned long long n) {
-    const float q = __fdiv_rn(95.0f, 100.0f);
+__device__ RankPair numpy_ranks(unsigned long long n, float q) {      // q = float32(percentile) / float32(100)
     const float nm1 = __ull2float_rn(n - 1);
     const float vi = __fmul_rn(nm1, q);
     const float prev_f = floorf(vi);
@@ -243,7 +242,8 @@ __device__ bool is_last_block(unsigned int* ticket) {
 }
 
 // ---- exact percentile from a full histogram (also the fallback) -----------------------------------
-__device__ void percentile_finalize(const uint32_t* __restrict__ ghist, int pedestal, int32_t* __restrict__ status) {
+__device__ void percentile_finalize(const uint32_t* __restrict__ ghist, int pedestal, int32_t* __restrict__ status,
+                                    float q) {
     // pass 1: total of the non-zero voxels, pass 2: the two ranks
     RankLookup first = block_rank_lookup(ghist, kHistBins, pedestal + 1, 0, ~0ull, ~0ull);
     const unsigned long long n = first.total;
@@ -251,7 +251,7 @@ __device__ void percentile_finalize(const uint32_t* __restrict__ ghist, int pede
         if (threadIdx.x == 0) write_result(status, 0, 0.f);
         return;
     }
-    const RankPair rp = numpy_ranks(n);
+    const RankPair rp = numpy_ranks(n, q);
     RankLookup look = block_rank_lookup(ghist, kHistBins, pedestal + 1, 0, rp.prev, rp.next);
     if (threadIdx.x == 0)
         write_result(status, n, numpy_lerp((float)(look.bin[0] - pedestal), (float)(look.bin[1] - pedestal), rp.gamma));
@@ -260,10 +260,10 @@ __device__ void percentile_finalize(const uint32_t* __restrict__ ghist, int pede
 // SP:46 takes the percentile of ALL voxels of the second channel (zeros included): the voxels at or below the
 // pedestal are `zeros` leading values 0 in the sorted order
 __device__ void percentile_finalize_all(const uint32_t* __restrict__ ghist, int pedestal, unsigned long long count,
-                                        int32_t* __restrict__ status) {
+                                        int32_t* __restrict__ status, float q) {
     RankLookup first = block_rank_lookup(ghist, kHistBins, pedestal + 1, 0, ~0ull, ~0ull);
     const unsigned long long zeros = count - first.total;
-    const RankPair rp = numpy_ranks(count);
+    const RankPair rp = numpy_ranks(count, q);
     RankLookup look = block_rank_lookup(ghist, kHistBins, pedestal + 1, zeros, rp.prev, rp.next);
     if (threadIdx.x == 0) {
         const float v0 = look.bin[0] < 0 ? 0.f : (float)(look.bin[0] - pedestal);
@@ -277,15 +277,15 @@ __device__ void percentile_finalize_all(const uint32_t* __restrict__ ghist, int 
 __global__ void __launch_bounds__(kHistThreads, 1)
 hist_percentile_kernel(const uint16_t* __restrict__ vol, size_t count, uint32_t* __restrict__ ghist, int pedestal,
                        int32_t* __restrict__ status, unsigned int* __restrict__ ticket, const int32_t* __restrict__ gate,
-                       int all_voxels) {
+                       int all_voxels, float q) {
     chain_release();
     chain_wait();
     if (gate && *gate == 0) return;
     extern __shared__ uint32_t sh[];
     hist_full_body(vol, count, ghist, sh);
     if (!is_last_block(ticket)) return;
-    if (all_voxels) percentile_finalize_all(ghist, pedestal, (unsigned long long)count, status);
-    else percentile_finalize(ghist, pedestal, status);
+    if (all_voxels) percentile_finalize_all(ghist, pedestal, (unsigned long long)count, status, q);
+    else percentile_finalize(ghist, pedestal, status, q);
 }
 
 // ---- step 1: value window from a sample ------------------------------------------------------------
@@ -300,7 +300,8 @@ constexpr int kCoarseBins = kHistBins >> kCoarseShift;      // 8192
 // gives the sample size, an exclusive scan and, once the rank interval is known, both of its ends.
 static_assert(kCoarseBins == kHistThreads * 8, "window_select keeps eight coarse bins per thread");
 
-__device__ void window_select(const uint32_t* __restrict__ shist, int pedestal, int32_t* __restrict__ status) {
+__device__ void window_select(const uint32_t* __restrict__ shist, int pedestal, int32_t* __restrict__ status,
+                              double q) {
     __shared__ unsigned long long warp_tot[kHistThreads / 32];
     __shared__ int found[2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -330,8 +331,8 @@ __device__ void window_select(const uint32_t* __restrict__ shist, int pedestal, 
         }
         return;
     }
-    const double centre = 0.95 * (double)(ns - 1);
-    const double margin = 4.0 + 9.0 * sqrt((double)ns * 0.0475);
+    const double centre = q * (double)(ns - 1);
+    const double margin = 4.0 + 9.0 * sqrt((double)ns * q * (1.0 - q));
     const double lo_r = centre - margin, hi_r = centre + margin + 1.0;
     const unsigned long long ranks[2] = {lo_r < 0.0 ? 0ull : (unsigned long long)lo_r,
                                          hi_r > (double)(ns - 1) ? ns - 1 : (unsigned long long)hi_r};
@@ -368,7 +369,7 @@ __device__ void window_select(const uint32_t* __restrict__ shist, int pedestal, 
 __global__ void __launch_bounds__(kHistThreads, 1)
 sample_window_kernel(const uint16_t* __restrict__ vol, size_t count, uint32_t stride, int pedestal,
                      uint32_t* __restrict__ shist, int32_t* __restrict__ status, unsigned int* __restrict__ ticket,
-                     uint4* __restrict__ zero_ptr, size_t zero_vecs) {
+                     uint4* __restrict__ zero_ptr, size_t zero_vecs, double q) {
     chain_release();
     __shared__ uint32_t sh[kCoarseBins];
     for (int i = threadIdx.x; i < kCoarseBins; i += kHistThreads) sh[i] = 0;
@@ -408,7 +409,7 @@ sample_window_kernel(const uint16_t* __restrict__ vol, size_t count, uint32_t st
     for (int i = threadIdx.x; i < kCoarseBins; i += kHistThreads)
         if (sh[i]) atomicAdd(&shist[i], sh[i]);
     if (!is_last_block(ticket)) return;
-    window_select(shist, pedestal, status);
+    window_select(shist, pedestal, status, q);
 }
 
 // ---- step 2: streaming count pass -----------------------------------------------------------------
@@ -432,7 +433,7 @@ static_assert(kWinBins == kCountThreads * 8, "window_finalize keeps eight window
 // Eight window bins per thread stay in registers: one round of loads gives the window total, its share of the
 // clamp sum, an exclusive scan, and - once the counts below the window are known - both ranks.
 __device__ void window_finalize(const uint32_t* __restrict__ gwin, const unsigned long long* __restrict__ gcounters,
-                                unsigned long long count, int pedestal, int32_t* __restrict__ status) {
+                                unsigned long long count, int pedestal, int32_t* __restrict__ status, float q) {
     __shared__ unsigned long long warp_tot[kCountThreads / 32], warp_share[kCountThreads / 32];
     __shared__ int found[2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -474,7 +475,7 @@ __device__ void window_finalize(const uint32_t* __restrict__ gwin, const unsigne
     const unsigned long long above = sane ? (clamp_sum - share_all) >> k : 0;
     const bool ok = sane && in_window + above + zeros <= count;
     const unsigned long long below_nz = ok ? count - in_window - above - zeros : 0;
-    const RankPair rp = numpy_ranks(n);
+    const RankPair rp = numpy_ranks(n, q);
     const unsigned long long ranks[2] = {rp.prev, rp.next};
     const unsigned long long excl = below_nz + before + incl - mine;
 #pragma unroll
@@ -506,7 +507,7 @@ __device__ void window_finalize(const uint32_t* __restrict__ gwin, const unsigne
 __global__ void __launch_bounds__(kCountThreads, 2)
 window_count_kernel(const uint16_t* __restrict__ vol, size_t count, int pedestal, int32_t* __restrict__ status,
                     uint32_t* __restrict__ gwin, unsigned long long* __restrict__ gcounters,
-                    unsigned int* __restrict__ ticket) {
+                    unsigned int* __restrict__ ticket, float q) {
     chain_release();
     __shared__ uint32_t win[kWinBins];
     __shared__ uint4 queue[kQueueCap];
@@ -633,7 +634,7 @@ window_count_kernel(const uint16_t* __restrict__ vol, size_t count, int pedestal
     for (int i = threadIdx.x; i <= (int)wn && i < kWinBins; i += kCountThreads)
         if (win[i]) atomicAdd(&gwin[i], win[i]);
     if (!is_last_block(ticket)) return;
-    window_finalize(gwin, gcounters, (unsigned long long)count, pedestal, status);
+    window_finalize(gwin, gcounters, (unsigned long long)count, pedestal, status, q);
 }
 
 // ---- launchers ------------------------------------------------------------------------------------
@@ -661,7 +662,7 @@ static int hist_grid(tsp_handle* h, size_t count, uint32_t stride) {
 // Also clears the status block (kStatusWords words) and - for the next stage - zero_bytes at zero_ptr (16-byte
 // aligned, may be null).
 int launch_percentile(tsp_handle* h, const uint16_t* d_vol, size_t count, int pedestal, int32_t* d_status,
-                      void* d_scratch, cudaStream_t s, void* zero_ptr, size_t zero_bytes) {
+                      void* d_scratch, cudaStream_t s, void* zero_ptr, size_t zero_bytes, float q, double q64) {
     int rc = ensure_hist_attr(h);
     if (rc) return rc;
     uint32_t* hist_full = (uint32_t*)d_scratch;
@@ -685,21 +686,21 @@ int launch_percentile(tsp_handle* h, const uint16_t* d_vol, size_t count, int pe
     }
     if (stride == 1) {
         hist_percentile_kernel<<<hist_grid(h, count, 1), kHistThreads, kHistSmemBytes, s>>>(
-            d_vol, count, hist_full, pedestal, d_status, tickets, nullptr, 0);
+            d_vol, count, hist_full, pedestal, d_status, tickets, nullptr, 0, q);
         TSP_LAUNCH_CHECK(h);
         return TSP_OK;
     }
     TSP_CUDA(launch_chained(sample_window_kernel, hist_grid(h, count, stride), kHistThreads, 0, s, d_vol, count, stride,
-                            pedestal, hist_sample, d_status, tickets + 1, (uint4*)zero_ptr, zero_bytes / 16));
+                            pedestal, hist_sample, d_status, tickets + 1, (uint4*)zero_ptr, zero_bytes / 16, q64));
     TSP_LAUNCH_CHECK(h);
     prof_mark(h, s, STG_PCT_SAMPLE);
     TSP_CUDA(launch_chained(window_count_kernel, h->sm_count * 2, kCountThreads, 0, s, d_vol, count, pedestal, d_status,
-                            win, counters, tickets + 2));
+                            win, counters, tickets + 2, q));
     TSP_LAUNCH_CHECK(h);
     prof_mark(h, s, STG_PCT_COUNT);      // what follows (the gated fallback) is booked on the caller's STG_PERCENTILE
     // exact fallback, armed by ST_NEED_FULL (returns at once otherwise)
     TSP_CUDA(launch_chained(hist_percentile_kernel, hist_grid(h, count, 1), kHistThreads, kHistSmemBytes, s, d_vol, count,
-                            hist_full, pedestal, d_status, tickets, d_status + ST_NEED_FULL, 0));
+                            hist_full, pedestal, d_status, tickets, d_status + ST_NEED_FULL, 0, q));
     TSP_LAUNCH_CHECK(h);
     return TSP_OK;
 }
@@ -707,7 +708,7 @@ int launch_percentile(tsp_handle* h, const uint16_t* d_vol, size_t count, int pe
 // SP:46: np.percentile(channel, 95) over every voxel (after the pedestal), exact, by the full histogram.
 // d_status: a status block of its own (ST_P95_BITS / ST_HAS_NONZERO are what launch_prepare reads).
 int launch_percentile_all(tsp_handle* h, const uint16_t* d_vol, size_t count, int pedestal, int32_t* d_status,
-                          void* d_scratch, cudaStream_t s) {
+                          void* d_scratch, cudaStream_t s, float q) {
     int rc = ensure_hist_attr(h);
     if (rc) return rc;
     uint32_t* hist_full = (uint32_t*)d_scratch;
@@ -715,7 +716,7 @@ int launch_percentile_all(tsp_handle* h, const uint16_t* d_vol, size_t count, in
     TSP_CUDA(cudaMemsetAsync(d_status, 0, kStatusWords * sizeof(int32_t), s));
     TSP_CUDA(cudaMemsetAsync(d_scratch, 0, percentile_scratch_bytes(), s));
     hist_percentile_kernel<<<hist_grid(h, count, 1), kHistThreads, kHistSmemBytes, s>>>(
-        d_vol, count, hist_full, pedestal, d_status, tickets, nullptr, 1);
+        d_vol, count, hist_full, pedestal, d_status, tickets, nullptr, 1, q);
     TSP_LAUNCH_CHECK(h);
     return TSP_OK;
 }

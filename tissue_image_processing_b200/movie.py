@@ -1,22 +1,29 @@
-"""Frame-parallel movie projection (the loop of reference surface_projection.py:205-212).
+"""Frame-parallel projection of movies and tiled images (the loops of reference surface_projection.py:205-212 and
+:294-301).
 
-The reference projects the time points of a movie one after the other on one CPU core.  Time points
-are independent, so here they are
+The reference projects the time points of a movie (or the XY tiles of a large image) one after the other on one CPU
+core.  They are independent, so here they are
 
-  * pipelined on each GPU through the frame slots of the C ABI (``tsp_frame_submit`` /
-    ``tsp_frame_wait``): the pinned host->device copy of frame t+1 overlaps the kernels of frame t and
-    the device->host copy of frame t-1;
-  * partitioned over GPUs by time frame: ``devices=[0, 1, ...]`` runs one host thread per GPU in this
-    process (ctypes releases the GIL), and under ``torchrun`` (one process per GPU) each rank takes the
-    next unclaimed frame from a counter shared through the job's store (``SharedFrameCounter``) - the host
-    links of an 8-GPU box are not equally fast (measured: 23 and 36 GB/s per GPU with all eight copying), a
-    static split would wait for the slowest.  No collective runs on the data path; ranks only meet when the
-    driver assembles the output arrays (``gather_movie``).
+  * pipelined on each GPU through the frame slots of the C ABI (``tsp_frame_submit`` / ``tsp_frame_wait``): the
+    host->device copy of frame t+1 overlaps the kernels of frame t and the device->host copy of frame t-1.  Frames
+    that do not already live in pinned memory are first copied into a ring of pinned staging buffers (one per slot,
+    several host threads per copy), so every DMA is asynchronous whatever the reader returned;
+  * returned in the dtype the caller stores: float64 / int64 like the reference operator, or - ``out_dtype="uint16"``,
+    what the movie driver writes to disk (BIM:481, SP:229-231) - converted on the device, 4 instead of 16 bytes per
+    pixel over the host link;
+  * partitioned over GPUs by frame, dynamically: ``devices=[0, 1, ...]`` runs one host thread per GPU in this process
+    and every thread takes the next frame from one shared queue; under ``torchrun`` (one process per GPU) each rank
+    takes the next unclaimed frame from a counter shared through the job's store (``SharedFrameCounter``) - the host
+    links of an 8-GPU box are not equally fast (measured: 23 and 36 GB/s per GPU with all eight copying), a static
+    split would wait for the slowest.  No collective runs on the data path; ranks only meet when the driver assembles
+    the output arrays on rank 0 (``gather_frames``: point-to-point sends of the owned frames over a gloo group).
 """
 from __future__ import annotations
 
 import os
+import queue
 import threading
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -24,7 +31,7 @@ from . import _native
 
 
 def frame_owner(t, world_size):
-    """Rank (or device slot) that projects time point ``t``: round-robin."""
+    """Static round-robin owner of frame ``t`` (only used where no shared counter is available)."""
     return t % world_size
 
 
@@ -39,30 +46,73 @@ def rank_world():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
 
 
+def as_uint16_stack(stack):
+    """The dtypes the B200 path takes: uint16 as is, uint8 widened; anything else is refused (the reference converts
+    every dtype with ``astype('float32')``; silently wrapping int32 / float stacks into uint16 would corrupt them)."""
+    stack = np.asarray(stack)
+    if stack.dtype == np.uint16:
+        return stack
+    if stack.dtype == np.uint8:
+        return stack.astype(np.uint16)
+    raise TypeError("the B200 projection path takes uint8/uint16 stacks (got %s)" % stack.dtype)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# control plane of a multi-rank job
+# ----------------------------------------------------------------------------------------------------------------
+_store_lock = threading.Lock()
+_job_store = None
+
+
+def _job_kv_store():
+    """A key-value store shared by the ranks of the job: the rendezvous store torch.distributed already runs (reached
+    through c10d's accessor when this torch has it), else a TCPStore of our own next to the rendezvous port."""
+    global _job_store
+    import torch.distributed as dist
+    with _store_lock:
+        if _job_store is not None:
+            return _job_store
+        getter = getattr(dist.distributed_c10d, "_get_default_store", None)
+        store = None
+        if getter is not None:
+            try:
+                store = getter()
+            except Exception:                                 # noqa: BLE001
+                store = None
+        if store is None:
+            from datetime import timedelta
+            port = int(os.environ.get("TSP_STORE_PORT", int(os.environ.get("MASTER_PORT", "29500")) + 17))
+            store = dist.TCPStore(os.environ.get("MASTER_ADDR", "127.0.0.1"), port, dist.get_world_size(),
+                                  is_master=dist.get_rank() == 0, timeout=timedelta(seconds=300))
+        _job_store = dist.PrefixStore("tsp_b200", store)
+        return _job_store
+
+
 class SharedFrameCounter:
-    """Hands out 0, 1, 2, ... exactly once across the ranks of a torchrun job: an atomic add on the job's
-    key-value store (the rendezvous TCPStore - control plane, ~0.1 ms per claim, no tensor traffic).  A single
-    process counts locally.  Every rank must create its counters in the same program order (the key is a
-    sequence number)."""
+    """Hands out 0, 1, 2, ... exactly once across the ranks of a torchrun job: an atomic add on the job's key-value
+    store (control plane, ~0.1 ms per claim, no tensor traffic).  A single process counts locally.  Every rank must
+    create its counters in the same program order (the key is a sequence number)."""
 
     _created = 0
 
     def __init__(self, tag="frames"):
         SharedFrameCounter._created += 1
-        self.key = "tsp_b200/%s/%d" % (tag, SharedFrameCounter._created)
+        self.key = "%s/%d" % (tag, SharedFrameCounter._created)
         self.local = 0
         self.store = None
+        self._lock = threading.Lock()
         try:
             import torch.distributed as dist
             if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-                self.store = dist.distributed_c10d._get_default_store()
-        except (ImportError, AttributeError, RuntimeError):   # pragma: no cover
+                self.store = _job_kv_store()
+        except ImportError:                                   # pragma: no cover
             self.store = None
 
     def next(self):
         if self.store is None:
-            self.local += 1
-            return self.local - 1
+            with self._lock:
+                self.local += 1
+                return self.local - 1
         return int(self.store.add(self.key, 1)) - 1
 
     def claims(self, total):
@@ -74,29 +124,131 @@ class SharedFrameCounter:
             yield i
 
 
-def gather_movie(arrays, owner_of_frame=None, world_size=None):
-    """Combine per-rank partial movie arrays (axis 0 = time, frames a rank does not own are zero) onto every
-    rank.  Output assembly only - uses the CPU (gloo) group when one exists; a single process is a no-op."""
-    import torch
+_gloo_group = None
+
+
+def host_group():
+    """A process group that can move CPU tensors: the default group when it has a CPU backend (gloo), otherwise a
+    gloo group created next to it (collective: every rank must reach the first call).  None for a single process."""
+    global _gloo_group
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-        return arrays
-    for a in arrays:
-        t = torch.from_numpy(a)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return None
+    if _gloo_group is None:
+        backend = str(dist.get_backend()).lower()
+        _gloo_group = dist.group.WORLD if "gloo" in backend else dist.new_group(backend="gloo")
+    return _gloo_group
+
+
+def gather_frames(arrays, owned, dst=0, all_ranks=False):
+    """Assemble the frames each rank projected.  ``arrays``: per-rank arrays with axis 0 = frame; ``owned``: the
+    frame indices this rank filled in.  Only owned frames travel: every rank sends them to ``dst`` point to point
+    (gloo); with ``all_ranks`` the assembled arrays are broadcast back.  Returns True on the ranks that hold the
+    complete arrays afterwards.  Output assembly only - nothing here is on the projection data path."""
+    import torch
+    import torch.distributed as dist
+    group = host_group()
+    if group is None:
+        return True
+    rank, world = dist.get_rank(), dist.get_world_size()
+    idx = torch.tensor(sorted(int(t) for t in owned), dtype=torch.int64)
+    counts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(counts, torch.tensor([idx.numel()], dtype=torch.int64), group=group)
+    if rank == dst:
+        for src in range(world):
+            n = int(counts[src].item())
+            if src == dst or n == 0:
+                continue
+            their = torch.empty(n, dtype=torch.int64)
+            dist.recv(their, src=src, group=group)
+            for a in arrays:
+                buf = torch.empty((n,) + tuple(a.shape[1:]), dtype=torch.from_numpy(a[:0]).dtype)
+                dist.recv(buf, src=src, group=group)
+                a[their.numpy()] = buf.numpy()
+    elif idx.numel() > 0:
+        dist.send(idx, dst=dst, group=group)
+        for a in arrays:
+            dist.send(torch.from_numpy(np.ascontiguousarray(a[idx.numpy()])), dst=dst, group=group)
+    if all_ranks:
+        for a in arrays:
+            t = torch.from_numpy(a) if a.flags.c_contiguous else None
+            if t is None:
+                raise ValueError("gather_frames(all_ranks=True) needs C-contiguous arrays")
+            dist.broadcast(t, src=dst, group=group)
+        return True
+    return rank == dst
+
+
+def gather_movie(arrays, owned=None, all_ranks=True):
+    """Backwards-compatible name: assemble per-rank movie arrays on every rank (``owned`` = the time points this rank
+    projected; None = every frame that is non-zero here)."""
+    if owned is None:
+        owned = [t for t in range(arrays[0].shape[0]) if np.any(arrays[0][t])]
+    gather_frames(arrays, owned, all_ranks=all_ranks)
     return arrays
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the pipeline
+# ----------------------------------------------------------------------------------------------------------------
+class _Staging:
+    """Pinned staging buffers of one GPU worker (one per frame slot, reallocated when the frame shape changes) and
+    the host threads that fill them."""
+
+    def __init__(self, slots, copy_threads):
+        self.bufs = [None] * slots
+        self.pool = ThreadPoolExecutor(max_workers=copy_threads) if copy_threads > 1 else None
+        self.copy_threads = copy_threads
+
+    def close(self):
+        if self.pool is not None:
+            self.pool.shutdown(wait=True)
+
+    @staticmethod
+    def is_pinned(arr):
+        import torch
+        try:
+            return arr.flags.c_contiguous and torch.from_numpy(arr).is_pinned()
+        except (TypeError, ValueError, RuntimeError):
+            return False
+
+    def stage(self, slot, stack):
+        """-> C-contiguous uint16 (C,Z,Y,X) array in pinned memory holding ``stack`` (itself when already pinned)."""
+        stack = as_uint16_stack(stack)
+        if stack.ndim != 4:
+            raise RuntimeError("sequence argument must have length equal to input rank")
+        if self.is_pinned(stack):
+            return stack
+        buf = self.bufs[slot]
+        if buf is None or buf.shape != stack.shape:
+            buf = self.bufs[slot] = _native.pinned_empty(stack.shape, np.uint16)
+        n = stack.shape[0] * stack.shape[1]
+        if self.pool is None or stack.nbytes < (8 << 20) or n < 2:
+            np.copyto(buf, stack)
+        else:                                      # plane ranges in parallel: numpy releases the GIL while it copies
+            src = stack.reshape((n,) + stack.shape[2:])
+            dst = buf.reshape((n,) + stack.shape[2:])
+            parts = min(self.copy_threads, n)
+            cuts = [n * k // parts for k in range(parts + 1)]
+            list(self.pool.map(lambda k: np.copyto(dst[cuts[k]:cuts[k + 1]], src[cuts[k]:cuts[k + 1]]), range(parts)))
+        return buf
 
 
 class FramePipeline:
     """Projects a sequence of frames on one or several GPUs of this process.
 
+    ``out_dtype``: "reference" (float64 projection, int64 height map - what the operator returns) or "uint16" (both
+    uint16, converted on the device - what the movie driver stores).
     ``operator`` is only a seam for host-side tests (it replaces the GPU call by a Python callable with the
     signature of ``time_point_surface_projection``); the product path is the C ABI.
     """
 
-    def __init__(self, devices=None, slots=2, mode=None, operator=None):
+    def __init__(self, devices=None, slots=2, mode=None, operator=None, out_dtype="reference", copy_threads=None):
+        if out_dtype not in ("reference", "uint16"):
+            raise ValueError("out_dtype must be 'reference' or 'uint16'")
         self.operator = operator
         self.mode = mode
+        self.out_dtype = out_dtype
         if operator is None:
             import torch
             if not torch.cuda.is_available():
@@ -105,11 +257,13 @@ class FramePipeline:
                 devices = [torch.cuda.current_device()]
         self.devices = list(devices) if devices is not None else [0]
         self.slots = max(1, min(int(slots), _native.MAX_SLOTS))
+        if copy_threads is None:
+            copy_threads = max(1, min(8, len(os.sched_getaffinity(0)) // max(1, len(self.devices))))
+        self.copy_threads = int(copy_threads)
+        self.h2d_bytes = 0                       # bytes handed to the GPUs so far (bench.py reports GB/s from it)
 
     # ---- one GPU: slot pipeline -------------------------------------------------------------------
-    def _run_device(self, device, frames, params, sink):
-        """frames: iterable of (t, stack) with stack a C-contiguous uint16 (C,Z,Y,X) host array (pinned memory
-        makes the copies asynchronous).  sink(t, proj float64 (C,Y,X), zmap int64 (Y,X), status)."""
+    def _operator_kwargs(self, params, device):
         mode = self.mode or params.get("mode") or os.environ.get("TSP_MODE", "fast")
         kw = dict(reference_channel=int(params.get("reference_channel", 0)), min_z=int(params.get("min_z", 0)),
                   max_z=int(params.get("max_z", 0)), airyscan=bool(params.get("airyscan", True)),
@@ -121,28 +275,41 @@ class FramePipeline:
             kw.update(bin_size=bin_size, method=params["method"])
         if params.get("build_manifold", False):
             kw.update(build_manifold=True)
-        inflight = [None] * self.slots          # (t, stack, proj, zmap) per slot
+        extra = {k: params[k] for k in _native.PARAM_KEYS if params.get(k) is not None}
+        if extra:
+            kw.update(params=extra)
+        return kw
+
+    def _run_device(self, device, frames, params, sink):
+        """frames: iterable of (key, stack) with stack a uint8/uint16 (C,Z,Y,X) host array.
+        sink(key, proj (C,Y,X), zmap (Y,X), status)."""
+        kw = self._operator_kwargs(params, device)
+        pdt, zdt = (np.uint16, np.uint16) if self.out_dtype == "uint16" else (np.float64, np.int64)
+        inflight = [None] * self.slots          # (key, pinned stack, proj, zmap) per slot
         bufs = [None] * self.slots              # pinned output buffers per slot, reused while the shape holds
+        staging = _Staging(self.slots, self.copy_threads)
 
         def drain(slot):
             if inflight[slot] is None:
                 return
-            t, stack, proj, zmap = inflight[slot]
+            key, _, proj, zmap = inflight[slot]
             status = _native.frame_wait(slot, device)
             inflight[slot] = None
-            sink(t, proj, zmap, status)
+            sink(key, proj, zmap, status)
 
         i = 0
         try:
-            for t, stack in frames:
+            for key, stack in frames:
                 slot = i % self.slots
                 drain(slot)
-                Cn, _, Y, X = stack.shape
+                pinned = staging.stage(slot, stack)
+                Cn, _, Y, X = pinned.shape
                 if bufs[slot] is None or bufs[slot][0].shape != (Cn, Y, X):
-                    bufs[slot] = (_native.pinned_empty((Cn, Y, X), np.float64), _native.pinned_empty((Y, X), np.int64))
+                    bufs[slot] = (_native.pinned_empty((Cn, Y, X), pdt), _native.pinned_empty((Y, X), zdt))
                 proj, zmap = bufs[slot]
-                _native.frame_submit(slot, stack, proj, zmap, **kw)
-                inflight[slot] = (t, stack, proj, zmap)
+                _native.frame_submit(slot, pinned, proj, zmap, **kw)
+                self.h2d_bytes += pinned.nbytes
+                inflight[slot] = (key, pinned, proj, zmap)
                 i += 1
             for k in range(self.slots):
                 drain((i + k) % self.slots)
@@ -154,24 +321,30 @@ class FramePipeline:
                     except Exception:                # noqa: BLE001
                         pass
                     inflight[slot] = None
+            staging.close()
 
     # ---- public ------------------------------------------------------------------------------------
     def project_frames(self, frames, sink, **params):
-        """Project ``frames`` (iterable of (t, stack)) and call ``sink(t, proj, zmap, status)`` for each.  The arrays
-        handed to ``sink`` are reused for later frames: copy what must be kept.  With several devices the
-        frames are dealt round-robin to one worker thread per GPU; ``sink`` is then called under a lock."""
+        """Project ``frames`` (iterable of (key, stack)) and call ``sink(key, proj, zmap, status)`` for each.  The
+        arrays handed to ``sink`` are reused for later frames: copy what must be kept.  With several devices one
+        worker thread per GPU takes the next frame from a shared queue (a GPU on a faster host link takes more);
+        ``sink`` is then called under a lock."""
         if self.operator is not None:
-            for t, stack in frames:
+            skip = ("mode", "axes", "z_map") + _native.PARAM_KEYS
+            for key, stack in frames:
+                stack = as_uint16_stack(stack)
                 proj, zmap = self.operator(stack[None], axes="TCZYX", z_map=True,
-                                           **{k: v for k, v in params.items() if k not in ("mode", "axes", "z_map")})
-                sink(t, np.asarray(proj, dtype=np.float64), np.asarray(zmap, dtype=np.int64), {})
+                                           **{k: v for k, v in params.items() if k not in skip})
+                if self.out_dtype == "uint16":
+                    sink(key, np.asarray(proj).astype(np.uint16), np.asarray(zmap).astype(np.uint16), {})
+                else:
+                    sink(key, np.asarray(proj, dtype=np.float64), np.asarray(zmap, dtype=np.int64), {})
             return
         if len(self.devices) == 1:
             self._run_device(self.devices[0], frames, params, sink)
             return
-        import queue
         lock = threading.Lock()
-        queues = [queue.Queue(maxsize=2 * self.slots) for _ in self.devices]
+        work = queue.Queue(maxsize=2 * self.slots * len(self.devices))
         errors = []
 
         def locked_sink(*a):
@@ -182,8 +355,8 @@ class FramePipeline:
             _native.bind_host_thread_to_gpu(self.devices[k])      # staging buffers next to the worker's GPU
 
             def gen():
-                while True:
-                    item = queues[k].get()
+                while not errors:
+                    item = work.get()
                     if item is None:
                         return
                     yield item
@@ -191,26 +364,36 @@ class FramePipeline:
                 self._run_device(self.devices[k], gen(), params, locked_sink)
             except Exception as exc:                 # noqa: BLE001
                 errors.append(exc)
-                while queues[k].get() is not None:   # keep the feeder from blocking
-                    pass
 
         threads = [threading.Thread(target=worker, args=(k,), daemon=True) for k in range(len(self.devices))]
         for th in threads:
             th.start()
-        for i, item in enumerate(frames):
-            queues[frame_owner(i, len(self.devices))].put(item)
-        for q in queues:
-            q.put(None)
+
+        def put(item):                               # never blocks on a queue nobody reads any more
+            while any(th.is_alive() for th in threads):
+                try:
+                    work.put(item, timeout=0.2)
+                    return True
+                except queue.Full:
+                    pass
+            return False
+
+        for item in frames:
+            if errors or not put(item):
+                break
+        for _ in threads:
+            put(None)
         for th in threads:
             th.join()
         if errors:
             raise errors[0]
 
-    def project_movie(self, path, series, out_projection, out_zmap, mode=None, **params):
-        """Driver hook used by ``movie_surface_projection``: read the time points of ``path`` (through the
-        ``basic_image_manipulations.open_image`` hook), project the ones this rank claims (shared counter:
-        every time point exactly once across the ranks, faster ranks take more) and scatter them into the
-        (T,C,1,Y,X) / (T,1,1,Y,X) arrays of SP:201-202."""
+    def project_movie(self, path, series, out_projection, out_zmap, mode=None, gather="all", **params):
+        """Project the time points of ``path`` / ``series`` (read through the ``basic_image_manipulations.open_image``
+        hook) that this rank claims (shared counter: every time point exactly once across the ranks, faster ranks
+        take more) and scatter them into ``out_projection`` (T,C,1,Y,X) / ``out_zmap`` (T,1,1,Y,X) - the arrays of
+        SP:201-202, in whatever dtype the caller allocated.  ``gather``: "all" assembles the arrays on every rank,
+        "root" on rank 0 only, None leaves each rank with its own frames.  Returns the time points projected here."""
         from . import basic_image_manipulations as bim
         img = bim.open_image(path)
         img.set_scene(series)
@@ -221,17 +404,18 @@ class FramePipeline:
             params = dict(params, mode=mode)
         for k in ("axes", "z_map"):
             params.pop(k, None)
+        owned = []
 
         def frames():
             for t in counter.claims(T):
-                chunk = np.asarray(data[t:t + 1].compute())[0]          # (C, Z, Y, X)
-                if chunk.dtype != np.uint16:
-                    chunk = chunk.astype(np.uint16)
-                yield t, np.ascontiguousarray(chunk)
+                yield t, np.asarray(data[t:t + 1].compute())[0]          # (C, Z, Y, X)
 
         def sink(t, proj, zmap, status):
             out_projection[t, :, 0] = proj
             out_zmap[t, 0, 0] = zmap
+            owned.append(t)
 
         self.project_frames(frames(), sink, **params)
-        gather_movie([out_projection, out_zmap])
+        if gather:
+            gather_frames([out_projection, out_zmap], owned, all_ranks=(gather == "all"))
+        return owned

@@ -3,17 +3,22 @@
 ``time_point_surface_projection`` keeps the reference signature (SP:17-19) and return dtypes
 (float64 projection, int64 height map) and runs the whole operator on the GPU through the C ABI
 (``tsp_project_frame_host``).  The drivers ``movie_surface_projection`` (SP:168-237) and
-``large_image_projection`` (SP:279-316) keep their signatures, resume files and dtype
-conventions; file I/O goes through the hooks of ``basic_image_manipulations`` (the reference's
-Bio-Formats stack is out of scope).
+``large_image_projection`` (SP:279-316) keep their signatures, file names, resume files and dtype
+conventions, but are built around ``movie.FramePipeline``: a frame source (time points of a movie file, XY tiles
+of a large image) feeds the GPU frame slots through pinned staging buffers, the results come back in the dtype
+that is written to disk (uint16 converted on the device for movies).  File I/O goes through the hooks of
+``basic_image_manipulations`` (the reference's Bio-Formats stack is out of scope).
 
 ``bin_size > 1`` (SP:39-53, methods max_averages / max_std / multi_channel) and ``build_manifold`` (SP:87-165)
 run on the GPU too; they use the direct-FIR score (``mode="fast"`` behaves like "exact" for them).
 
-Extension (keyword-only, defaults preserve reference behaviour): ``mode`` selects the score
-stage - "fast" (default, multirate sigma=30 stage), "exact" (direct FIR, fp32) or "bitexact"
-(direct FIR, scipy's float64 summation order; bit-identical height map and projection).
-The default can also be set with the environment variable TSP_MODE.
+Extensions (keyword-only, defaults preserve reference behaviour):
+  ``mode``        score stage: "fast" (default, multirate sigma=30 stage), "exact" (direct FIR, fp32) or "bitexact"
+                  (direct FIR, scipy's float64 summation order; bit-identical height map and projection).  The
+                  default can also be set with the environment variable TSP_MODE.
+  ``percentile``, ``pedestal``, ``sigma_pre``, ``sigma_score``, ``sigma_mask``
+                  the constants the reference hard-codes at SP:35, SP:28, SP:37, SP:55 and SP:70-71 (95, 10000,
+                  (0.5,1,1), (0.5,30,30), (1,2,2)); e.g. ``sigma_mask=(3, 2, 2)`` projects a wider z band.
 """
 from __future__ import annotations
 
@@ -24,22 +29,20 @@ import numpy as np
 
 from . import _native
 from . import basic_image_manipulations as bim
-from .basic_image_manipulations import put_channel_axis_first, read_image_in_chunks
+from .basic_image_manipulations import put_channel_axis_first, read_image_in_chunks  # noqa: F401
+from .movie import as_uint16_stack, rank_world
 
 DEFAULT_MODE = os.environ.get("TSP_MODE", "fast")
 
 
 def _as_uint16_stack(image):
-    if image.dtype == np.uint16:
-        return np.ascontiguousarray(image)
-    if image.dtype == np.uint8:
-        return np.ascontiguousarray(image.astype(np.uint16))
-    raise TypeError("the B200 projection path takes uint8/uint16 stacks (got %s)" % image.dtype)
+    return np.ascontiguousarray(as_uint16_stack(image))
 
 
 def time_point_surface_projection(time_point, axes, reference_channel, min_z=0, max_z=0,
                                   method='max_averages', bin_size=1, airyscan=True, z_map=False, atoh_shift=0,
-                                  build_manifold=False, *, mode=None, device=None):
+                                  build_manifold=False, *, mode=None, device=None, percentile=None, pedestal=None,
+                                  sigma_pre=None, sigma_score=None, sigma_mask=None):
     """SP:17-85.  See SURVEY.md section 3.3 for the behavioural spec this reproduces, quirks
     included: airyscan defaults to True; ``min_z`` is added to the height map even when
     ``max_z == 0``; the band is indexed with the un-cropped height (IndexError when it leaves the
@@ -58,12 +61,16 @@ def time_point_surface_projection(time_point, axes, reference_channel, min_z=0, 
         raise RuntimeError("sequence argument must have length equal to input rank")
     if bin_size > 1 and method not in _native.METHODS:
         raise TypeError("exceptions must derive from BaseException")      # SP:53 raises a str
+    if percentile is not None and not 0 <= percentile <= 100:
+        raise ValueError("Percentiles must be in the range [0, 100]")     # what np.percentile raises at SP:35
     stack = _as_uint16_stack(image)
+    params = dict(percentile=percentile, pedestal=pedestal, sigma_pre=sigma_pre, sigma_score=sigma_score,
+                  sigma_mask=sigma_mask)
     proj, zmap, _ = _native.project_frame_host(stack, int(reference_channel), int(min_z), int(max_z),
                                                bool(airyscan), int(atoh_shift), mode or DEFAULT_MODE, device,
                                                bin_size=int(bin_size) if bin_size > 1 else 1,
                                                method=method if bin_size > 1 else "max_averages",
-                                               build_manifold=bool(build_manifold))
+                                               build_manifold=bool(build_manifold), params=params)
     if axes_wo_t.find("C") < 0:                         # unreachable in the reference (see above)
         proj = proj[0]
     if z_map:
@@ -73,33 +80,26 @@ def time_point_surface_projection(time_point, axes, reference_channel, min_z=0, 
 
 def build_continues_manifold(score):
     """SP:87-128 on the GPU: score (Z, Y, X) float32 -> int64 height map grown outwards from the global score
-    maximum (``tsp_build_manifold``; at most 254 planes)."""
+    maximum (``tsp_build_manifold``; at most 254 planes).  The per-pixel rule of SP:130-165 (find_pixel_plane) only
+    exists fused inside that kernel."""
     return _native.build_manifold(np.ascontiguousarray(score, dtype=np.float32))
 
 
-def find_pixel_plane(score, chozen_z, pixel_row, pixel_col, max_row, max_col, max_plane):
-    raise NotImplementedError("find_pixel_plane (SP:130-165) is only available fused inside build_continues_manifold "
-                              "on the B200 path")
-
-
 # ------------------------------------------------------------------------------------------------
-# drivers
+# on-disk conventions
 # ------------------------------------------------------------------------------------------------
 def concatenate_time_points(files):
-    """BIM:478-495 without the resize branch: load per-movie arrays, truncate to uint16, pad the
-    channel axis at the front when a later movie has fewer channels, concatenate along T."""
-    imgs = []
-    for file in files:
-        img = np.load(file).astype("uint16")
-        if imgs:
-            for dim in range(1, img.ndim - 2):
-                missing = imgs[0].shape[dim] - img.shape[dim]
-                if missing > 0:
-                    pad = [(0, 0)] * img.ndim
-                    pad[dim] = (missing, 0)
-                    img = np.pad(img, pad_width=pad, constant_values=0)
-        imgs.append(img)
-    return np.concatenate(imgs, axis=0)
+    """What BIM:478-495 does to the per-movie arrays of one position (without its resize branch): every array is
+    cast to uint16 (truncation), later movies that lost channels get zero channels in FRONT, then all are joined
+    along time."""
+    movies = [np.load(f).astype("uint16") for f in files]
+    lead = movies[0].shape
+    for k in range(1, len(movies)):
+        m = movies[k]
+        grow = [(max(lead[d] - m.shape[d], 0), 0) if 1 <= d < m.ndim - 2 else (0, 0) for d in range(m.ndim)]
+        if any(g[0] for g in grow):
+            movies[k] = np.pad(m, grow, constant_values=0)
+    return np.concatenate(movies, axis=0)
 
 
 def save_tiff(path, image, metadata=None, axes="", data_type=""):
@@ -123,165 +123,223 @@ tiff_writer = _default_tiff_writer        # replaceable hook: callable(path, ima
 
 
 def update_projection_metadata(metadata, frames_number, series=0):
-    """SP:319-327."""
-    metadata.images = [metadata.images[series]]
-    metadata.images[0].name = 'position%d' % series
-    metadata.images[0].pixels.dimension_order = 'XYCTZ'
-    metadata.images[0].pixels.size_z = 1
-    metadata.images[0].pixels.size_t = frames_number
-    metadata.images[0].pixels.type = 'uint16'
-    metadata.images[0].pixels.planes = metadata.images[0].pixels.planes[:metadata.images[0].pixels.size_c]
+    """SP:319-327: the OME metadata of one projected position - a single image named after the position, one
+    plane per channel, ``frames_number`` time points, uint16, XYCTZ."""
+    image = metadata.images[series]
+    pixels = image.pixels
+    metadata.images = [image]
+    image.name = 'position%d' % series
+    for field, value in (("dimension_order", 'XYCTZ'), ("size_z", 1), ("size_t", frames_number), ("type", 'uint16')):
+        setattr(pixels, field, value)
+    pixels.planes = pixels.planes[:pixels.size_c]
     return metadata
+
+
+def movie_schedule(n_files, position_final_movie, n_positions):
+    """The bookkeeping of SP:181-221 / SP:240-262 as data: yields (file index, series index inside that file,
+    position).  A position whose final movie is ``f`` is absent from the files after ``f``, and the series of a file
+    number the positions still alive, in order."""
+    alive = list(range(n_positions))
+    for f in range(n_files):
+        for series, position in enumerate(alive):
+            yield f, series, position
+        alive = [p for p in alive if position_final_movie[p] != f + 1]
+
+
+_STAGE_SCALARS = ("x_unit", "y_unit", "z_unit")
+_PIXEL_SCALARS = ("physical_size_x", "physical_size_y", "physical_size_z")
 
 
 def save_stage_positions(files, position_final_movie, initial_positions_number, output_dir, only_position=0,
                          output_name=""):
-    """SP:240-276: per-position stage coordinates, one entry per time point, pickled."""
-    positions = list(range(initial_positions_number))
-    meta = bim.get_image_metadata(files[0])
+    """SP:240-276: ``stage_locations_position%d.pkl`` per position - the stage x / y / z of every time point (one
+    entry per frame, movie after movie), their units and the physical pixel sizes of the first movie."""
+    wanted = [p for p in range(initial_positions_number) if only_position <= 0 or p == only_position - 1]
+    tracks = {}
+    first = bim.get_image_metadata(files[0])
+    for p in range(initial_positions_number):              # units and pixel sizes: first movie, series = position
+        im = first.images[p]
+        rec = {axis: [] for axis in "xyz"}
+        rec.update({k: getattr(im.stage_label, k) for k in _STAGE_SCALARS})
+        rec.update({k: getattr(im.pixels, k) for k in _PIXEL_SCALARS})
+        tracks[p] = rec
+    per_file = {0: first}
+    for f, series, p in movie_schedule(len(files), position_final_movie, initial_positions_number):
+        if f > 0 and p not in wanted:
+            continue                                       # SP:259-260 skips other positions only after the first movie
+        if f not in per_file:
+            per_file[f] = bim.get_image_metadata(files[f])
+        im = per_file[f].images[series]
+        for axis in "xyz":
+            tracks[p][axis].extend([getattr(im.stage_label, axis)] * im.pixels.size_t)
+    for p in wanted:
+        with open(os.path.join(output_dir, output_name + "stage_locations_position%d.pkl" % (p + 1)), 'wb') as f:
+            pickle.dump(tracks[p], f)
 
-    def entry(im):
-        n = im.pixels.size_t
-        return {"x": [im.stage_label.x] * n, "y": [im.stage_label.y] * n, "z": [im.stage_label.z] * n,
-                "x_unit": im.stage_label.x_unit, "y_unit": im.stage_label.y_unit,
-                "z_unit": im.stage_label.z_unit, "physical_size_x": im.pixels.physical_size_x,
-                "physical_size_y": im.pixels.physical_size_y, "physical_size_z": im.pixels.physical_size_z}
 
-    stage_pos = [entry(meta.images[i]) for i in range(initial_positions_number)]
-    for position in range(initial_positions_number):
-        if position_final_movie[position] == 1:
-            positions.remove(position)
-    for file_index in range(1, len(files)):
-        meta = bim.get_image_metadata(files[file_index])
-        done = []
-        for position_index, position in enumerate(positions):
-            if position_final_movie[position] == file_index + 1:
-                done.append(position)
-            if only_position > 0 and position != only_position - 1:
-                continue
-            im = meta.images[position_index]
-            for k in "xyz":
-                stage_pos[position][k].extend([getattr(im.stage_label, k)] * im.pixels.size_t)
-        for p in done:
-            positions.remove(p)
-    for i in range(initial_positions_number):
-        if only_position > 0 and i != only_position - 1:
-            continue
-        with open(os.path.join(output_dir, output_name + "stage_locations_position%d.pkl" % (i + 1)), 'wb') as f:
-            pickle.dump(stage_pos[i], f)
+# ------------------------------------------------------------------------------------------------
+# drivers
+# ------------------------------------------------------------------------------------------------
+def _default_pipeline(mode, out_dtype):
+    from .movie import FramePipeline
+    return FramePipeline(mode=mode, out_dtype=out_dtype)
+
+
+def _job_barrier():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            from .movie import host_group
+            dist.barrier(group=host_group())
+    except ImportError:                                   # pragma: no cover
+        pass
 
 
 def movie_surface_projection(files, reference_channel, position_final_movie, initial_positions_number, output_dir,
                              method, bin_size, build_manifold, only_position, zmin, zmax, airyscan,
                              output_name="", *, mode=None, frame_pipeline=None):
-    """SP:168-237.  Per (file, position): project every time point (frames are independent; with
-    ``frame_pipeline`` - see ``movie.FramePipeline`` - they are spread over the GPUs of the box),
-    store per-movie .npy resume files, then per position concatenate (uint16 truncation), save the
-    OME-TIFF / ``zmap_position%d.npy`` / stage pickle and delete the resume files."""
-    positions = list(range(initial_positions_number))
-    time_points_number = np.zeros((initial_positions_number, len(files)))
-    projection_files = [[] for _ in range(initial_positions_number)]
-    zmap_files = [[] for _ in range(initial_positions_number)]
-    for file_num, file in enumerate(files):
-        remove_positions = []
-        dims = bim.get_image_dimensions(file)
-        for position_num, position in enumerate(positions):
-            if position_final_movie[position] == file_num + 1:
-                remove_positions.append(position)
-            if only_position > 0 and position != only_position - 1:
-                continue
-            projection_path = os.path.join(output_dir, "position%d_movie%d_projection.npy" % (position, file_num))
-            zmap_path = os.path.join(output_dir, "position%d_movie%d_zmap.npy" % (position, file_num))
-            projection_files[position].append(projection_path)
-            zmap_files[position].append(zmap_path)
-            print("Projecting position %d, movie %d" % (position + 1, file_num + 1))
-            time_points_number[position, file_num] = dims.T
-            if os.path.isfile(projection_path) and os.path.isfile(zmap_path):
-                continue                                                   # resume (SP:199-200)
-            current_projection = np.zeros((dims.T, dims.C, 1, dims.Y, dims.X))
-            current_zmap = np.zeros((dims.T, 1, 1, dims.Y, dims.X))
-            if reference_channel >= dims.C:
-                reference_channel = dims.C - 1
-            params = dict(axes='TCZYX', reference_channel=reference_channel, z_map=True, method=method,
-                          bin_size=bin_size, atoh_shift=0, build_manifold=build_manifold, min_z=zmin,
-                          max_z=zmax, airyscan=airyscan)
-            if frame_pipeline is not None:
-                frame_pipeline.project_movie(file, position_num, current_projection, current_zmap,
-                                             mode=mode, **params)
-            else:
-                projector = read_image_in_chunks(file, series=position_num, dt=1,
-                                                 apply_function=_operator_with_mode(mode),
-                                                 output=[current_projection, current_zmap], **params)
-                for time_point_index, _ in enumerate(projector):
-                    print("Projecting timepoint %d" % (time_point_index + 1))
-            current_projection = current_projection.reshape((dims.T, dims.C, dims.Y, dims.X))
-            np.save(projection_path, current_projection)
-            np.save(zmap_path, current_zmap)
-        for to_delete in remove_positions:
-            positions.remove(to_delete)
-    for position in range(initial_positions_number):
-        if only_position > 0 and position != only_position - 1:
+    """SP:168-237.  Every (movie file, position) pair becomes one job: its time points stream through a
+    ``movie.FramePipeline`` (pinned staging, frame slots, uint16 conversion on the device; under torchrun the ranks
+    share the time points and rank 0 assembles them) into the resume files ``position%d_movie%d_{projection,zmap}.npy``
+    of SP:193-194.  When all jobs are done, rank 0 joins the movies of each position along time and writes
+    ``position%d.tif`` (uint16, TCYX), ``zmap_position%d.npy`` (uint16, (T,1,1,Y,X)) and the stage pickle, then deletes
+    the resume files.  A job whose two resume files exist is skipped (SP:199-200)."""
+    rank, world = rank_world()
+    root = rank == 0
+    pipeline = frame_pipeline if frame_pipeline is not None else _default_pipeline(mode, "uint16")
+    out_dtype = np.uint16 if pipeline.out_dtype == "uint16" else np.float64
+    chosen = [p for p in range(initial_positions_number) if only_position <= 0 or p == only_position - 1]
+    frames_of = {p: 0 for p in chosen}
+    resume = {p: ([], []) for p in range(initial_positions_number)}
+    dims_of = {}
+    for f, series, position in movie_schedule(len(files), position_final_movie, initial_positions_number):
+        if position not in chosen:
             continue
-        former_metadata = bim.get_image_metadata(files[0], series=position)
-        new_metadata = update_projection_metadata(former_metadata, np.sum(time_points_number[position, :]),
-                                                  series=position)
-        movie_projection = concatenate_time_points(projection_files[position])
-        save_tiff(os.path.join(output_dir, output_name + "position%d.tif" % (position + 1)), movie_projection,
-                  metadata=new_metadata, axes="TCYX", data_type="uint16")
-        movie_zmap = np.concatenate([np.load(f).astype("uint16") for f in zmap_files[position]], axis=0)
-        np.save(os.path.join(output_dir, output_name + "zmap_position%d.npy" % (position + 1)), movie_zmap)
-    save_stage_positions(files, position_final_movie, initial_positions_number, output_dir,
-                         only_position=only_position, output_name=output_name)
-    for position_files in projection_files + zmap_files:
-        for projection_file in position_files:
-            os.remove(projection_file)
+        if f not in dims_of:
+            dims_of[f] = bim.get_image_dimensions(files[f])
+        dims = dims_of[f]
+        stem = os.path.join(output_dir, "position%d_movie%d" % (position, f))
+        proj_path, zmap_path = stem + "_projection.npy", stem + "_zmap.npy"
+        resume[position][0].append(proj_path)
+        resume[position][1].append(zmap_path)
+        frames_of[position] += dims.T
+        if root:
+            print("Projecting position %d, movie %d" % (position + 1, f + 1))
+        done = os.path.isfile(proj_path) and os.path.isfile(zmap_path)
+        if world > 1:                                  # every rank must take the same branch: rank 0's view decides
+            done = _broadcast_flag(done)
+        if done:
+            continue
+        reference_channel = min(reference_channel, dims.C - 1)       # SP:203-204 (sticks for the later jobs too)
+        proj = np.zeros((dims.T, dims.C, 1, dims.Y, dims.X), dtype=out_dtype)
+        zmap = np.zeros((dims.T, 1, 1, dims.Y, dims.X), dtype=out_dtype)
+        pipeline.project_movie(files[f], series, proj, zmap, mode=mode, gather="root",
+                               reference_channel=reference_channel, method=method, bin_size=bin_size, atoh_shift=0,
+                               build_manifold=build_manifold, min_z=zmin, max_z=zmax, airyscan=airyscan)
+        if root:
+            np.save(proj_path, proj.reshape((dims.T, dims.C, dims.Y, dims.X)))
+            np.save(zmap_path, zmap)
+    if root:
+        for position in chosen:
+            proj_files, zmap_files = resume[position]
+            metadata = update_projection_metadata(bim.get_image_metadata(files[0], series=position),
+                                                  float(frames_of[position]), series=position)
+            save_tiff(os.path.join(output_dir, output_name + "position%d.tif" % (position + 1)),
+                      concatenate_time_points(proj_files), metadata=metadata, axes="TCYX", data_type="uint16")
+            np.save(os.path.join(output_dir, output_name + "zmap_position%d.npy" % (position + 1)),
+                    np.concatenate([np.load(z).astype("uint16") for z in zmap_files], axis=0))
+        save_stage_positions(files, position_final_movie, initial_positions_number, output_dir,
+                             only_position=only_position, output_name=output_name)
+        for proj_files, zmap_files in resume.values():
+            for path in proj_files + zmap_files:
+                os.remove(path)
+    _job_barrier()                                     # nobody returns before the outputs are on disk
 
 
-def _operator_with_mode(mode):
-    if mode is None:
-        return time_point_surface_projection
+def _broadcast_flag(flag):
+    import torch
+    import torch.distributed as dist
+    from .movie import host_group
+    t = torch.tensor([1 if flag else 0], dtype=torch.int64)
+    dist.broadcast(t, src=0, group=host_group())
+    return bool(t.item())
 
-    def op(chunk, **kw):
-        return time_point_surface_projection(chunk, mode=mode, **kw)
-    return op
+
+def _tiles(extent_y, extent_x, chunk):
+    step_y, step_x = (chunk or extent_y), (chunk or extent_x)
+    for y in range(0, extent_y, step_y):
+        for x in range(0, extent_x, step_x):
+            yield y, min(y + step_y, extent_y), x, min(x + step_x, extent_x)
 
 
 def large_image_projection(input_dir, output_dir, input_file_name, position=1, reference_channel=0, chunk_size=0,
                            bin_size=1, channels_shift=0, min_z=0, max_z=0, method="", build_manifold=False,
-                           airyscan=False, *, mode=None):
-    """SP:279-316: fixed-sample projection in independent (no halo) XY tiles of ``chunk_size``."""
-    if not hasattr(position, "__len__"):
-        position = [position]
-        add_pos = False
-    else:
-        add_pos = True
+                           airyscan=False, *, mode=None, frame_pipeline=None):
+    """SP:279-316: fixed-sample projection.  The image is cut into independent XY tiles of ``chunk_size`` (no halo,
+    every tile with its own percentile and edges - BIM:104-149 semantics) which stream through the frame pipeline like
+    the time points of a movie; the float64 results are assembled into ``<name>[_position%d]_projection.tif`` (rescaled
+    to the global maximum, uint16, BIM:183-186) and ``<name>[_position%d]_zmap.npy`` (float64 (T,Y,X))."""
+    many = hasattr(position, "__len__")
     path = os.path.join(input_dir, input_file_name)
     if not os.path.exists(path):
         return 0
+    rank, _ = rank_world()
+    pipeline = frame_pipeline if frame_pipeline is not None else _default_pipeline(mode, "reference")
+    if pipeline.out_dtype != "reference":
+        raise ValueError("large_image_projection rescales float64 results: the pipeline must return the reference dtypes")
     dims = bim.get_image_dimensions(path)
-    for pos in position:
+    postfix = '.' + input_file_name.split('.')[-1]
+    for pos in (position if many else [position]):
         projection = np.zeros((dims.T, dims.C, 1, dims.Y, dims.X))
         zmap = np.zeros((dims.T, 1, 1, dims.Y, dims.X))
-        projector = read_image_in_chunks(path, dx=chunk_size, dy=chunk_size, dt=1,
-                                         apply_function=_operator_with_mode(mode),
-                                         output=[projection, zmap], axes='TCZYX', min_z=min_z, max_z=max_z,
-                                         reference_channel=reference_channel, series=int(pos - 1), z_map=True,
-                                         method=method, bin_size=bin_size, atoh_shift=channels_shift,
-                                         build_manifold=build_manifold, airyscan=airyscan)
-        for chunk_num, _ in enumerate(projector):
-            print("Projecting position %d chunk %d" % (pos, chunk_num + 1), flush=True)
-        if dims.T > 1:
-            projection = projection.reshape((dims.T, dims.C, dims.Y, dims.X))
-        else:
-            projection = projection.reshape((dims.C, dims.Y, dims.X))
-        zmap = zmap.reshape((dims.T, dims.Y, dims.X))
-        postfix = '.' + input_file_name.split('.')[-1]
-        pos_addition = "_position%d" % pos if add_pos else ""
-        projection_file_name = os.path.join(output_dir,
-                                            input_file_name.replace(postfix, pos_addition + "_projection.tif"))
-        zmap_filename = os.path.join(output_dir, input_file_name.replace(postfix, pos_addition + "_zmap.npy"))
-        save_tiff(projection_file_name, projection, axes="TCYX" if dims.T > 1 else "CYX", data_type="uint16")
-        np.save(zmap_filename, zmap)
+        img = bim.open_image(path)
+        img.set_scene(int(pos - 1))
+        data = img.get_image_dask_data()
+        tiles = [(t,) + tile for t in range(dims.T) for tile in _tiles(dims.Y, dims.X, chunk_size)]
+        from .movie import SharedFrameCounter, gather_frames
+        counter = SharedFrameCounter("tiles")
+        mine = []
+
+        def source():
+            for k in counter.claims(len(tiles)):
+                t, y0, y1, x0, x1 = tiles[k]
+                yield k, np.asarray(data[t:t + 1, :, :, y0:y1, x0:x1].compute())[0]
+
+        def sink(k, proj, zm, status):
+            t, y0, y1, x0, x1 = tiles[k]
+            projection[t, :, 0, y0:y1, x0:x1] = proj
+            zmap[t, 0, 0, y0:y1, x0:x1] = zm
+            mine.append(k)
+            print("Projecting position %d chunk %d" % (pos, k + 1), flush=True)
+
+        pipeline.project_frames(source(), sink, mode=mode, reference_channel=reference_channel, min_z=min_z,
+                                max_z=max_z, method=method, bin_size=bin_size, atoh_shift=channels_shift,
+                                build_manifold=build_manifold, airyscan=airyscan)
+        if _multi_rank():
+            # tiles are scattered inside frames: ship whole arrays of the tiles' frames as a sum of disjoint parts
+            _merge_disjoint([projection, zmap])
+        if rank == 0:
+            tag = "_position%d" % pos if many else ""
+            out_proj = projection.reshape((dims.T, dims.C, dims.Y, dims.X) if dims.T > 1 else (dims.C, dims.Y, dims.X))
+            save_tiff(os.path.join(output_dir, input_file_name.replace(postfix, tag + "_projection.tif")), out_proj,
+                      axes="TCYX" if dims.T > 1 else "CYX", data_type="uint16")
+            np.save(os.path.join(output_dir, input_file_name.replace(postfix, tag + "_zmap.npy")),
+                    zmap.reshape((dims.T, dims.Y, dims.X)))
+    _job_barrier()
+
+
+def _multi_rank():
+    return rank_world()[1] > 1
+
+
+def _merge_disjoint(arrays):
+    """Tiles of one frame may have been projected by different ranks: every pixel was written by exactly one rank
+    (zero elsewhere), so a sum over the ranks onto rank 0 assembles the frame (gloo group, output assembly only)."""
+    import torch
+    import torch.distributed as dist
+    from .movie import host_group
+    for a in arrays:
+        dist.reduce(torch.from_numpy(a), dst=0, op=dist.ReduceOp.SUM, group=host_group())
 
 
 # ------------------------------------------------------------------------------------------------

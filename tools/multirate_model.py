@@ -1,5 +1,7 @@
-"""Host-side filter tables for the ``fast`` focus-score stage (own design; the reference
-evaluates surface_projection.py:37 + :55 as two full-rate scipy Gaussian blurs).
+"""numpy model of the ``fast`` focus-score stage (own design; the reference evaluates
+surface_projection.py:37 + :55 as two full-rate scipy Gaussian blurs).  Design and validation tool only: the library
+builds its tables in C++ (csrc/fast.cu); tests/test_multirate_design.py ties the two together (same coarse taps to
+1e-15, operator error of the factorisation within the stated bound).
 
 Along one in-plane axis of length N the reference applies ``H30c @ H1c`` (sigma=1 then sigma=30,
 both edge-replicated, truncated at 4 sigma and renormalised).  The fast path factors it as
@@ -13,7 +15,7 @@ both edge-replicated, truncated at 4 sigma and renormalised).  The fast path fac
     (including its renormalisation) for all 8 output phases;
   * along z the two sigma=0.5 passes are one exact banded Z x Z matrix.
 
-Everything is float64 numpy on tiny 1-D problems; the tables are uploaded once per shape.
+Everything is float64 numpy on tiny 1-D problems.
 """
 from __future__ import annotations
 
