@@ -186,3 +186,36 @@ def test_cli_flags_and_dispatch(monkeypatch, tmp_path):
     sp.main(["-i", d, "--separate-files", "--only-position", "1"])
     kind, a, k = calls.pop()
     assert kind == "movie" and a[0] == [os.path.join(d, "a.czi")] and a[2] == (1,) and k["output_name"] == "a.czi"
+
+
+def test_rank_to_device_order_interleaves_link_groups():
+    """topology.interleaved_order: GPUs grouped by the host-link rate they reach, ranks dealt over the groups in turn
+    (the measured 8 x B200 box: four GPUs at 23 GB/s, four at 36 GB/s)."""
+    from tissue_image_processing_b200.topology import interleaved_order
+    rates = [23.3, 23.3, 23.3, 23.4, 35.6, 35.6, 35.7, 35.5]
+    assert interleaved_order(rates) == [4, 0, 5, 1, 6, 2, 7, 3]
+    assert interleaved_order([54.0, 53.8, 54.1, 53.9]) == [0, 1, 2, 3]
+    assert interleaved_order([50.0]) == [0]
+    assert sorted(interleaved_order([10, 30, 20, 30, 10, 20])) == list(range(6))
+
+
+def test_bench_movie_source_through_the_driver(tmp_path, monkeypatch):
+    """bench.py's in-memory movie source (cycling pageable frames) drives movie_surface_projection like an image
+    file would; the operator seam stands in for the GPU here."""
+    import bench
+    from tissue_image_processing_b200 import basic_image_manipulations as bim
+    from tissue_image_processing_b200 import surface_projection as sp
+    from tissue_image_processing_b200.movie import FramePipeline
+    frames = [synth.synth_stack(6, 24, 32, seed=s) for s in range(3)]
+    source = bench._CyclicMovie(frames, 7)
+    monkeypatch.setattr(bim, "open_image", lambda path: source)
+    written = {}
+    monkeypatch.setattr(sp, "tiff_writer", lambda path, image, axes, metadata: written.update({path: image}))
+    pipe = FramePipeline(operator=orc.time_point_surface_projection, out_dtype="uint16")
+    sp.movie_surface_projection(["m.czi"], 0, [1], 1, str(tmp_path), "max_averages", 1, False, 0, 0, 0, False,
+                                frame_pipeline=pipe)
+    tif = written[os.path.join(str(tmp_path), "position1.tif")]
+    assert tif.shape == (7, 1, 24, 32) and tif.dtype == np.uint16
+    for t in range(7):
+        want = orc.time_point_surface_projection(frames[t % 3][None], "TCZYX", 0, airyscan=False).astype("uint16")
+        assert np.array_equal(tif[t], want)

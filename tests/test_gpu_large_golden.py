@@ -15,7 +15,9 @@ import numpy as np
 import pytest
 
 from oracle import large_cases
-from tests.parity import compare_frame
+from scipy.ndimage import maximum_filter
+
+from tests.parity import PROJ_RTOL, compare_frame
 
 pytestmark = pytest.mark.gpu
 
@@ -73,7 +75,12 @@ def test_reference_golden_at_bench_size(case, tsp):
     for mode in ("exact", "fast"):
         got_proj, got_zmap = tsp.time_point_surface_projection(chunk, "TCZYX", mode=mode, **kw)
         stats = compare_frame(got_proj, got_zmap, ref_proj, want_zmap, gap)
-        # and directly against the stored reference rows (independent of the bitexact run above)
-        row_stats = compare_frame(got_proj[:, rows], got_zmap[rows], want_rows, want_zmap[rows], gap[rows])
-        viol = int(((got_zmap != want_zmap) & ~near_tie).sum())
-        print(name, mode, stats, "rule violations", viol, "row check max rel", row_stats["proj_max_rel"])
+        # and directly against the stored reference rows (independent of the bitexact run above), away from the
+        # +-8 px neighbourhood of tolerated height differences
+        diff = got_zmap != want_zmap
+        clean = ~(maximum_filter(diff.astype(np.uint8), size=17, mode="constant") > 0)[rows]
+        rel = np.abs(got_proj[:, rows] - want_rows) / np.maximum(np.abs(want_rows), 1e-300)
+        row_max = float(rel[:, clean].max())
+        assert row_max <= PROJ_RTOL, (mode, row_max)
+        viol = int((diff & ~near_tie).sum())
+        print(name, mode, stats, "rule violations", viol, "row check max rel", row_max)

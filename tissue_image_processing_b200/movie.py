@@ -154,6 +154,9 @@ def gather_frames(arrays, owned, dst=0, all_ranks=False):
     idx = torch.tensor(sorted(int(t) for t in owned), dtype=torch.int64)
     counts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
     dist.all_gather(counts, torch.tensor([idx.numel()], dtype=torch.int64), group=group)
+    def wire(a):                      # gloo moves bytes; uint16 (the movie dtype) is not one of its scalar types
+        return torch.from_numpy(a).view(torch.uint8)
+
     if rank == dst:
         for src in range(world):
             n = int(counts[src].item())
@@ -162,19 +165,18 @@ def gather_frames(arrays, owned, dst=0, all_ranks=False):
             their = torch.empty(n, dtype=torch.int64)
             dist.recv(their, src=src, group=group)
             for a in arrays:
-                buf = torch.empty((n,) + tuple(a.shape[1:]), dtype=torch.from_numpy(a[:0]).dtype)
-                dist.recv(buf, src=src, group=group)
-                a[their.numpy()] = buf.numpy()
+                buf = np.empty((n,) + tuple(a.shape[1:]), dtype=a.dtype)
+                dist.recv(wire(buf), src=src, group=group)
+                a[their.numpy()] = buf
     elif idx.numel() > 0:
         dist.send(idx, dst=dst, group=group)
         for a in arrays:
-            dist.send(torch.from_numpy(np.ascontiguousarray(a[idx.numpy()])), dst=dst, group=group)
+            dist.send(wire(np.ascontiguousarray(a[idx.numpy()])), dst=dst, group=group)
     if all_ranks:
         for a in arrays:
-            t = torch.from_numpy(a) if a.flags.c_contiguous else None
-            if t is None:
+            if not a.flags.c_contiguous:
                 raise ValueError("gather_frames(all_ranks=True) needs C-contiguous arrays")
-            dist.broadcast(t, src=dst, group=group)
+            dist.broadcast(wire(a), src=dst, group=group)
         return True
     return rank == dst
 
