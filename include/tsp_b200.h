@@ -121,7 +121,9 @@ int tsp_destroy(tsp_handle* h);
 /* Bytes of device scratch tsp_project_frame needs for this frame shape and mode. */
 size_t tsp_project_workspace_bytes(const tsp_frame_desc* desc);
 
-/* Device-resident call.  d_stack (C,Z,Y,X) uint16; d_proj (C,Y,X) float32 = SP:72-79 (the
+/* Device-resident call.  Repeated calls with the same descriptor and buffers (a frame slot, a movie loop) replay the
+ * frame's launch sequence as a CUDA graph: one launch per frame instead of a dozen.
+ * d_stack (C,Z,Y,X) uint16; d_proj (C,Y,X) float32 = SP:72-79 (the
  * reference's float64 values are float32-exact); d_zmap (Y,X) int32 = chosen_z of SP:61
  * (min_z already added).  Stream ordered, returns without synchronising; call
  * tsp_get_frame_status() afterwards to learn about TSP_ERR_BAND_INDEX. */
@@ -237,9 +239,9 @@ int64_t tsp_launch_count(const tsp_handle* h);
 /* Kernel-variant switches for tests and A/B measurements (the product path never needs them; they replace the
  * environment variables of ABI 2, which were read on every launch).  Keys: "no_ring" (strip decimation instead of
  * the TMA ring), "band_variant" (0 auto, 2 register-prefetch kernel, 3 TMA ring kernel for every tile), "no_chain"
- * (plain launches everywhere), "interp_rows" (2, 4 or 8 image rows per thread of the interpolation stage).  The same
- * keys are read ONCE at tsp_create from the environment as TSP_NO_RING, TSP_BAND_VARIANT, TSP_NO_CHAIN,
- * TSP_INTERP_ROWS. */
+ * (plain launches everywhere), "interp_rows" (2, 4 or 8 image rows per thread of the interpolation stage), "graphs"
+ * (0: never replay a frame as a CUDA graph).  The same keys are read ONCE at tsp_create from the environment as
+ * TSP_NO_RING, TSP_BAND_VARIANT, TSP_NO_CHAIN, TSP_INTERP_ROWS, TSP_NO_GRAPHS. */
 int tsp_debug_set(tsp_handle* h, const char* key, int value);
 
 /* Optional per-stage device timing: when enabled, tsp_project_frame records CUDA events on the

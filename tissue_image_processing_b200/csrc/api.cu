@@ -249,6 +249,7 @@ int tsp_create(int device, tsp_handle** out) {
     h->dbg.no_ring = env_int("TSP_NO_RING", 0);
     h->dbg.band_variant = env_int("TSP_BAND_VARIANT", 0);
     h->dbg.interp_rows = env_int("TSP_INTERP_ROWS", 4);
+    h->dbg.graphs = env_int("TSP_NO_GRAPHS", 0) ? 0 : 1;
     if (env_int("TSP_NO_CHAIN", 0)) g_no_chain.store(true);
     *out = h;
     return TSP_OK;
@@ -264,6 +265,7 @@ int tsp_debug_set(tsp_handle* h, const char* key, int value) {
     else if (!strcmp(key, "band_variant") && (value == 0 || value == 2 || value == 3)) h->dbg.band_variant = value;
     else if (!strcmp(key, "interp_rows") && (value == 2 || value == 4 || value == 8)) h->dbg.interp_rows = value;
     else if (!strcmp(key, "no_chain")) g_no_chain.store(value != 0);
+    else if (!strcmp(key, "graphs")) h->dbg.graphs = value != 0;
     else {
         set_error("unknown debug switch %s = %d", key, value);
         return TSP_ERR_INVALID;
@@ -286,6 +288,9 @@ int tsp_destroy(tsp_handle* h) {
         if (sl.h_status) cudaFreeHost(sl.h_status);
         if (sl.stream) cudaStreamDestroy(sl.stream);
     }
+    for (auto& g : h->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (h->capture_stream) cudaStreamDestroy(h->capture_stream);
     if (h->h_status) cudaFreeHost(h->h_status);
     if (h->stream) cudaStreamDestroy(h->stream);
     for (cudaEvent_t ev : h->prof_events) cudaEventDestroy(ev);
@@ -303,12 +308,11 @@ size_t tsp_project_workspace_bytes(const tsp_frame_desc* desc) {
     return carve(desc, c, pr, nullptr).total;
 }
 
-int tsp_project_frame(tsp_handle* h, const tsp_frame_desc* desc, const uint16_t* d_stack, float* d_proj,
-                      int32_t* d_zmap, void* d_workspace, size_t workspace_bytes, void* cuda_stream) {
-    if (!h || !desc || !d_stack || !d_proj || !d_zmap || !d_workspace) {
-        set_error("null argument");
-        return TSP_ERR_INVALID;
-    }
+}  // extern "C"
+
+// Enqueues the kernels of one frame on `s` (plain launches or, when `s` is being captured, graph nodes).
+static int project_frame_eager(tsp_handle* h, const tsp_frame_desc* desc, const uint16_t* d_stack, float* d_proj,
+                               int32_t* d_zmap, void* d_workspace, size_t workspace_bytes, cudaStream_t s) {
     Crop c;
     Params pr;
     int rc = resolve_crop(desc, &c);
@@ -320,8 +324,6 @@ int tsp_project_frame(tsp_handle* h, const tsp_frame_desc* desc, const uint16_t*
         set_error("workspace %zu bytes < required %zu", workspace_bytes, w.total);
         return TSP_ERR_WORKSPACE;
     }
-    TSP_CUDA(cudaSetDevice(h->device));
-    cudaStream_t s = (cudaStream_t)cuda_stream;
     struct ChainScope {          // launches happen on this thread: the flag covers exactly this frame's kernels
         explicit ChainScope(bool on) { tl_chain_launches = on; }
         ~ChainScope() { tl_chain_launches = true; }
@@ -455,6 +457,105 @@ int tsp_project_frame(tsp_handle* h, const tsp_frame_desc* desc, const uint16_t*
                                     desc->reference_channel, desc->atoh_shift, ped, w.status, true, s, worklist);
     prof_mark(h, s, STG_BAND);
     return rc;
+}
+
+
+// ---- CUDA graph replay ------------------------------------------------------------------------------------------
+// A frame is a dozen launches (memset, tensor-map encodes, ten kernels): ~40 us of host time, more than the GPU needs
+// for a 512x512x32 stack.  Frames of a movie run again and again with the same descriptor and the same buffers (a
+// frame slot, a DeviceProjector), so the launch sequence is captured once into a CUDA graph - programmatic dependent
+// launches become programmatic edges - and replayed with one cudaGraphLaunch.  Keyed by descriptor + pointers; the
+// first call with a key runs eagerly (it also uploads per-shape tables, which cannot be captured), the second is
+// captured, later ones replay.  Anything that fails to capture falls back to plain launches for good.
+struct GraphKey {
+    tsp_frame_desc desc;
+    const void* stack;
+    void* proj;
+    void* zmap;
+    void* ws;
+    size_t ws_bytes;
+};
+
+static std::string graph_key(const tsp_frame_desc* desc, const void* stack, void* proj, void* zmap, void* ws, size_t n) {
+    GraphKey k;
+    memset(&k, 0, sizeof k);
+    k.desc = *desc;
+    k.stack = stack; k.proj = proj; k.zmap = zmap; k.ws = ws; k.ws_bytes = n;
+    return std::string((const char*)&k, sizeof k);
+}
+
+static constexpr size_t kGraphCacheEntries = 48;
+
+extern "C" {
+
+int tsp_project_frame(tsp_handle* h, const tsp_frame_desc* desc, const uint16_t* d_stack, float* d_proj,
+                      int32_t* d_zmap, void* d_workspace, size_t workspace_bytes, void* cuda_stream) {
+    if (!h || !desc || !d_stack || !d_proj || !d_zmap || !d_workspace) {
+        set_error("null argument");
+        return TSP_ERR_INVALID;
+    }
+    TSP_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    if (h->profiling || !h->dbg.graphs)
+        return project_frame_eager(h, desc, d_stack, d_proj, d_zmap, d_workspace, workspace_bytes, s);
+    const std::string key = graph_key(desc, d_stack, d_proj, d_zmap, d_workspace, workspace_bytes);
+    std::unique_lock<std::mutex> lock(h->graph_mu);
+    tsp_handle::GraphEntry* e = nullptr;
+    for (auto& g : h->graphs)
+        if (g.key == key) { e = &g; break; }
+    if (!e) {
+        if (h->graphs.size() >= kGraphCacheEntries) {              // evict the least recently used
+            size_t victim = 0;
+            for (size_t i = 1; i < h->graphs.size(); ++i)
+                if (h->graphs[i].last_use < h->graphs[victim].last_use) victim = i;
+            if (h->graphs[victim].exec) cudaGraphExecDestroy(h->graphs[victim].exec);
+            h->graphs.erase(h->graphs.begin() + victim);
+        }
+        h->graphs.emplace_back();
+        e = &h->graphs.back();
+        e->key = key;
+        e->last_use = ++h->graph_tick;
+        lock.unlock();                                              // first sight: plain launches (tables get uploaded)
+        return project_frame_eager(h, desc, d_stack, d_proj, d_zmap, d_workspace, workspace_bytes, s);
+    }
+    e->last_use = ++h->graph_tick;
+    if (!e->exec && !e->failed) {
+        if (!h->capture_stream) TSP_CUDA(cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking));
+        const int64_t before = h->launches;
+        cudaGraph_t graph = nullptr;
+        int rc = TSP_OK;
+        if (cudaStreamBeginCapture(h->capture_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            rc = project_frame_eager(h, desc, d_stack, d_proj, d_zmap, d_workspace, workspace_bytes, h->capture_stream);
+            const cudaError_t ce = cudaStreamEndCapture(h->capture_stream, &graph);
+            if (rc == TSP_OK && ce == cudaSuccess && graph &&
+                cudaGraphInstantiate(&e->exec, graph, 0) == cudaSuccess) {
+                e->launches = h->launches - before;
+            } else {
+                e->exec = nullptr;
+                e->failed = true;
+            }
+            if (graph) cudaGraphDestroy(graph);
+        } else {
+            e->failed = true;
+        }
+        h->launches = before;
+        cudaGetLastError();                                         // a failed capture leaves a sticky-looking error behind
+        if (rc != TSP_OK && rc != TSP_ERR_CUDA) return rc;          // argument errors are the caller's, not the capture's
+    }
+    if (e->exec) {
+        cudaGraphExec_t exec = e->exec;
+        const int64_t n = e->launches;
+        const cudaError_t le = cudaGraphLaunch(exec, s);
+        if (le != cudaSuccess) {
+            set_error("cudaGraphLaunch failed: %s", cudaGetErrorString(le));
+            return TSP_ERR_CUDA;
+        }
+        h->launches += n;
+        h->graph_replays++;
+        return TSP_OK;
+    }
+    lock.unlock();
+    return project_frame_eager(h, desc, d_stack, d_proj, d_zmap, d_workspace, workspace_bytes, s);
 }
 
 int tsp_set_profiling(tsp_handle* h, int enable) {

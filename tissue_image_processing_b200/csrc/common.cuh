@@ -201,7 +201,21 @@ struct tsp_handle {
         int no_ring = 0;         // strip decimation kernel instead of the TMA ring
         int band_variant = 0;    // 0 auto, 2 register-prefetch kernel, 3 TMA ring kernel for every tile
         int interp_rows = 4;     // image rows per thread of the interpolation + argmax stage
+        int graphs = 1;          // replay a frame's launch sequence as a CUDA graph (api.cu)
     } dbg;
+    // CUDA graphs of frames seen before, keyed by descriptor + buffer pointers (api.cu: tsp_project_frame)
+    struct GraphEntry {
+        std::string key;
+        cudaGraphExec_t exec = nullptr;
+        int64_t launches = 0;
+        uint64_t last_use = 0;
+        bool failed = false;
+    };
+    std::vector<GraphEntry> graphs;
+    std::mutex graph_mu;
+    cudaStream_t capture_stream = nullptr;
+    uint64_t graph_tick = 0;
+    int64_t graph_replays = 0;
     std::mutex mu;        // guards taps / tables
     std::mutex host_mu;   // guards d_scratch and the slot table (held only while a call is being enqueued)
     std::mutex single_mu; // tsp_project_frame_host: one blocking call at a time on the handle's own slot

@@ -677,8 +677,14 @@ int launch_percentile(tsp_handle* h, const uint16_t* d_vol, size_t count, int pe
         TSP_CUDA(cudaMemsetAsync(d_scratch, 0, percentile_scratch_bytes(), s));
     }
     const bool zero_vec_ok = zero_ptr && (reinterpret_cast<uintptr_t>(zero_ptr) & 15) == 0 && zero_bytes % 16 == 0;
+    // sampling stride: ~4 M sampled lines' worth of voxels for large volumes, never less than ~1 M (a 16 MiB stack is
+    // sampled 1 in 8: the full-histogram kernel needs 35 us there - its 148 privatised tables flush 65536 bins each -
+    // the sampled window + count pass 20 us); below 2 M voxels the full histogram is the cheaper way
+    size_t target = count / 16;
+    if (target < ((size_t)1 << 19)) target = (size_t)1 << 19;
+    if (target > kSampleTarget) target = kSampleTarget;
     uint32_t stride = 1;
-    while ((count / stride) > 2 * kSampleTarget && stride < 1024) stride *= 2;
+    while ((count / stride) > 2 * target && stride < 1024) stride *= 2;
     if (stride == 1 || !zero_vec_ok) {
         if (zero_ptr && zero_bytes) TSP_CUDA(cudaMemsetAsync(zero_ptr, 0, zero_bytes, s));
         zero_ptr = nullptr;

@@ -88,18 +88,27 @@ def build_continues_manifold(score):
 # ------------------------------------------------------------------------------------------------
 # on-disk conventions
 # ------------------------------------------------------------------------------------------------
-def concatenate_time_points(files):
+def _load_uint16(path, fresh=None):
+    """A per-movie array as uint16 (BIM:481 / SP:230: astype truncates): from ``fresh`` when this run just computed
+    and saved it, else from the resume file."""
+    arr = fresh.get(path) if fresh else None
+    if arr is None:
+        arr = np.load(path)
+    return arr if arr.dtype == np.uint16 else arr.astype("uint16")
+
+
+def concatenate_time_points(files, fresh=None):
     """What BIM:478-495 does to the per-movie arrays of one position (without its resize branch): every array is
     cast to uint16 (truncation), later movies that lost channels get zero channels in FRONT, then all are joined
     along time."""
-    movies = [np.load(f).astype("uint16") for f in files]
+    movies = [_load_uint16(f, fresh) for f in files]
     lead = movies[0].shape
     for k in range(1, len(movies)):
         m = movies[k]
         grow = [(max(lead[d] - m.shape[d], 0), 0) if 1 <= d < m.ndim - 2 else (0, 0) for d in range(m.ndim)]
         if any(g[0] for g in grow):
             movies[k] = np.pad(m, grow, constant_values=0)
-    return np.concatenate(movies, axis=0)
+    return movies[0] if len(movies) == 1 else np.concatenate(movies, axis=0)
 
 
 def save_tiff(path, image, metadata=None, axes="", data_type=""):
@@ -211,6 +220,7 @@ def movie_surface_projection(files, reference_channel, position_final_movie, ini
     chosen = [p for p in range(initial_positions_number) if only_position <= 0 or p == only_position - 1]
     frames_of = {p: 0 for p in chosen}
     resume = {p: ([], []) for p in range(initial_positions_number)}
+    fresh = {}                                         # arrays computed in this run: no need to read them back
     dims_of = {}
     for f, series, position in movie_schedule(len(files), position_final_movie, initial_positions_number):
         if position not in chosen:
@@ -237,7 +247,9 @@ def movie_surface_projection(files, reference_channel, position_final_movie, ini
                                reference_channel=reference_channel, method=method, bin_size=bin_size, atoh_shift=0,
                                build_manifold=build_manifold, min_z=zmin, max_z=zmax, airyscan=airyscan)
         if root:
-            np.save(proj_path, proj.reshape((dims.T, dims.C, dims.Y, dims.X)))
+            fresh[proj_path] = proj.reshape((dims.T, dims.C, dims.Y, dims.X))
+            fresh[zmap_path] = zmap
+            np.save(proj_path, fresh[proj_path])
             np.save(zmap_path, zmap)
     if root:
         for position in chosen:
@@ -245,9 +257,10 @@ def movie_surface_projection(files, reference_channel, position_final_movie, ini
             metadata = update_projection_metadata(bim.get_image_metadata(files[0], series=position),
                                                   float(frames_of[position]), series=position)
             save_tiff(os.path.join(output_dir, output_name + "position%d.tif" % (position + 1)),
-                      concatenate_time_points(proj_files), metadata=metadata, axes="TCYX", data_type="uint16")
+                      concatenate_time_points(proj_files, fresh), metadata=metadata, axes="TCYX", data_type="uint16")
+            zmaps = [_load_uint16(z, fresh) for z in zmap_files]
             np.save(os.path.join(output_dir, output_name + "zmap_position%d.npy" % (position + 1)),
-                    np.concatenate([np.load(z).astype("uint16") for z in zmap_files], axis=0))
+                    zmaps[0] if len(zmaps) == 1 else np.concatenate(zmaps, axis=0))
         save_stage_positions(files, position_final_movie, initial_positions_number, output_dir,
                              only_position=only_position, output_name=output_name)
         for proj_files, zmap_files in resume.values():
