@@ -434,10 +434,14 @@ static int project_frame_eager(tsp_handle* h, const tsp_frame_desc* desc, const 
         if (rc) return rc;
     } else {
         NvtxRange r("tsp/score_fir");
-        rc = launch_prepare(h, ref, w.volA, nvox, ped, w.status, s);
-        if (rc) return rc;
-        prof_mark(h, s, STG_PREPARE);
-        rc = gaussian_blur<float>(h, w.volA, w.volB, w.volA, c.zc, Y, X, sig_pre, fp64, s);
+        if (fp64) {
+            rc = launch_prepare(h, ref, w.volA, nvox, ped, w.status, s);
+            if (rc) return rc;
+            prof_mark(h, s, STG_PREPARE);
+            rc = gaussian_blur<float>(h, w.volA, w.volB, w.volA, c.zc, Y, X, sig_pre, true, s);
+        } else {                       // fp32: conversion, pedestal and clip ride in the first (z) pass
+            rc = prepare_and_blur_f32(h, ref, w.volB, w.volA, c.zc, Y, X, sig_pre, ped, w.status, s);
+        }
         if (rc) return rc;
         prof_mark(h, s, STG_BLUR_PRE);
         rc = gaussian_blur<float>(h, w.volB, w.volA, w.volB, c.zc, Y, X, sig_score, fp64, s);

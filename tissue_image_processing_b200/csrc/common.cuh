@@ -268,6 +268,8 @@ int launch_fir_axis(tsp_handle* h, const T* d_in, T* d_out, int Z, int Y, int X,
 template <typename T>
 int gaussian_blur(tsp_handle* h, const T* d_in, T* d_out, T* d_tmp, int Z, int Y, int X,
                   const double sigma[3], bool fp64, cudaStream_t s);
+int prepare_and_blur_f32(tsp_handle* h, const uint16_t* d_in, float* d_out, float* d_tmp, int Z, int Y, int X,
+                         const double sigma[3], int pedestal, const int32_t* d_status, cudaStream_t s);
 int launch_argmax(tsp_handle* h, const float* d_score, int32_t* d_zmap, int Z, int Y, int X,
                   int z_offset, int32_t* d_status, cudaStream_t s);
 int launch_band_project_ex(tsp_handle* h, const uint16_t* d_stack, size_t channel_stride, size_t z0_offset,

@@ -7,6 +7,8 @@
 //           outermost inwards, (a + b) * w added with separate mul/add (TSP_MODE_BITEXACT)
 #include <math.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace tsp {
@@ -242,10 +244,229 @@ fir_x_kernel(const T* __restrict__ in, T* __restrict__ out, size_t total_rows, i
     }
 }
 
+// ---- fp32 passes at packed rate (TSP_MODE_EXACT, the general path, the materialised band mask) ------------------
+// On sm_100 a scalar FFMA issues every second cycle per scheduler; the packed FFMA2 (two FMAs per lane) issues at
+// the same rate, so only packed arithmetic reaches the FP32 peak.  Both in-plane passes therefore run the same
+// register-blocked line filter on PAIRS of lines: a thread owns 16 consecutive outputs of two neighbouring lines
+// (float2 accumulators), the taps stream through a 16-entry circular window of (w, w) pairs, every input pair costs
+// two 8-byte shared loads and 16 FFMA2.  241 taps (sigma = 30): 256 FFMA2 per 16 x 2 outputs, 94 % of them useful.
+//   y pass: lines = image columns; a lane owns a column pair (adjacent floats: natural float2 loads, conflict free)
+//   x pass: lines = image rows; a lane owns a row pair, interleaved as float2 in shared memory with an odd pitch
+//           (conflict-free 8-byte loads down the lanes); the rows are loaded coalesced and transposed on the way in
+constexpr int kL2Out = 16;                 // outputs per thread along the line
+constexpr int kL2Warps = 8;                // warps per CTA = segments of 16 outputs along the line
+constexpr int kL2Tile = kL2Warps * kL2Out; // 128 outputs along the line per CTA
+
+__device__ __forceinline__ void line_fir16(const float2* __restrict__ col, int stride, const float2* __restrict__ wsh2,
+                                           int r, float2 (&acc)[kL2Out]) {
+    float2 wc[kL2Out];
+#pragma unroll
+    for (int j = 0; j < kL2Out; ++j) {
+        acc[j] = make_float2(0.f, 0.f);
+        wc[j] = make_float2(0.f, 0.f);
+    }
+    // input ii (relative to the first output) feeds output j with tap ii - j; wsh2[i] = tap i for i in [0, 2r], 0 beyond
+    for (int ii = 0; ii < kL2Out + 2 * r; ii += kL2Out) {
+#pragma unroll
+        for (int u = 0; u < kL2Out; ++u) {
+            wc[u] = wsh2[ii + u];
+            const float2 v = col[(size_t)(ii + u) * stride];
+#pragma unroll
+            for (int j = 0; j < kL2Out; ++j) acc[j] = __ffma2_rn(v, wc[(u - j + kL2Out) % kL2Out], acc[j]);
+        }
+    }
+}
+
+// y pass: CTA = 64 columns (32 pairs) x 128 output rows of one plane
+__global__ void __launch_bounds__(32 * kL2Warps)
+fir_y2_kernel(const float* __restrict__ in, float* __restrict__ out, int Y, int X, int r, const float* __restrict__ w32) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int rows_alloc = kL2Tile + 2 * r + kL2Out;                 // slack: the blocked loop overruns by < 16 inputs
+    float* tile = reinterpret_cast<float*>(smem_raw);               // [rows_alloc][64]
+    float2* wsh2 = reinterpret_cast<float2*>(tile + (size_t)rows_alloc * 64);
+    const int lane = threadIdx.x, warp = threadIdx.y, tid = warp * 32 + lane;
+    const int x0 = blockIdx.x * 64, y0 = blockIdx.y * kL2Tile;
+    const size_t zoff = (size_t)blockIdx.z * Y * X;
+    if (x0 + 64 <= X && (X & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {      // 16-byte loads
+        float4* tile4 = reinterpret_cast<float4*>(tile);
+        for (int i = tid; i < rows_alloc * 16; i += 32 * kL2Warps) {
+            const int yy = clampi(y0 - r + (i >> 4), 0, Y - 1);
+            tile4[i] = __ldg(reinterpret_cast<const float4*>(in + zoff + (size_t)yy * X + x0) + (i & 15));
+        }
+    } else {
+        for (int i = tid; i < rows_alloc * 64; i += 32 * kL2Warps) {
+            const int yy = clampi(y0 - r + i / 64, 0, Y - 1), xx = min(x0 + (i & 63), X - 1);
+            tile[i] = __ldg(in + zoff + (size_t)yy * X + xx);
+        }
+    }
+    for (int i = tid; i < 2 * r + 1 + 2 * kL2Out; i += 32 * kL2Warps) {
+        const float w = i <= 2 * r ? w32[i] : 0.f;
+        wsh2[i] = make_float2(w, w);
+    }
+    __syncthreads();
+    float2 acc[kL2Out];
+    line_fir16(reinterpret_cast<const float2*>(tile) + (size_t)(warp * kL2Out) * 32 + lane, 32, wsh2, r, acc);
+    const int x = x0 + 2 * lane;
+#pragma unroll
+    for (int j = 0; j < kL2Out; ++j) {
+        const int y = y0 + warp * kL2Out + j;
+        if (y >= Y || x >= X) continue;
+        float* dst = out + zoff + (size_t)y * X + x;
+        if (x + 1 < X && (X & 1) == 0) *reinterpret_cast<float2*>(dst) = acc[j];
+        else {
+            dst[0] = acc[j].x;
+            if (x + 1 < X) dst[1] = acc[j].y;
+        }
+    }
+}
+
+// x pass: CTA = 64 rows (32 pairs) x 128 output columns; rows run over the flattened (Z*Y) row index
+__global__ void __launch_bounds__(32 * kL2Warps)
+fir_x2_kernel(const float* __restrict__ in, float* __restrict__ out, size_t total_rows, int X, int r,
+              const float* __restrict__ w32) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int xlen = kL2Tile + 2 * r + kL2Out;
+    const int pitch = xlen | 1;                                      // odd, in float2 units
+    float2* tile2 = reinterpret_cast<float2*>(smem_raw);            // [32 row pairs][pitch]
+    float2* wsh2 = tile2 + (size_t)32 * pitch;
+    const int lane = threadIdx.x, warp = threadIdx.y, tid = warp * 32 + lane;
+    const int x0 = blockIdx.x * kL2Tile;
+    const size_t row0 = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * 64;
+    if (row0 >= total_rows) return;
+    float* tile = reinterpret_cast<float*>(tile2);
+    for (int rr = warp; rr < 64; rr += kL2Warps) {                   // one warp per row: coalesced along x
+        size_t row = row0 + rr;
+        if (row >= total_rows) row = total_rows - 1;
+        const float* src = in + row * X;
+        float* dst = tile + ((size_t)(rr >> 1) * pitch) * 2 + (rr & 1);
+        if ((r & 3) == 0 && (X & 3) == 0 && x0 - r >= 0 && x0 - r + xlen <= X &&
+            (reinterpret_cast<uintptr_t>(in) & 15) == 0) {                                     // 16-byte loads
+            const float4* src4 = reinterpret_cast<const float4*>(src + (x0 - r));
+            for (int i = lane; i < xlen / 4; i += 32) {
+                const float4 v = __ldg(src4 + i);
+                dst[8 * i] = v.x; dst[8 * i + 2] = v.y; dst[8 * i + 4] = v.z; dst[8 * i + 6] = v.w;
+            }
+        } else {
+            for (int i = lane; i < xlen; i += 32) dst[2 * i] = __ldg(src + clampi(x0 - r + i, 0, X - 1));
+        }
+    }
+    for (int i = tid; i < 2 * r + 1 + 2 * kL2Out; i += 32 * kL2Warps) {
+        const float w = i <= 2 * r ? w32[i] : 0.f;
+        wsh2[i] = make_float2(w, w);
+    }
+    __syncthreads();
+    float2 acc[kL2Out];
+    line_fir16(tile2 + (size_t)lane * pitch + warp * kL2Out, 1, wsh2, r, acc);
+    const int xo = x0 + warp * kL2Out;
+    const size_t ra = row0 + 2 * lane, rb = ra + 1;
+    const bool vec = (X & 3) == 0 && xo + kL2Out <= X;
+    if (ra < total_rows) {
+        float* da = out + ra * X + xo;
+        if (vec) {
+#pragma unroll
+            for (int q = 0; q < kL2Out / 4; ++q)
+                reinterpret_cast<float4*>(da)[q] = make_float4(acc[4 * q].x, acc[4 * q + 1].x, acc[4 * q + 2].x, acc[4 * q + 3].x);
+        } else {
+#pragma unroll
+            for (int j = 0; j < kL2Out; ++j)
+                if (xo + j < X) da[j] = acc[j].x;
+        }
+    }
+    if (rb < total_rows) {
+        float* db = out + rb * X + xo;
+        if (vec) {
+#pragma unroll
+            for (int q = 0; q < kL2Out / 4; ++q)
+                reinterpret_cast<float4*>(db)[q] = make_float4(acc[4 * q].y, acc[4 * q + 1].y, acc[4 * q + 2].y, acc[4 * q + 3].y);
+        } else {
+#pragma unroll
+            for (int j = 0; j < kL2Out; ++j)
+                if (xo + j < X) db[j] = acc[j].y;
+        }
+    }
+}
+
+// z pass: a thread marches one group of four columns through the planes with the 2R+1 inputs it needs in registers:
+// every voxel is read once and written once (the generic kernel re-reads each input 2R+1 times through the caches)
+template <int R>
+__global__ void __launch_bounds__(256) fir_z_march_kernel(const float* __restrict__ in, float* __restrict__ out, int Z,
+                                                          size_t plane4, const float* __restrict__ w32) {
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= plane4) return;
+    const float4* src = reinterpret_cast<const float4*>(in) + p;
+    float4* dst = reinterpret_cast<float4*>(out) + p;
+    float w[2 * R + 1];
+#pragma unroll
+    for (int k = 0; k <= 2 * R; ++k) w[k] = __ldg(w32 + k);
+    float4 win[2 * R + 1];                        // win[k] = plane z - R + k (edge replicated)
+#pragma unroll
+    for (int k = 0; k <= 2 * R; ++k) win[k] = __ldg(src + (size_t)clampi(k - R, 0, Z - 1) * plane4);
+    for (int z0 = 0; z0 < Z; z0 += 2 * R + 1) {
+#pragma unroll
+        for (int u = 0; u <= 2 * R; ++u) {        // the window rotates through its 2R+1 names: no register moves
+            const int z = z0 + u;
+            if (z >= Z) break;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k <= 2 * R; ++k) {
+                const float4 v = win[(u + k) % (2 * R + 1)];
+                a.x = fmaf(w[k], v.x, a.x); a.y = fmaf(w[k], v.y, a.y);
+                a.z = fmaf(w[k], v.z, a.z); a.w = fmaf(w[k], v.w, a.w);
+            }
+            dst[(size_t)z * plane4] = a;
+            win[u] = __ldg(src + (size_t)clampi(z + R + 1, 0, Z - 1) * plane4);   // slot of plane z - R becomes z + R + 1
+        }
+    }
+}
+
 template <typename T>
 int launch_fir_axis(tsp_handle* h, const T* d_in, T* d_out, int Z, int Y, int X, int axis,
                     const DeviceTaps& taps, bool fp64, cudaStream_t s) {
     const int r = taps.radius;
+    if constexpr (std::is_same<T, float>::value) {
+        if (!fp64) {
+            const float* fin = d_in;
+            float* fout = d_out;
+            const size_t plane = (size_t)Y * X;
+            const bool al16 = ((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_out)) & 15) == 0;
+            if (axis == 0 && (r == 2 || r == 4 || r == 1 || r == 0) && plane % 4 == 0 && al16) {
+                const size_t plane4 = plane / 4;
+                const unsigned blocks = (unsigned)((plane4 + 255) / 256);
+                if (r == 0) fir_z_march_kernel<0><<<blocks, 256, 0, s>>>(fin, fout, Z, plane4, taps.w32);
+                else if (r == 1) fir_z_march_kernel<1><<<blocks, 256, 0, s>>>(fin, fout, Z, plane4, taps.w32);
+                else if (r == 2) fir_z_march_kernel<2><<<blocks, 256, 0, s>>>(fin, fout, Z, plane4, taps.w32);
+                else fir_z_march_kernel<4><<<blocks, 256, 0, s>>>(fin, fout, Z, plane4, taps.w32);
+                TSP_LAUNCH_CHECK(h);
+                return TSP_OK;
+            }
+            if (axis == 1) {
+                const size_t smem = (size_t)(kL2Tile + 2 * r + kL2Out) * 64 * sizeof(float) +
+                                    (size_t)(2 * r + 1 + 2 * kL2Out) * sizeof(float2);
+                if (smem <= 200 * 1024) {
+                    TSP_CUDA(cudaFuncSetAttribute(fir_y2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    dim3 grid((X + 63) / 64, (Y + kL2Tile - 1) / kL2Tile, Z);
+                    fir_y2_kernel<<<grid, dim3(32, kL2Warps), smem, s>>>(fin, fout, Y, X, r, taps.w32);
+                    TSP_LAUNCH_CHECK(h);
+                    return TSP_OK;
+                }
+            }
+            if (axis == 2) {
+                const int xlen = kL2Tile + 2 * r + kL2Out;
+                const size_t smem = (size_t)32 * (xlen | 1) * sizeof(float2) + (size_t)(2 * r + 1 + 2 * kL2Out) * sizeof(float2);
+                if (smem <= 200 * 1024) {
+                    TSP_CUDA(cudaFuncSetAttribute(fir_x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    const size_t total_rows = (size_t)Z * Y;
+                    const size_t groups = (total_rows + 63) / 64;
+                    dim3 grid((X + kL2Tile - 1) / kL2Tile, 1, 1);
+                    grid.y = (unsigned)(groups < 32768 ? groups : 32768);
+                    grid.z = (unsigned)((groups + grid.y - 1) / grid.y);
+                    fir_x2_kernel<<<grid, dim3(32, kL2Warps), smem, s>>>(fin, fout, total_rows, X, r, taps.w32);
+                    TSP_LAUNCH_CHECK(h);
+                    return TSP_OK;
+                }
+            }
+        }
+    }
     if (axis == 0) {
         const size_t plane = (size_t)Y * X;
         const int threads = 256;
@@ -311,6 +532,80 @@ int gaussian_blur(tsp_handle* h, const T* d_in, T* d_out, T* d_tmp, int Z, int Y
     rc = launch_fir_axis<T>(h, d_out, d_tmp, Z, Y, X, 1, t[1], fp64, s);
     if (rc) return rc;
     return launch_fir_axis<T>(h, d_tmp, d_out, Z, Y, X, 2, t[2], fp64, s);
+}
+
+// The same march reading the raw uint16 stack: SP:26-36 (float conversion, pedestal, percentile clip) happen on the
+// way into the window, so the fp32 path never writes the un-blurred float volume (one 1 GB write + read less at
+// 2048 x 2048 x 64)
+template <int R>
+__global__ void __launch_bounds__(256) prep_fir_z_march_kernel(const uint16_t* __restrict__ in, float* __restrict__ out,
+                                                               int Z, size_t plane4, const float* __restrict__ w32,
+                                                               int pedestal, const int32_t* __restrict__ status) {
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= plane4) return;
+    const bool clip = status[ST_HAS_NONZERO] != 0;
+    const float p95 = clip ? __int_as_float(status[ST_P95_BITS]) : 3.0e38f;
+    const uint2* src = reinterpret_cast<const uint2*>(in) + p;
+    float4* dst = reinterpret_cast<float4*>(out) + p;
+    auto load = [&](int z) {
+        const uint2 q = __ldg(src + (size_t)clampi(z, 0, Z - 1) * plane4);
+        const int v0 = (int)(q.x & 0xffffu) - pedestal, v1 = (int)(q.x >> 16) - pedestal;
+        const int v2 = (int)(q.y & 0xffffu) - pedestal, v3 = (int)(q.y >> 16) - pedestal;
+        return make_float4(fminf((float)max(v0, 0), p95), fminf((float)max(v1, 0), p95), fminf((float)max(v2, 0), p95),
+                           fminf((float)max(v3, 0), p95));
+    };
+    float w[2 * R + 1];
+#pragma unroll
+    for (int k = 0; k <= 2 * R; ++k) w[k] = __ldg(w32 + k);
+    float4 win[2 * R + 1];
+#pragma unroll
+    for (int k = 0; k <= 2 * R; ++k) win[k] = load(k - R);
+    for (int z0 = 0; z0 < Z; z0 += 2 * R + 1) {
+#pragma unroll
+        for (int u = 0; u <= 2 * R; ++u) {
+            const int z = z0 + u;
+            if (z >= Z) break;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k <= 2 * R; ++k) {
+                const float4 v = win[(u + k) % (2 * R + 1)];
+                a.x = fmaf(w[k], v.x, a.x); a.y = fmaf(w[k], v.y, a.y);
+                a.z = fmaf(w[k], v.z, a.z); a.w = fmaf(w[k], v.w, a.w);
+            }
+            dst[(size_t)z * plane4] = a;
+            win[u] = load(z + R + 1);
+        }
+    }
+}
+
+// SP:26-37 in fp32: prepared volume blurred with `sigma`, result in d_out, d_tmp is scratch of the same size.  Takes
+// the fused march when it applies, otherwise prepare + the three generic passes (d_tmp holds the prepared volume).
+int prepare_and_blur_f32(tsp_handle* h, const uint16_t* d_in, float* d_out, float* d_tmp, int Z, int Y, int X,
+                         const double sigma[3], int pedestal, const int32_t* d_status, cudaStream_t s) {
+    DeviceTaps t[3];
+    for (int a = 0; a < 3; ++a) {
+        int rc = get_taps(h, sigma[a], &t[a]);
+        if (rc) return rc;
+    }
+    const size_t plane = (size_t)Y * X;
+    const int r = t[0].radius;
+    const bool fused = (r == 0 || r == 1 || r == 2 || r == 4) && plane % 4 == 0 &&
+                       (reinterpret_cast<uintptr_t>(d_in) & 7) == 0 && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0;
+    if (!fused) {
+        int rc = launch_prepare(h, d_in, d_tmp, (size_t)Z * plane, pedestal, d_status, s);
+        if (rc) return rc;
+        return gaussian_blur<float>(h, d_tmp, d_out, d_tmp, Z, Y, X, sigma, false, s);
+    }
+    const size_t plane4 = plane / 4;
+    const unsigned blocks = (unsigned)((plane4 + 255) / 256);
+    if (r == 0) prep_fir_z_march_kernel<0><<<blocks, 256, 0, s>>>(d_in, d_out, Z, plane4, t[0].w32, pedestal, d_status);
+    else if (r == 1) prep_fir_z_march_kernel<1><<<blocks, 256, 0, s>>>(d_in, d_out, Z, plane4, t[0].w32, pedestal, d_status);
+    else if (r == 2) prep_fir_z_march_kernel<2><<<blocks, 256, 0, s>>>(d_in, d_out, Z, plane4, t[0].w32, pedestal, d_status);
+    else prep_fir_z_march_kernel<4><<<blocks, 256, 0, s>>>(d_in, d_out, Z, plane4, t[0].w32, pedestal, d_status);
+    TSP_LAUNCH_CHECK(h);
+    int rc = launch_fir_axis<float>(h, d_out, d_tmp, Z, Y, X, 1, t[1], false, s);
+    if (rc) return rc;
+    return launch_fir_axis<float>(h, d_tmp, d_out, Z, Y, X, 2, t[2], false, s);
 }
 
 template int gaussian_blur<float>(tsp_handle*, const float*, float*, float*, int, int, int, const double[3], bool, cudaStream_t);
