@@ -239,9 +239,10 @@ int64_t tsp_launch_count(const tsp_handle* h);
 /* Kernel-variant switches for tests and A/B measurements (the product path never needs them; they replace the
  * environment variables of ABI 2, which were read on every launch).  Keys: "no_ring" (strip decimation instead of
  * the TMA ring), "band_variant" (0 auto, 2 register-prefetch kernel, 3 TMA ring kernel for every tile), "no_chain"
- * (plain launches everywhere), "interp_rows" (2, 4 or 8 image rows per thread of the interpolation stage), "graphs"
- * (0: never replay a frame as a CUDA graph).  The same keys are read ONCE at tsp_create from the environment as
- * TSP_NO_RING, TSP_BAND_VARIANT, TSP_NO_CHAIN, TSP_INTERP_ROWS, TSP_NO_GRAPHS. */
+ * (plain launches everywhere), "interp_rows" (2, 4 or 8 image rows per thread of the interpolation stage),
+ * "interp_global" (interpolation stage with its control points read from L2 instead of staged in shared memory),
+ * "graphs" (0: never replay a frame as a CUDA graph).  The same keys are read ONCE at tsp_create from the
+ * environment as TSP_NO_RING, TSP_BAND_VARIANT, TSP_NO_CHAIN, TSP_INTERP_ROWS, TSP_INTERP_GLOBAL, TSP_NO_GRAPHS. */
 int tsp_debug_set(tsp_handle* h, const char* key, int value);
 
 /* Optional per-stage device timing: when enabled, tsp_project_frame records CUDA events on the

@@ -221,3 +221,30 @@ def test_host_c_abi_call_matches_device_call(nat):
     assert np.array_equal(zmap, dzmap.cpu().numpy().astype(np.int64))
     assert st["has_nonzero"] and not st["band_index_error"]
     assert p.status()["percentile95"] == st["percentile95"]
+
+
+@pytest.mark.parametrize("shape", [(24, 520, 776), (9, 131, 264), (70, 300, 1032), (5, 77, 2056)])
+def test_interpolation_stage_variants_agree(nat, shape):
+    """The interpolation + argmax stage staged in shared memory (default) and reading its control points from L2
+    (round-1 kernel, tsp_debug_set "interp_global") run the same arithmetic: identical height maps and projections,
+    also with plain instead of graph-replayed launches."""
+    import torch
+    Z, Y, X = shape
+    stack = torch.from_numpy(synth.synth_stack(Z, Y, X, seed=sum(shape))).cuda()
+    p = nat.DeviceProjector(1, Z, Y, X, mode="fast")
+    outs = []
+    try:
+        for key, val in ((None, 0), ("interp_global", 1), ("graphs", 0)):
+            if key:
+                nat.debug_set(key, val)
+            for _ in range(3):                       # first call plain, second captured, third replayed
+                proj, zmap = p.run(stack)
+            torch.cuda.synchronize()
+            outs.append((proj.clone(), zmap.clone()))
+            if key:
+                nat.debug_set(key, 1 - val)
+    finally:
+        nat.debug_set("interp_global", 0)
+        nat.debug_set("graphs", 1)
+    for proj, zmap in outs[1:]:
+        assert torch.equal(zmap, outs[0][1]) and torch.equal(proj, outs[0][0])

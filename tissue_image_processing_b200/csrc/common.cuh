@@ -202,6 +202,7 @@ struct tsp_handle {
         int band_variant = 0;    // 0 auto, 2 register-prefetch kernel, 3 TMA ring kernel for every tile
         int interp_rows = 4;     // image rows per thread of the interpolation + argmax stage
         int graphs = 1;          // replay a frame's launch sequence as a CUDA graph (api.cu)
+        int interp_global = 0;   // interpolation stage reads its control points from L2 (round-1 kernel) instead of shared memory
     } dbg;
     // CUDA graphs of frames seen before, keyed by descriptor + buffer pointers (api.cu: tsp_project_frame)
     struct GraphEntry {
@@ -238,6 +239,7 @@ struct tsp_handle {
     };
     Slot slots[TSP_MAX_SLOTS + 1];       // the last one belongs to tsp_project_frame_host
     // per-device one-time setup done (constant memory, function attributes)
+    size_t interp_smem_set = 0;
     bool fast_consts = false, band_consts = false, hist_attr = false, ring_attr = false, band3_attr = false, band4_attr = false, xy_attr = false, manifold_attr = false, count_attr = false;
     // optional per-stage timing (tsp_set_profiling): CUDA events recorded on the launching stream
     bool profiling = false;
