@@ -386,6 +386,90 @@ fir_x2_kernel(const float* __restrict__ in, float* __restrict__ out, size_t tota
     }
 }
 
+// Short in-plane filters (sigma = 1 and 2 of SP:37 / SP:70-71: radius <= 8) as ONE kernel: a 32 x 128 output tile with
+// its halo goes to shared memory, the y pass writes an intermediate tile (float32, the rounding point between scipy's
+// passes), the x pass reads it - one global read and one write instead of two of each.  Taps are zero padded to the
+// compile-time radius R; sums run over the taps in ascending order like the unfused passes (adding w = 0 terms is exact).
+constexpr int kYXTY = 32, kYXTX = 128;
+
+template <int R>
+__global__ void __launch_bounds__(256) fir_yx_fused_kernel(const float* __restrict__ in, float* __restrict__ out, int Y,
+                                                           int X, int ry, int rx, const float* __restrict__ wy32,
+                                                           const float* __restrict__ wx32) {
+    constexpr int IW = kYXTX + 2 * R, IH = kYXTY + 2 * R, NT = 2 * R + 1;
+    __shared__ float in_s[IH][IW];
+    __shared__ float mid_s[kYXTY][IW];
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * kYXTX, y0 = blockIdx.y * kYXTY;
+    const size_t zoff = (size_t)blockIdx.z * Y * X;
+    float wy[NT], wx[NT];                          // tap k multiplies the sample at offset k - R
+#pragma unroll
+    for (int k = 0; k < NT; ++k) {
+        const int ky = k - R + ry, kx = k - R + rx;
+        wy[k] = (ky >= 0 && ky <= 2 * ry) ? __ldg(wy32 + ky) : 0.f;
+        wx[k] = (kx >= 0 && kx <= 2 * rx) ? __ldg(wx32 + kx) : 0.f;
+    }
+    for (int i = tid; i < IH * IW; i += 256) {
+        const int r = i / IW, c = i - r * IW;
+        const int yy = clampi(y0 - R + r, 0, Y - 1), xx = clampi(x0 - R + c, 0, X - 1);
+        in_s[r][c] = __ldg(in + zoff + (size_t)yy * X + xx);
+    }
+    __syncthreads();
+    // y pass: task = (column, group of 8 output rows)
+    for (int task = tid; task < IW * (kYXTY / 8); task += 256) {
+        const int c = task % IW, g = task / IW;
+        float v[8 + 2 * R];
+#pragma unroll
+        for (int i = 0; i < 8 + 2 * R; ++i) v[i] = in_s[8 * g + i][c];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float a = 0.f;
+#pragma unroll
+            for (int k = 0; k < NT; ++k) a = fmaf(wy[k], v[j + k], a);
+            mid_s[8 * g + j][c] = a;
+        }
+    }
+    __syncthreads();
+    // x pass: task = (row, group of 8 output columns)
+    for (int task = tid; task < kYXTY * (kYXTX / 8); task += 256) {
+        const int g = task % (kYXTX / 8), r = task / (kYXTX / 8);
+        const int y = y0 + r, x = x0 + 8 * g;
+        if (y >= Y || x >= X) continue;
+        float v[8 + 2 * R];
+#pragma unroll
+        for (int i = 0; i < 8 + 2 * R; ++i) v[i] = mid_s[r][8 * g + i];
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float a = 0.f;
+#pragma unroll
+            for (int k = 0; k < NT; ++k) a = fmaf(wx[k], v[j + k], a);
+            o[j] = a;
+        }
+        float* dst = out + zoff + (size_t)y * X + x;
+        if (x + 7 < X && (X & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+            reinterpret_cast<float4*>(dst)[0] = make_float4(o[0], o[1], o[2], o[3]);
+            reinterpret_cast<float4*>(dst)[1] = make_float4(o[4], o[5], o[6], o[7]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (x + j < X) dst[j] = o[j];
+        }
+    }
+}
+
+// both in-plane passes of a float32 blur, d_in -> d_out (d_in is not modified); false when the radii are too large
+static bool fir_yx_fused(tsp_handle* h, const float* d_in, float* d_out, int Z, int Y, int X, const DeviceTaps& ty,
+                         const DeviceTaps& tx, cudaStream_t s) {
+    const int r = ty.radius > tx.radius ? ty.radius : tx.radius;
+    if (r > 8) return false;
+    dim3 grid((X + kYXTX - 1) / kYXTX, (Y + kYXTY - 1) / kYXTY, Z);
+    if (r <= 4) fir_yx_fused_kernel<4><<<grid, 256, 0, s>>>(d_in, d_out, Y, X, ty.radius, tx.radius, ty.w32, tx.w32);
+    else fir_yx_fused_kernel<8><<<grid, 256, 0, s>>>(d_in, d_out, Y, X, ty.radius, tx.radius, ty.w32, tx.w32);
+    h->launches++;
+    return true;
+}
+
 // z pass: a thread marches one group of four columns through the planes with the 2R+1 inputs it needs in registers:
 // every voxel is read once and written once (the generic kernel re-reads each input 2R+1 times through the caches)
 template <int R>
@@ -527,6 +611,23 @@ int gaussian_blur(tsp_handle* h, const T* d_in, T* d_out, T* d_tmp, int Z, int Y
         int rc = get_taps(h, sigma[a], &t[a]);
         if (rc) return rc;
     }
+    if constexpr (std::is_same<T, float>::value) {
+        // short in-plane filters: y and x in one kernel (z pass into d_tmp first).  Callers may pass d_tmp == d_in:
+        // the marching z pass works in place (it never re-reads a plane it has written), the generic one does not
+        const int rz = t[0].radius;
+        const bool march = (rz == 0 || rz == 1 || rz == 2 || rz == 4) && ((size_t)Y * X) % 4 == 0 &&
+                           ((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_tmp)) & 15) == 0;
+        if (!fp64 && t[1].radius <= 8 && t[2].radius <= 8 && (march || (const void*)d_tmp != (const void*)d_in)) {
+            int rc = launch_fir_axis<T>(h, d_in, d_tmp, Z, Y, X, 0, t[0], false, s);
+            if (rc) return rc;
+            fir_yx_fused(h, d_tmp, d_out, Z, Y, X, t[1], t[2], s);
+            if (cudaGetLastError() != cudaSuccess) {
+                set_error("fused y/x pass failed to launch");
+                return TSP_ERR_CUDA;
+            }
+            return TSP_OK;
+        }
+    }
     int rc = launch_fir_axis<T>(h, d_in, d_out, Z, Y, X, 0, t[0], fp64, s);
     if (rc) return rc;
     rc = launch_fir_axis<T>(h, d_out, d_tmp, Z, Y, X, 1, t[1], fp64, s);
@@ -590,7 +691,8 @@ int prepare_and_blur_f32(tsp_handle* h, const uint16_t* d_in, float* d_out, floa
     const size_t plane = (size_t)Y * X;
     const int r = t[0].radius;
     const bool fused = (r == 0 || r == 1 || r == 2 || r == 4) && plane % 4 == 0 &&
-                       (reinterpret_cast<uintptr_t>(d_in) & 7) == 0 && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0;
+                       (reinterpret_cast<uintptr_t>(d_in) & 7) == 0 &&
+                       ((reinterpret_cast<uintptr_t>(d_out) | reinterpret_cast<uintptr_t>(d_tmp)) & 15) == 0;
     if (!fused) {
         int rc = launch_prepare(h, d_in, d_tmp, (size_t)Z * plane, pedestal, d_status, s);
         if (rc) return rc;
@@ -598,11 +700,21 @@ int prepare_and_blur_f32(tsp_handle* h, const uint16_t* d_in, float* d_out, floa
     }
     const size_t plane4 = plane / 4;
     const unsigned blocks = (unsigned)((plane4 + 255) / 256);
-    if (r == 0) prep_fir_z_march_kernel<0><<<blocks, 256, 0, s>>>(d_in, d_out, Z, plane4, t[0].w32, pedestal, d_status);
-    else if (r == 1) prep_fir_z_march_kernel<1><<<blocks, 256, 0, s>>>(d_in, d_out, Z, plane4, t[0].w32, pedestal, d_status);
-    else if (r == 2) prep_fir_z_march_kernel<2><<<blocks, 256, 0, s>>>(d_in, d_out, Z, plane4, t[0].w32, pedestal, d_status);
-    else prep_fir_z_march_kernel<4><<<blocks, 256, 0, s>>>(d_in, d_out, Z, plane4, t[0].w32, pedestal, d_status);
+    const bool short_xy = t[1].radius <= 8 && t[2].radius <= 8;
+    float* zdst = short_xy ? d_tmp : d_out;          // the fused y/x kernel then goes d_tmp -> d_out
+    if (r == 0) prep_fir_z_march_kernel<0><<<blocks, 256, 0, s>>>(d_in, zdst, Z, plane4, t[0].w32, pedestal, d_status);
+    else if (r == 1) prep_fir_z_march_kernel<1><<<blocks, 256, 0, s>>>(d_in, zdst, Z, plane4, t[0].w32, pedestal, d_status);
+    else if (r == 2) prep_fir_z_march_kernel<2><<<blocks, 256, 0, s>>>(d_in, zdst, Z, plane4, t[0].w32, pedestal, d_status);
+    else prep_fir_z_march_kernel<4><<<blocks, 256, 0, s>>>(d_in, zdst, Z, plane4, t[0].w32, pedestal, d_status);
     TSP_LAUNCH_CHECK(h);
+    if (short_xy) {
+        fir_yx_fused(h, d_tmp, d_out, Z, Y, X, t[1], t[2], s);
+        if (cudaGetLastError() != cudaSuccess) {
+            set_error("fused y/x pass failed to launch");
+            return TSP_ERR_CUDA;
+        }
+        return TSP_OK;
+    }
     int rc = launch_fir_axis<float>(h, d_out, d_tmp, Z, Y, X, 1, t[1], false, s);
     if (rc) return rc;
     return launch_fir_axis<float>(h, d_tmp, d_out, Z, Y, X, 2, t[2], false, s);
