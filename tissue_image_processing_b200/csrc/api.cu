@@ -251,7 +251,6 @@ int tsp_create(int device, tsp_handle** out) {
     h->dbg.interp_rows = env_int("TSP_INTERP_ROWS", 4);
     h->dbg.graphs = env_int("TSP_NO_GRAPHS", 0) ? 0 : 1;
     h->dbg.interp_global = env_int("TSP_INTERP_GLOBAL", 0);
-    h->dbg.fused_count_probe = env_int("TSP_FUSED_COUNT_PROBE", 0);
     if (env_int("TSP_NO_CHAIN", 0)) g_no_chain.store(true);
     *out = h;
     return TSP_OK;
@@ -269,7 +268,6 @@ int tsp_debug_set(tsp_handle* h, const char* key, int value) {
     else if (!strcmp(key, "no_chain")) g_no_chain.store(value != 0);
     else if (!strcmp(key, "graphs")) h->dbg.graphs = value != 0;
     else if (!strcmp(key, "interp_global")) h->dbg.interp_global = value != 0;
-    else if (!strcmp(key, "fused_count_probe")) h->dbg.fused_count_probe = value != 0;
     else {
         set_error("unknown debug switch %s = %d", key, value);
         return TSP_ERR_INVALID;

@@ -202,7 +202,6 @@ struct tsp_handle {
         int band_variant = 0;    // 0 auto, 2 register-prefetch kernel, 3 TMA ring kernel for every tile
         int interp_rows = 4;     // image rows per thread of the interpolation + argmax stage
         int graphs = 1;          // replay a frame's launch sequence as a CUDA graph (api.cu)
-        int fused_count_probe = 0;   // MEASUREMENT ONLY: the decimation kernel also runs the counting pass's arithmetic
         int interp_global = 0;   // interpolation stage reads its control points from L2 (round-1 kernel) instead of shared memory
     } dbg;
     // CUDA graphs of frames seen before, keyed by descriptor + buffer pointers (api.cu: tsp_project_frame)
