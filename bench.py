@@ -232,6 +232,7 @@ class Timer:
     def prime(self):
         """Every (projector, frame) pair twice: the library replays a frame's launches as a CUDA graph from the third
         call with the same buffers on (first call plain, second captured) - none of that inside a timed region."""
+        self.torch.cuda.synchronize()          # the frames were generated on the current stream: side streams must see them
         for _ in range(2):
             for f in self.frames:
                 self.one.run(f)
@@ -278,6 +279,7 @@ def run_configs(args, torch, nat, device, index, peak, barrier, max_over_ranks):
         streams = args.movie_streams if frame_bytes < (200 << 20) else args.streams
         if frame_bytes >= (3 << 30):
             streams = 2
+        print("bench: %s (%d frames in the input pool, %d in flight)" % (key, pool, streams), file=sys.stderr, flush=True)
         t = Timer(torch, nat, device, index, C, Zs, Ys, Xs, "fast", streams, frames)
         t.prime()
         t.serial(3)
@@ -574,6 +576,7 @@ def run_gpu(args, rank, world, local_rank):
         return
 
     # ---- end to end through the public API ----------------------------------------------------------
+    print("bench: end to end", file=sys.stderr, flush=True)
     host_frames = []
     for f in frames:
         h = nat.pinned_empty((1, 1, Z, Y, X), np.uint16)

@@ -362,10 +362,22 @@ class DeviceProjector:
         self.workspace = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
         self.proj = torch.empty((Cn, Y, X), dtype=torch.float32, device=self.device)
         self.zmap = torch.empty((Y, X), dtype=torch.int32, device=self.device)
+        # torch's caching allocator may have handed out blocks that earlier work of the allocating stream is still
+        # writing (temporaries freed a moment ago): a frame launched on ANOTHER stream must be ordered behind that
+        with torch.cuda.device(self.device):
+            self._ready = torch.cuda.Event()
+            self._ready.record()
+        self._ordered = set()
 
     def run(self, d_stack, stream=None):
         """d_stack: CUDA uint16 tensor (C,Z,Y,X), contiguous.  Asynchronous."""
         assert d_stack.is_cuda and d_stack.is_contiguous() and d_stack.element_size() == 2
+        if stream is None:
+            import torch
+            stream = torch.cuda.current_stream(self.device)
+        if stream.cuda_stream not in self._ordered:
+            stream.wait_event(self._ready)
+            self._ordered.add(stream.cuda_stream)
         rc = self.lib.tsp_project_frame(self.h, C.byref(self.desc), C.c_void_p(d_stack.data_ptr()),
                                         C.c_void_p(self.proj.data_ptr()), C.c_void_p(self.zmap.data_ptr()),
                                         C.c_void_p(self.workspace.data_ptr()), self.ws_bytes, _stream_ptr(stream))

@@ -16,6 +16,7 @@ void set_error(const char* fmt, ...) {
 
 thread_local bool tl_chain_launches = true;
 std::atomic<bool> g_no_chain{false};
+bool g_sync_launches = false;
 
 static const char* kStageNames[STG_COUNT] = {"percentile", "decimate", "coarse", "interp_argmax", "prepare",
                                              "blur_pre", "blur_score", "argmax", "band", "widen",
@@ -252,6 +253,7 @@ int tsp_create(int device, tsp_handle** out) {
     h->dbg.graphs = env_int("TSP_NO_GRAPHS", 0) ? 0 : 1;
     h->dbg.interp_global = env_int("TSP_INTERP_GLOBAL", 0);
     if (env_int("TSP_NO_CHAIN", 0)) g_no_chain.store(true);
+    g_sync_launches = env_int("TSP_SYNC_LAUNCHES", 0) != 0;
     *out = h;
     return TSP_OK;
 }

@@ -73,6 +73,7 @@ enum Stage {
     do {                                                                                       \
         (h)->launches++;                                                                       \
         cudaError_t _e = cudaGetLastError();                                                   \
+        if (_e == cudaSuccess && tsp::g_sync_launches) _e = cudaDeviceSynchronize();           \
         if (_e != cudaSuccess) {                                                               \
             tsp::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, \
                            __LINE__);                                                          \
@@ -111,7 +112,8 @@ constexpr int kTapPad = 8;
 // may start queueing.  Launched the ordinary way (<<<>>>) both calls do nothing.  What this buys is the ~2 us of
 // launch latency and ramp at each of the frame's ten kernel boundaries.
 extern thread_local bool tl_chain_launches;      // false while a TSP_FRAME_CONCURRENT frame is being enqueued
-extern std::atomic<bool> g_no_chain;             // A/B switch (TSP_NO_CHAIN at tsp_create, tsp_debug_set "no_chain")
+extern std::atomic<bool> g_no_chain;
+extern bool g_sync_launches;                     // debugging aid (TSP_SYNC_LAUNCHES=1): device sync + error check per launch             // A/B switch (TSP_NO_CHAIN at tsp_create, tsp_debug_set "no_chain")
 #ifdef __CUDACC__
 __device__ __forceinline__ void chain_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void chain_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

@@ -45,6 +45,7 @@ for ns in streams:
         torch.cuda.synchronize()
         return e0.elapsed_time(e1)
 
+    torch.cuda.synchronize()
     for _ in range(2):                   # every (projector, frame) pair twice: graphs captured before timing
         for f in frames:
             for k in range(ns):
