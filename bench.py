@@ -277,6 +277,8 @@ def run_configs(args, torch, nat, device, index, peak, barrier, max_over_ranks):
         frames = [synth_frame_device(torch, 200 + i, device, (Zs, Ys, Xs), C) for i in range(pool)]
         steps = max(4, min(args.steps, int(0.25e12 // (C * Zs * Ys * Xs * 64)) + 4))
         streams = args.movie_streams if frame_bytes < (200 << 20) else args.streams
+        if frame_bytes < (40 << 20):
+            streams = 2 * args.movie_streams         # a 16 MiB stack is launch-latency bound: more frames in flight
         if frame_bytes >= (3 << 30):
             streams = 2
         print("bench: %s (%d frames in the input pool, %d in flight)" % (key, pool, streams), file=sys.stderr, flush=True)

@@ -492,7 +492,7 @@ static std::string graph_key(const tsp_frame_desc* desc, const void* stack, void
     return std::string((const char*)&k, sizeof k);
 }
 
-static constexpr size_t kGraphCacheEntries = 48;
+static constexpr size_t kGraphCacheEntries = 256;
 
 extern "C" {
 
