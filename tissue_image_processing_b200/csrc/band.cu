@@ -7,6 +7,8 @@
 // registers), keeps a 9-plane window of A per pixel and applies the z taps as the exact
 // edge-replicating 9-band matrix (SURVEY trap T9), multiplying the raw uint16 voxels as they
 // stream by.  Only planes inside the band are read from HBM.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace tsp {
@@ -1011,31 +1013,44 @@ __global__ void __launch_bounds__(kB2Threads, 3) band_project4_kernel(const __gr
 #pragma unroll
     for (int q = 0; q < 4; ++q) best[q] = make_float2(0.f, 0.f);
     mbar_wait(bar_s, 0);
+    // The walk, specialised on the number of planes the tile spans (block-uniform switch): planes beyond zhi hold
+    // exact zeros, their terms are left out at compile time (a tile spanning two planes runs 18 instead of 57
+    // (step, plane) terms).  Dropping fma(w, 0, m) terms does not change m: bit-identical to the full form.
+    auto walk = [&](auto span_tag) {
+        constexpr int NR = decltype(span_tag)::value;
 #pragma unroll
-    for (int i = 0; i < kB4NW; ++i) {
-        const int z = zlo - 4 + i;
-        if (z > zend) break;                                       // block-uniform
-        if (z < zbeg) continue;
-        const uint4 cur = *reinterpret_cast<const uint4*>(my_vox + (size_t)z * kB3PlaneBytes);
-        float2 m[4];
+        for (int i = 0; i < NR + 8; ++i) {
+            const int z = zlo - 4 + i;
+            if (z > zend) break;                                   // block-uniform
+            if (z < zbeg) continue;
+            const uint4 cur = *reinterpret_cast<const uint4*>(my_vox + (size_t)z * kB3PlaneBytes);
+            float2 m[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) m[q] = make_float2(0.f, 0.f);
+            for (int q = 0; q < 4; ++q) m[q] = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < kB4NP; ++j) {
-            if (j > i || j < i - 8) continue;                      // outside the 9-band: compile time
-            const float2 w = wtab[i][j];
+            for (int j = 0; j < NR; ++j) {
+                if (j > i || j < i - 8) continue;                  // outside the 9-band: compile time
+                const float2 w = wtab[i][j];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) m[q] = __ffma2_rn(w, A[j][q], m[q]);
+                for (int q = 0; q < 4; ++q) m[q] = __ffma2_rn(w, A[j][q], m[q]);
+            }
+            const uint32_t w0[4] = {cur.x, cur.y, cur.z, cur.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float2 f = __fadd2_rn(make_float2(band_u16f_lo(w0[q], magic), band_u16f_hi(w0[q], magic)), nbias);
+                if (AIRY) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); }
+                const float2 pr = __fmul2_rn(f, m[q]);
+                best[q].x = fmaxf(best[q].x, pr.x);
+                best[q].y = fmaxf(best[q].y, pr.y);
+            }
         }
-        const uint32_t w0[4] = {cur.x, cur.y, cur.z, cur.w};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            float2 f = __fadd2_rn(make_float2(band_u16f_lo(w0[q], magic), band_u16f_hi(w0[q], magic)), nbias);
-            if (AIRY) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); }
-            const float2 pr = __fmul2_rn(f, m[q]);
-            best[q].x = fmaxf(best[q].x, pr.x);
-            best[q].y = fmaxf(best[q].y, pr.y);
-        }
+    };
+    switch (zhi - zlo + 1) {
+        case 1: walk(std::integral_constant<int, 1>{}); break;
+        case 2: walk(std::integral_constant<int, 2>{}); break;
+        case 3: walk(std::integral_constant<int, 3>{}); break;
+        case 4: walk(std::integral_constant<int, 4>{}); break;
+        default: walk(std::integral_constant<int, 5>{}); break;
     }
     if (inside) {
         float* dst = a.proj + ((size_t)ch * a.Y + y) * a.X + x;

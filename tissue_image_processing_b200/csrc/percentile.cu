@@ -704,8 +704,13 @@ int launch_percentile(tsp_handle* h, const uint16_t* d_vol, size_t count, int pe
                             win, counters, tickets + 2, q));
     TSP_LAUNCH_CHECK(h);
     prof_mark(h, s, STG_PCT_COUNT);      // what follows (the gated fallback) is booked on the caller's STG_PERCENTILE
-    // exact fallback, armed by ST_NEED_FULL (returns at once otherwise)
-    TSP_CUDA(launch_chained(hist_percentile_kernel, hist_grid(h, count, 1), kHistThreads, kHistSmemBytes, s, d_vol, count,
+    // exact fallback, armed by ST_NEED_FULL (returns at once otherwise).  It is almost never armed (a sample of fewer
+    // than 1024 non-zero voxels, a window wider than 4096 values), but its CTAs - 1024 threads, 128 KB of shared
+    // memory - each claim a whole SM while they are scheduled: a small grid keeps the gate cheap for the frames
+    // running next to this one (the armed case then takes 16 instead of 148 SMs for its one pass over the stack)
+    int fgrid = hist_grid(h, count, 1);
+    if (fgrid > 16) fgrid = 16;
+    TSP_CUDA(launch_chained(hist_percentile_kernel, fgrid, kHistThreads, kHistSmemBytes, s, d_vol, count,
                             hist_full, pedestal, d_status, tickets, d_status + ST_NEED_FULL, 0, q));
     TSP_LAUNCH_CHECK(h);
     return TSP_OK;
