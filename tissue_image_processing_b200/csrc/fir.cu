@@ -470,6 +470,171 @@ static bool fir_yx_fused(tsp_handle* h, const float* d_in, float* d_out, int Z, 
     return true;
 }
 
+// ---- streaming form of the long line filters (radius 9 .. 120: the sigma = 30 passes) ----------------------------
+// The tiled kernels above re-read a 2r-row halo per 128 outputs (3 x the volume at r = 120) and load / compute in
+// turns.  Here a CTA owns its lines for their whole length: a shared-memory RING of 512 line positions, the next 128
+// positions arriving by cp.async while the current 128 outputs are computed - every input is fetched once and the
+// loads hide behind the FMAs.  Ring coordinate rho = position + r, so the first input of an output block sits at a
+// multiple of 16: the 16-input blocks of the register filter never straddle the ring's wrap-around.
+constexpr int kRingLen = 512;                         // line positions in the ring (power of two)
+constexpr int kStreamMaxR = (kRingLen - 128 - kL2Tile - kL2Out) / 2;      // 120
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4s(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+
+// the register filter of line_fir16 reading a ring: block b (16 inputs) starts at ring position (rho0 + 16 b) & 511
+template <typename Index>
+__device__ __forceinline__ void line_fir16_ring(Index at, int rho0, const float2* __restrict__ wsh2, int r,
+                                                float2 (&acc)[kL2Out]) {
+    float2 wc[kL2Out];
+#pragma unroll
+    for (int j = 0; j < kL2Out; ++j) {
+        acc[j] = make_float2(0.f, 0.f);
+        wc[j] = make_float2(0.f, 0.f);
+    }
+    for (int ii = 0; ii < kL2Out + 2 * r; ii += kL2Out) {
+        const float2* blk = at((rho0 + ii) & (kRingLen - 1));
+#pragma unroll
+        for (int u = 0; u < kL2Out; ++u) {
+            wc[u] = wsh2[ii + u];
+            const float2 v = at.step(blk, u);
+#pragma unroll
+            for (int j = 0; j < kL2Out; ++j) acc[j] = __ffma2_rn(v, wc[(u - j + kL2Out) % kL2Out], acc[j]);
+        }
+    }
+}
+
+struct YRingIndex {          // ring[rho][32 column pairs]: a lane owns a column pair
+    const float2* base;      // + lane
+    __device__ __forceinline__ const float2* operator()(int rho) const { return base + (size_t)rho * 32; }
+    __device__ __forceinline__ float2 step(const float2* blk, int u) const { return blk[u * 32]; }
+};
+struct XRingIndex {          // ring[32 row pairs][pitch]: a lane owns a row pair
+    const float2* base;      // + lane * pitch
+    __device__ __forceinline__ const float2* operator()(int rho) const { return base + rho; }
+    __device__ __forceinline__ float2 step(const float2* blk, int u) const { return blk[u]; }
+};
+
+// y pass: CTA = 64 columns of one plane, all rows
+__global__ void __launch_bounds__(32 * kL2Warps)
+fir_y_stream_kernel(const float* __restrict__ in, float* __restrict__ out, int Y, int X, int r,
+                    const float* __restrict__ w32) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* ring = reinterpret_cast<float*>(smem_raw);                           // [512][64]
+    float2* wsh2 = reinterpret_cast<float2*>(ring + (size_t)kRingLen * 64);
+    const int lane = threadIdx.x, warp = threadIdx.y, tid = warp * 32 + lane;
+    const int x0 = blockIdx.x * 64;
+    const size_t zoff = (size_t)blockIdx.z * Y * X;
+    for (int i = tid; i < 2 * r + 1 + 2 * kL2Out; i += 32 * kL2Warps) {
+        const float w = i <= 2 * r ? w32[i] : 0.f;
+        wsh2[i] = make_float2(w, w);
+    }
+    // rows rho in [lo, hi) of the ring <- image rows clamp(rho - r): 16 float4 per row (x0 + 64 <= X, X % 4 == 0)
+    auto fetch = [&](int lo, int hi) {
+        for (int i = tid; i < (hi - lo) * 16; i += 32 * kL2Warps) {
+            const int rho = lo + (i >> 4);
+            const int yy = clampi(rho - r, 0, Y - 1);
+            cp_async16(ring + (size_t)(rho & (kRingLen - 1)) * 64 + 4 * (i & 15), in + zoff + (size_t)yy * X + x0 + 4 * (i & 15));
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const int need = kL2Tile + 2 * r + kL2Out;                                  // inputs of one step
+    fetch(0, need);
+    const int nsteps = (Y + kL2Tile - 1) / kL2Tile;
+    for (int s = 0; s < nsteps; ++s) {
+        const int y0 = s * kL2Tile;
+        __syncthreads();                                  // everyone is done with the rows the next fetch overwrites
+        if (s + 1 < nsteps) fetch(y0 + need, y0 + need + kL2Tile);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");                    // this step's rows have landed
+        __syncthreads();
+        float2 acc[kL2Out];
+        const YRingIndex at{reinterpret_cast<const float2*>(ring) + lane};
+        line_fir16_ring(at, y0 + warp * kL2Out, wsh2, r, acc);
+        const int x = x0 + 2 * lane;
+#pragma unroll
+        for (int j = 0; j < kL2Out; ++j) {
+            const int y = y0 + warp * kL2Out + j;
+            if (y < Y) *reinterpret_cast<float2*>(out + zoff + (size_t)y * X + x) = acc[j];
+        }
+    }
+}
+
+// x pass: CTA = 64 rows (32 pairs) of the flattened (Z*Y) row index, all columns
+__global__ void __launch_bounds__(32 * kL2Warps)
+fir_x_stream_kernel(const float* __restrict__ in, float* __restrict__ out, size_t total_rows, int X, int r,
+                    const float* __restrict__ w32) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int pitch = kRingLen + 1;                                         // odd, in float2 units
+    float2* ring2 = reinterpret_cast<float2*>(smem_raw);                        // [32 row pairs][pitch]
+    float2* wsh2 = ring2 + (size_t)32 * pitch;
+    float* ringf = reinterpret_cast<float*>(ring2);
+    const int lane = threadIdx.x, warp = threadIdx.y, tid = warp * 32 + lane;
+    const size_t row0 = ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 64;
+    if (row0 >= total_rows) return;
+    for (int i = tid; i < 2 * r + 1 + 2 * kL2Out; i += 32 * kL2Warps) {
+        const float w = i <= 2 * r ? w32[i] : 0.f;
+        wsh2[i] = make_float2(w, w);
+    }
+    // columns rho in [lo, hi) <- image columns clamp(rho - r), every row of the CTA: a warp takes rows warp, warp+8, ..
+    auto fetch = [&](int lo, int hi) {
+        for (int rr = warp; rr < 64; rr += kL2Warps) {
+            size_t row = row0 + rr;
+            if (row >= total_rows) row = total_rows - 1;
+            const float* src = in + row * X;
+            float* dst = ringf + ((size_t)(rr >> 1) * pitch) * 2 + (rr & 1);
+            for (int rho = lo + lane; rho < hi; rho += 32)
+                cp_async4s(dst + 2 * (rho & (kRingLen - 1)), src + clampi(rho - r, 0, X - 1));
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const int need = kL2Tile + 2 * r + kL2Out;
+    fetch(0, need);
+    const int nsteps = (X + kL2Tile - 1) / kL2Tile;
+    const size_t ra = row0 + 2 * lane, rb = ra + 1;
+    for (int s = 0; s < nsteps; ++s) {
+        const int xs = s * kL2Tile;
+        __syncthreads();
+        if (s + 1 < nsteps) fetch(xs + need, xs + need + kL2Tile);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncthreads();
+        float2 acc[kL2Out];
+        const XRingIndex at{ring2 + (size_t)lane * pitch};
+        line_fir16_ring(at, xs + warp * kL2Out, wsh2, r, acc);
+        const int xo = xs + warp * kL2Out;
+        const bool vec = (X & 3) == 0 && xo + kL2Out <= X;
+        if (ra < total_rows) {
+            float* da = out + ra * X + xo;
+            if (vec) {
+#pragma unroll
+                for (int q = 0; q < kL2Out / 4; ++q)
+                    reinterpret_cast<float4*>(da)[q] = make_float4(acc[4 * q].x, acc[4 * q + 1].x, acc[4 * q + 2].x, acc[4 * q + 3].x);
+            } else {
+#pragma unroll
+                for (int j = 0; j < kL2Out; ++j)
+                    if (xo + j < X) da[j] = acc[j].x;
+            }
+        }
+        if (rb < total_rows) {
+            float* db = out + rb * X + xo;
+            if (vec) {
+#pragma unroll
+                for (int q = 0; q < kL2Out / 4; ++q)
+                    reinterpret_cast<float4*>(db)[q] = make_float4(acc[4 * q].y, acc[4 * q + 1].y, acc[4 * q + 2].y, acc[4 * q + 3].y);
+            } else {
+#pragma unroll
+                for (int j = 0; j < kL2Out; ++j)
+                    if (xo + j < X) db[j] = acc[j].y;
+            }
+        }
+    }
+}
+
 // z pass: a thread marches one group of four columns through the planes with the 2R+1 inputs it needs in registers:
 // every voxel is read once and written once (the generic kernel re-reads each input 2R+1 times through the caches)
 template <int R>
@@ -520,6 +685,25 @@ int launch_fir_axis(tsp_handle* h, const T* d_in, T* d_out, int Z, int Y, int X,
                 else if (r == 1) fir_z_march_kernel<1><<<blocks, 256, 0, s>>>(fin, fout, Z, plane4, taps.w32);
                 else if (r == 2) fir_z_march_kernel<2><<<blocks, 256, 0, s>>>(fin, fout, Z, plane4, taps.w32);
                 else fir_z_march_kernel<4><<<blocks, 256, 0, s>>>(fin, fout, Z, plane4, taps.w32);
+                TSP_LAUNCH_CHECK(h);
+                return TSP_OK;
+            }
+            if (axis == 1 && r > 8 && r <= kStreamMaxR && X % 64 == 0 && al16 && Y >= kL2Tile) {
+                const size_t smem = (size_t)kRingLen * 64 * sizeof(float) + (size_t)(2 * r + 1 + 2 * kL2Out) * sizeof(float2);
+                TSP_CUDA(cudaFuncSetAttribute(fir_y_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                dim3 grid(X / 64, 1, Z);
+                fir_y_stream_kernel<<<grid, dim3(32, kL2Warps), smem, s>>>(fin, fout, Y, X, r, taps.w32);
+                TSP_LAUNCH_CHECK(h);
+                return TSP_OK;
+            }
+            if (axis == 2 && r > 8 && r <= kStreamMaxR && X >= kL2Tile) {
+                const size_t smem = (size_t)32 * (kRingLen + 1) * sizeof(float2) + (size_t)(2 * r + 1 + 2 * kL2Out) * sizeof(float2);
+                TSP_CUDA(cudaFuncSetAttribute(fir_x_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                const size_t total_rows = (size_t)Z * Y;
+                const size_t groups = (total_rows + 63) / 64;
+                dim3 grid((unsigned)(groups < 32768 ? groups : 32768), 1, 1);
+                grid.y = (unsigned)((groups + grid.x - 1) / grid.x);
+                fir_x_stream_kernel<<<grid, dim3(32, kL2Warps), smem, s>>>(fin, fout, total_rows, X, r, taps.w32);
                 TSP_LAUNCH_CHECK(h);
                 return TSP_OK;
             }
