@@ -122,6 +122,12 @@ def test_host_calls_from_several_threads_and_next_to_a_pipeline(tsp, nat):
     from tissue_image_processing_b200.movie import FramePipeline
     frames = [synth.synth_stack(10, 72, 264, seed=20 + i)[None] for i in range(4)]
     want = [tsp.time_point_surface_projection(f, "TCZYX", 0, airyscan=False, z_map=True) for f in frames]
+    for rep in range(3):                # plain launches, graph capture, graph replay: all the same numbers
+        again = [tsp.time_point_surface_projection(f, "TCZYX", 0, airyscan=False, z_map=True) for f in frames]
+        for i, ((p0, z0), (p1, z1)) in enumerate(zip(want, again)):
+            assert np.array_equal(z0, z1) and np.array_equal(p0, p1), (
+                "repeat %d of frame %d differs: %d height-map pixels, max projection difference %g"
+                % (rep, i, int((z0 != z1).sum()), float(np.abs(p0 - p1).max())))
     errors, results = [], {}
 
     def caller(k):
@@ -130,7 +136,7 @@ def test_host_calls_from_several_threads_and_next_to_a_pipeline(tsp, nat):
                 i = (k + rep) % 4
                 p, z = tsp.time_point_surface_projection(frames[i], "TCZYX", 0, airyscan=False, z_map=True)
                 if not (np.array_equal(p, want[i][0]) and np.array_equal(z, want[i][1])):
-                    errors.append((k, rep))
+                    errors.append((k, rep, i, int((z != want[i][1]).sum()), float(np.abs(p - want[i][0]).max())))
         except Exception as exc:                            # noqa: BLE001
             errors.append(exc)
 

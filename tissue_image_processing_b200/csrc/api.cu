@@ -918,6 +918,10 @@ int tsp_band_project(tsp_handle* h, const uint16_t* d_stack, const int32_t* d_zm
     cudaStream_t s = (cudaStream_t)cuda_stream;
     TSP_CUDA(cudaMemsetAsync(d_workspace, 0, kStatusWords * sizeof(int32_t), s));
     const size_t plane = (size_t)rows * cols;
+    struct PlainLaunches {               // the first kernel follows a memset: no programmatic launches for this call
+        PlainLaunches() { tl_chain_launches = false; }
+        ~PlainLaunches() { tl_chain_launches = true; }
+    } plain;
     return launch_band_project_ex(h, d_stack, (size_t)planes * plane, 0, d_zmap, d_proj, channels, planes, rows,
                                   cols, reference_channel, atoh_shift, airyscan ? kAiryscanPedestal : 0,
                                   (int32_t*)d_workspace, false, s,

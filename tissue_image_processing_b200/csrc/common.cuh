@@ -118,6 +118,22 @@ extern bool g_sync_launches;                     // debugging aid (TSP_SYNC_LAUN
 __device__ __forceinline__ void chain_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void chain_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// launch_after_copy(): the same launch WITHOUT the attribute, for a kernel whose predecessor on the stream is a memset
+// or copy rather than a kernel: there is no prologue to overlap with, and inside a captured graph an early start
+// against a non-kernel node is not something to rely on.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_after_copy(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                     Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cfg.attrs = nullptr;
+    cfg.numAttrs = 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
                                   Args&&... args) {

@@ -696,7 +696,7 @@ int launch_percentile(tsp_handle* h, const uint16_t* d_vol, size_t count, int pe
         TSP_LAUNCH_CHECK(h);
         return TSP_OK;
     }
-    TSP_CUDA(launch_chained(sample_window_kernel, hist_grid(h, count, stride), kHistThreads, 0, s, d_vol, count, stride,
+    TSP_CUDA(launch_after_copy(sample_window_kernel, hist_grid(h, count, stride), kHistThreads, 0, s, d_vol, count, stride,
                             pedestal, hist_sample, d_status, tickets + 1, (uint4*)zero_ptr, zero_bytes / 16, q64));
     TSP_LAUNCH_CHECK(h);
     prof_mark(h, s, STG_PCT_SAMPLE);
