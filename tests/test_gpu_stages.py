@@ -34,6 +34,18 @@ def test_gaussian_blur_f32_bit_exact(nat, sigma, shape):
     np.testing.assert_allclose(got32, want, rtol=3e-6, atol=0)
 
 
+@pytest.mark.parametrize("sigma,shape", [((0.5, 30.0, 30.0), (3, 384, 448)), ((0.5, 30.0, 30.0), (2, 200, 192)),
+                                         ((1.0, 5.0, 11.0), (2, 300, 320)), ((0.5, 2.5, 29.9), (1, 129, 1024))])
+def test_gaussian_blur_f32_streaming_line_filters(nat, sigma, shape):
+    """The fp32 (exact-mode) in-plane passes of radius 9 .. 120 at sizes where the streaming kernels apply (X % 64 == 0,
+    Y >= 128): the 384-position shared-memory ring (full at radius 120, with slack below), lines longer and shorter
+    than one ring, a last step that is only partly inside the image - against scipy's float64 accumulation."""
+    rng = np.random.default_rng(sum(shape))
+    vol = rng.integers(0, 4096, size=shape).astype(np.float32) + rng.random(shape).astype(np.float32)
+    got32 = nat.gaussian_blur(_cuda(vol), sigma, fp64_accumulate=False).cpu().numpy()
+    np.testing.assert_allclose(got32, orc.blur_image(vol, sigma), rtol=3e-6, atol=0)
+
+
 @pytest.mark.parametrize("shape", [(12, 96, 112), (7, 53, 67)])
 def test_gaussian_blur_u16_truncates_like_scipy(nat, shape):
     rng = np.random.default_rng(3)
@@ -161,7 +173,8 @@ def test_band_projection_from_oracle_height_map(nat, shift, ref):
                                                  ((21, 64, 64), 3, 2, False), ((30, 33, 72), 2, -2, True),
                                                  ((44, 160, 192), 1, 0, "gappy"), ((35, 96, 136), 2, 0, "gappy"),
                                                  ((26, 160, 256), 2, 0, "mixed"), ((19, 96, 192), 3, -1, "mixed"),
-                                                 ((6, 64, 128), 1, 0, "mixed"), ((64, 256, 320), 1, 0, False)])
+                                                 ((6, 64, 128), 1, 0, "mixed"), ((64, 256, 320), 1, 0, False),
+                                                 ((40, 160, 256), 1, 0, "steep"), ((48, 192, 320), 2, 1, "steep")])
 def test_band_projection_tma_ring(nat, shape, C, shift, noisy):
     """TMA path of the band stage (X % 8 == 0, tile inside the image): shallow tiles in the register kernel, plane
     ranges deeper than the ring (a noisy height map walks every plane, refilling the ring) through the worklist, one /
@@ -184,6 +197,9 @@ def test_band_projection_tma_ring(nat, shape, C, shift, noisy):
         zmap[40:56, :64] = 1
         zmap[-32:, -64:] = rng.integers(0, hi + 1, size=(32, 64))
         zmap[Y // 2, X // 2] = min(hi, zmap[Y // 2, X // 2] + 3)
+    elif noisy == "steep":         # slope growing with x: tiles spanning 1 .. 5 planes (register kernel) next to
+        yy, xx = np.mgrid[0:Y, 0:X]  # tiles of 6 .. 16 planes (worklist)
+        zmap = np.clip(np.floor(yy * (0.02 + 0.2 * xx / X)).astype(np.int64), 0, hi)
     elif noisy:
         zmap = rng.integers(0, hi + 1, size=(Y, X)).astype(np.int64)
     else:

@@ -472,12 +472,17 @@ static bool fir_yx_fused(tsp_handle* h, const float* d_in, float* d_out, int Z, 
 
 // ---- streaming form of the long line filters (radius 9 .. 120: the sigma = 30 passes) ----------------------------
 // The tiled kernels above re-read a 2r-row halo per 128 outputs (3 x the volume at r = 120) and load / compute in
-// turns.  Here a CTA owns its lines for their whole length: a shared-memory RING of 512 line positions, the next 128
-// positions arriving by cp.async while the current 128 outputs are computed - every input is fetched once and the
-// loads hide behind the FMAs.  Ring coordinate rho = position + r, so the first input of an output block sits at a
-// multiple of 16: the 16-input blocks of the register filter never straddle the ring's wrap-around.
-constexpr int kRingLen = 512;                         // line positions in the ring (power of two)
-constexpr int kStreamMaxR = (kRingLen - 128 - kL2Tile - kL2Out) / 2;      // 120
+// turns.  Here a CTA owns its lines for their whole length: a shared-memory RING of 384 line positions = exactly the
+// inputs of one step of 128 outputs at r = 120 (96 KB: TWO CTAs per SM).  Every input is fetched once (cp.async);
+// the 128 positions of the next step are requested as soon as every warp has finished the current step - they
+// overwrite the 128 oldest - and arrive while the CTA stores its outputs and the SM's other CTA computes: with one
+// 128 KB ring (512 positions, loads behind the CTA's own FMAs) the SM held 8 warps and the FMA pipe idled 24 % of
+// the time (ncu: sm__pipe_fma_cycles_active 76 %, occupancy 12.5 %).  Ring coordinate rho = position + r, so the
+// first input of an output block sits at a multiple of 16: the 16-input blocks of the register filter never
+// straddle the ring's wrap-around (384 = 24 x 16).
+constexpr int kRingLen = 384;                         // line positions in the ring (a multiple of 16)
+constexpr int kStreamMaxR = (kRingLen - kL2Tile - kL2Out) / 2;            // 120
+__device__ __forceinline__ int ring_slot(int rho) { return rho % kRingLen; }
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
@@ -496,8 +501,10 @@ __device__ __forceinline__ void line_fir16_ring(Index at, int rho0, const float2
         acc[j] = make_float2(0.f, 0.f);
         wc[j] = make_float2(0.f, 0.f);
     }
+    int pos = ring_slot(rho0);
     for (int ii = 0; ii < kL2Out + 2 * r; ii += kL2Out) {
-        const float2* blk = at((rho0 + ii) & (kRingLen - 1));
+        const float2* blk = at(pos);
+        pos = pos + kL2Out >= kRingLen ? pos + kL2Out - kRingLen : pos + kL2Out;
 #pragma unroll
         for (int u = 0; u < kL2Out; ++u) {
             wc[u] = wsh2[ii + u];
@@ -520,7 +527,7 @@ struct XRingIndex {          // ring[32 row pairs][pitch]: a lane owns a row pai
 };
 
 // y pass: CTA = 64 columns of one plane, all rows
-__global__ void __launch_bounds__(32 * kL2Warps)
+__global__ void __launch_bounds__(32 * kL2Warps, 2)
 fir_y_stream_kernel(const float* __restrict__ in, float* __restrict__ out, int Y, int X, int r,
                     const float* __restrict__ w32) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -538,23 +545,22 @@ fir_y_stream_kernel(const float* __restrict__ in, float* __restrict__ out, int Y
         for (int i = tid; i < (hi - lo) * 16; i += 32 * kL2Warps) {
             const int rho = lo + (i >> 4);
             const int yy = clampi(rho - r, 0, Y - 1);
-            cp_async16(ring + (size_t)(rho & (kRingLen - 1)) * 64 + 4 * (i & 15), in + zoff + (size_t)yy * X + x0 + 4 * (i & 15));
+            cp_async16(ring + (size_t)ring_slot(rho) * 64 + 4 * (i & 15), in + zoff + (size_t)yy * X + x0 + 4 * (i & 15));
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    const int need = kL2Tile + 2 * r + kL2Out;                                  // inputs of one step
+    const int need = kL2Tile + 2 * r + kL2Out;                                  // inputs of one step (<= kRingLen)
     fetch(0, need);
     const int nsteps = (Y + kL2Tile - 1) / kL2Tile;
     for (int s = 0; s < nsteps; ++s) {
         const int y0 = s * kL2Tile;
-        __syncthreads();                                  // everyone is done with the rows the next fetch overwrites
-        if (s + 1 < nsteps) fetch(y0 + need, y0 + need + kL2Tile);
-        else asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 1;" ::: "memory");                    // this step's rows have landed
+        asm volatile("cp.async.wait_group 0;" ::: "memory");                    // this step's rows have landed
         __syncthreads();
         float2 acc[kL2Out];
         const YRingIndex at{reinterpret_cast<const float2*>(ring) + lane};
         line_fir16_ring(at, y0 + warp * kL2Out, wsh2, r, acc);
+        __syncthreads();                                  // everyone is done with the rows the next fetch overwrites
+        if (s + 1 < nsteps) fetch(y0 + need, y0 + need + kL2Tile);
         const int x = x0 + 2 * lane;
 #pragma unroll
         for (int j = 0; j < kL2Out; ++j) {
@@ -565,7 +571,7 @@ fir_y_stream_kernel(const float* __restrict__ in, float* __restrict__ out, int Y
 }
 
 // x pass: CTA = 64 rows (32 pairs) of the flattened (Z*Y) row index, all columns
-__global__ void __launch_bounds__(32 * kL2Warps)
+__global__ void __launch_bounds__(32 * kL2Warps, 2)
 fir_x_stream_kernel(const float* __restrict__ in, float* __restrict__ out, size_t total_rows, int X, int r,
                     const float* __restrict__ w32) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -588,7 +594,7 @@ fir_x_stream_kernel(const float* __restrict__ in, float* __restrict__ out, size_
             const float* src = in + row * X;
             float* dst = ringf + ((size_t)(rr >> 1) * pitch) * 2 + (rr & 1);
             for (int rho = lo + lane; rho < hi; rho += 32)
-                cp_async4s(dst + 2 * (rho & (kRingLen - 1)), src + clampi(rho - r, 0, X - 1));
+                cp_async4s(dst + 2 * ring_slot(rho), src + clampi(rho - r, 0, X - 1));
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -598,14 +604,13 @@ fir_x_stream_kernel(const float* __restrict__ in, float* __restrict__ out, size_
     const size_t ra = row0 + 2 * lane, rb = ra + 1;
     for (int s = 0; s < nsteps; ++s) {
         const int xs = s * kL2Tile;
-        __syncthreads();
-        if (s + 1 < nsteps) fetch(xs + need, xs + need + kL2Tile);
-        else asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
         float2 acc[kL2Out];
         const XRingIndex at{ring2 + (size_t)lane * pitch};
         line_fir16_ring(at, xs + warp * kL2Out, wsh2, r, acc);
+        __syncthreads();                                  // everyone is done with the columns the next fetch overwrites
+        if (s + 1 < nsteps) fetch(xs + need, xs + need + kL2Tile);
         const int xo = xs + warp * kL2Out;
         const bool vec = (X & 3) == 0 && xo + kL2Out <= X;
         if (ra < total_rows) {

@@ -27,6 +27,40 @@ __global__ void __launch_bounds__(256) probe(float* out, int iters, float a, flo
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// MODE 2: the register-blocked line filter of fir.cu (line_fir16): 16 float2 accumulators, a 16-entry circular window
+// of (w, w) pairs and one input pair per step, both from shared memory - 2 LDS.64 + 16 FFMA2 per input pair.
+// `ctas_per_sm` x 256 threads per SM: how close this very instruction pattern gets to the FFMA2 rate above.
+__global__ void __launch_bounds__(256) probe_line(float* out, int iters, int nblk) {
+    __shared__ float2 tile[(16 * 9) * 32];
+    __shared__ float2 wsh[16 * 17];
+    for (int i = threadIdx.x; i < 16 * 9 * 32; i += 256) tile[i] = make_float2(1e-3f * (i & 63), 2e-3f * (i & 31));
+    for (int i = threadIdx.x; i < 16 * 17; i += 256) wsh[i] = make_float2(1.f / (1 + i), 1.f / (1 + i));
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    float2 acc[16], wc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        acc[j] = make_float2(0.f, 0.f);
+        wc[j] = make_float2(0.f, 0.f);
+    }
+    for (int it = 0; it < iters; ++it) {
+        const float2* col = tile + lane;
+        for (int ii = 0; ii < 16 * nblk; ii += 16) {
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                wc[u] = wsh[ii + u];
+                const float2 v = col[((ii + u) & 127) * 32];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[j] = __ffma2_rn(v, wc[(u - j + 16) % 16], acc[j]);
+            }
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) s += acc[j].x + acc[j].y;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 int main() {
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, 0);
@@ -48,6 +82,19 @@ int main() {
             const double fma = (double)blocks * 256 * iters * 32;
             if (rep) printf("%s: %.3f ms, %.1f TFMA/s (%.1f TFLOP/s), %d SMs\n", mode ? "FFMA2" : "FFMA ", ms, fma / ms / 1e9,
                             2 * fma / ms / 1e9, prop.multiProcessorCount);
+        }
+    }
+    for (int ctas = 1; ctas <= 4; ++ctas) {
+        const int nb = prop.multiProcessorCount * ctas, it2 = 400, nblk = 16;
+        for (int rep = 0; rep < 2; ++rep) {
+            cudaEventRecord(e0);
+            probe_line<<<nb, 256>>>(out, it2, nblk);
+            cudaEventRecord(e1);
+            cudaEventSynchronize(e1);
+            float ms;
+            cudaEventElapsedTime(&ms, e0, e1);
+            const double fma = (double)nb * 256 * it2 * nblk * 16 * 32;
+            if (rep) printf("line filter pattern, %d x 256 threads per SM: %.3f ms, %.1f TFMA/s\n", ctas, ms, fma / ms / 1e9);
         }
     }
     return 0;
