@@ -84,7 +84,11 @@ def _score_with_peak(shape, where, seed, smooth):
     ((7, 23, 31), (11, 15), False), ((7, 23, 31), (0, 0), False), ((7, 23, 31), (22, 30), False),
     ((5, 16, 16), (0, 15), False), ((9, 30, 12), (29, 0), True), ((4, 1, 40), (0, 17), False),
     ((4, 40, 1), (20, 0), False), ((3, 9, 9), (4, 4), False), ((12, 64, 80), (31, 40), True),
-    ((2, 33, 35), (16, 17), False), ((1, 12, 12), (3, 9), False), ((20, 150, 170), (10, 160), True)])
+    ((2, 33, 35), (16, 17), False), ((1, 12, 12), (3, 9), False), ((20, 150, 170), (10, 160), True),
+    # edges longer than one thread walks (composition of the transition tables over 32 runs): random and smooth
+    # scores, start in a corner / on an edge / inside, and more planes than one lane round (P > 32, P > 64)
+    ((6, 300, 420), (150, 200), False), ((40, 260, 300), (0, 0), True), ((200, 130, 140), (129, 70), False),
+    ((70, 200, 333), (100, 332), True)])
 def test_manifold_equals_reference_algorithm(nat, shape, where, smooth):
     """Integer result of a sequential algorithm: must be identical, including the wrap of row -1 (start rows that
     make the left edge span the whole height) and the truncated mean of two-apart neighbours."""

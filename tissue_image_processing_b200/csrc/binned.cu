@@ -260,17 +260,20 @@ __device__ __forceinline__ int mf_neighbour(const MfCtx& m, int row, int col, in
     return col < m.C - 1 ? m.chosen[(size_t)row * m.C + col + 1] : -1;
 }
 
+// first maximum of planes lo .. hi-1 (two or three of them, never more); the loads do not depend on each other: one
+// trip to L2, not three
 __device__ __forceinline__ int mf_argmax_window(const MfCtx& m, int row, int col, int lo, int hi) {
     const float* s = m.score + (size_t)row * m.C + col;
-    float best = s[(size_t)lo * m.plane];
+    const float v0 = s[(size_t)lo * m.plane];
+    const float v1 = lo + 1 < hi ? s[(size_t)(lo + 1) * m.plane] : v0;
+    const float v2 = lo + 2 < hi ? s[(size_t)(lo + 2) * m.plane] : v0;
+    float best = v0;
     int bz = lo;
-    for (int z = lo + 1; z < hi; ++z) {
-        const float v = s[(size_t)z * m.plane];
-        if (v > best) {
-            best = v;
-            bz = z;
-        }
+    if (v1 > best) {
+        best = v1;
+        bz = lo + 1;
     }
+    if (v2 > best) bz = lo + 2;
     return bz;
 }
 
@@ -287,9 +290,22 @@ __device__ __forceinline__ int mf_decide(const MfCtx& m, int row, int col, int f
 
 // One ring segment: `n` cells starting at (r0, c0), stepping (dr, dc).  prev_dir = direction from a cell to the
 // cell visited before it.
+//   phase A (all threads): every cell's rule as a transition table T_k: plane of the predecessor -> plane of the cell;
+//   phase B: the chain c_k = T_k[c_(k-1)].  Function composition is associative, so the chain is cut into 32 runs:
+//            warp w first sends EVERY possible incoming plane through its run (lane = plane, independent lookups:
+//            the composite H_w of its tables), then one lane walks H_0 .. H_(w-1) from the segment's start to find
+//            the plane that really enters run w and follows its own run with it.  Depth n/16 + 31 dependent
+//            shared-memory lookups instead of n (a 2048-cell edge: 159 instead of 2048); short segments keep the
+//            single walk;
+//   phase C (all threads): publish.
+constexpr int kMfSeqCells = 96;              // segments up to this length are walked by one thread
+constexpr int kMfCorners = 32;               // cells per chunk whose table is filled by a whole warp
+
 __device__ void mf_segment(const MfCtx& m, int r0, int c0, int dr, int dc, int n, int prev_dir, unsigned char* tab,
-                           unsigned char* outv, int ppad, int chunk_cells) {
+                           unsigned char* outv, unsigned char* comp, int* corners, int ppad, int chunk_cells) {
     const int tid = threadIdx.x;
+    int& corner_n = corners[0];
+    int* corner_k = corners + 1;
     for (int base = 0; base < n; base += chunk_cells) {
         const int cn = min(chunk_cells, n - base);
         // phase A: transition tables
@@ -309,29 +325,102 @@ __device__ void mf_segment(const MfCtx& m, int r0, int c0, int dr, int dc, int n
                 if (e0 == -2) e0 = v;
                 else if (e1 == -2) e1 = v;
             }
+            // tables are written four entries per 32-bit store; consecutive cells are an odd number of words apart
+            // (ppad / 4 is odd), so the stores of a warp fall into 32 different banks (byte stores at a pitch of
+            // 64 bytes were a 16-way bank conflict: 33 us of a 2048-cell segment)
+            uint32_t* T4 = reinterpret_cast<uint32_t*>(T);
             if (e0 != -3 && e1 != -3) {                     // the predecessor is not consulted: a constant
                 const int r = e0 == -2 ? 0 : mf_decide(m, row, col, e0, e1 == -2 ? -1 : e1);
                 const uint32_t w = 0x01010101u * (uint32_t)r;
-                for (int v = 0; v < ppad; v += 4) *reinterpret_cast<uint32_t*>(T + v) = w;
+                for (int v = 0; v < ppad; v += 4) T4[v >> 2] = w;
             } else if (e1 == -2) {                          // only the predecessor: three-plane window around it
-                for (int v = 0; v < m.P; ++v) T[v] = (unsigned char)mf_decide(m, row, col, v, -1);
+                // (the corner cells of a ring.)  One entry per plane, each an argmax over three planes of the score:
+                // left to this thread they are P dependent trips to L2 (23 us at 64 planes, with the other 1023
+                // threads waiting at the barrier) - the cell goes on a list and a whole warp fills its table below
+                const int slot = atomicAdd(&corner_n, 1);
+                if (slot < kMfCorners) {
+                    corner_k[slot] = k;
+                } else {
+                    for (int v = 0; v < m.P; v += 4) {
+                        uint32_t w = 0;
+                        for (int i = 0; i < 4 && v + i < m.P; ++i) w |= (uint32_t)mf_decide(m, row, col, v + i, -1) << (8 * i);
+                        T4[v >> 2] = w;
+                    }
+                }
             } else {                                        // the predecessor and one plane from memory
+                // the three rules that can fire (SP:153-163) look at planes a-1, a, a+1 only: one round of loads
                 const int a = e0 == -3 ? e1 : e0;
-                const int same = mf_decide(m, row, col, a, a);
-                const int below = a > 0 ? mf_decide(m, row, col, a - 1, a) : 0;        // predecessor at a - 1
-                const int above = a + 1 < m.P ? mf_decide(m, row, col, a + 1, a) : 0;  // predecessor at a + 1
-                for (int v = 0; v < m.P; ++v)
-                    T[v] = (unsigned char)(v == a ? same : v == a - 1 ? below : v == a + 1 ? above : (v + a) >> 1);
+                const float* sp = m.score + (size_t)row * m.C + col;
+                const float s0 = sp[(size_t)a * m.plane];
+                const float sm = a > 0 ? sp[(size_t)(a - 1) * m.plane] : s0;
+                const float s1 = a + 1 < m.P ? sp[(size_t)(a + 1) * m.plane] : s0;
+                int same = a > 0 ? a - 1 : a;                              // mf_decide(a, a): planes a-1 .. a+1
+                {
+                    float best = a > 0 ? sm : s0;
+                    if (a > 0 && s0 > best) { best = s0; same = a; }
+                    if (a + 1 < m.P && s1 > best) same = a + 1;
+                }
+                const int below = a > 0 ? (s0 > sm ? a : a - 1) : 0;       // mf_decide(a - 1, a): planes a-1, a
+                const int above = a + 1 < m.P ? (s1 > s0 ? a + 1 : a) : 0; // mf_decide(a + 1, a): planes a, a+1
+                for (int v = 0; v < m.P; v += 4) {
+                    uint32_t w = 0;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int u = v + i;
+                        const int t = u == a ? same : u == a - 1 ? below : u == a + 1 ? above : (u + a) >> 1;
+                        w |= (uint32_t)(t & 0xff) << (8 * i);
+                    }
+                    T4[v >> 2] = w;
+                }
             }
         }
         __syncthreads();
-        // phase B: one thread follows the chain
-        if (tid == 0) {
-            int c = 0;
-            if (base > 0) c = outv[chunk_cells - 1];        // not used: the first table of a chunk is constant
-            for (int k = 0; k < cn; ++k) {
-                c = tab[(size_t)k * ppad + c];
-                outv[k] = (unsigned char)c;
+        {   // tables of the listed corner cells: warp per cell, lane per plane
+            const int ncorner = min(corner_n, kMfCorners);
+            if (ncorner > 0) {                              // block-uniform
+                for (int e = tid >> 5; e < ncorner; e += kMfThreads / 32) {
+                    const int k = corner_k[e];
+                    const int row = r0 + (base + k) * dr, col = c0 + (base + k) * dc;
+                    for (int v = tid & 31; v < m.P; v += 32) tab[(size_t)k * ppad + v] = (unsigned char)mf_decide(m, row, col, v, -1);
+                }
+                __syncthreads();
+                if (tid == 0) corner_n = 0;
+            }
+        }
+        // phase B (the first table of a chunk is constant: whatever enters it, 0 here, is ignored)
+        if (cn <= kMfSeqCells) {
+            if (tid == 0) {
+                int c = 0;
+                for (int k = 0; k < cn; ++k) {
+                    c = tab[(size_t)k * ppad + c];
+                    outv[k] = (unsigned char)c;
+                }
+            }
+        } else {
+            const int lane = tid & 31, warp = tid >> 5;
+            const int per = (cn + 31) / 32;                  // cells per run
+            const int k0 = min(warp * per, cn), k1 = min(k0 + per, cn);
+            {   // H_warp[v] for every plane v: lane takes v = lane, lane + 32, ... (eight independent chains)
+                int x[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] = min(lane + 32 * i, m.P - 1);
+                for (int k = k0; k < k1; ++k) {
+                    const unsigned char* T = tab + (size_t)k * ppad;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) x[i] = T[x[i]];
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (lane + 32 * i < m.P) comp[warp * ppad + lane + 32 * i] = (unsigned char)x[i];
+            }
+            __syncthreads();
+            if (lane == 0 && k0 < k1) {
+                int c = 0;
+                for (int u = 0; u < warp; ++u) c = comp[u * ppad + c];       // what enters this run
+                for (int k = k0; k < k1; ++k) {
+                    c = tab[(size_t)k * ppad + c];
+                    outv[k] = (unsigned char)c;
+                }
             }
         }
         __syncthreads();
@@ -368,6 +457,9 @@ manifold_kernel(const float* __restrict__ score, int32_t* chosen, int P, int R, 
     extern __shared__ __align__(16) unsigned char mf_smem[];
     unsigned char* tab = mf_smem;
     unsigned char* outv = mf_smem + (size_t)chunk_cells * ppad;
+    unsigned char* comp = outv + chunk_cells;                    // [32 runs][ppad]: composite table of every run
+    __shared__ int corners[1 + kMfCorners];                      // [0]: cells on the list, then their indices
+    if (threadIdx.x == 0) corners[0] = 0;
     MfCtx m;
     m.score = score;
     m.chosen = chosen;
@@ -387,12 +479,12 @@ manifold_kernel(const float* __restrict__ score, int32_t* chosen, int P, int R, 
         // right edge, lower half: rows r0 .. r0+d going down
         if (c0 + d < C) {
             const int last = min(r0 + d, R - 1);
-            mf_segment(m, r0, c0 + d, 1, 0, last - r0 + 1, 0, tab, outv, ppad, chunk_cells);
+            mf_segment(m, r0, c0 + d, 1, 0, last - r0 + 1, 0, tab, outv, comp, corners, ppad, chunk_cells);
         }
         // bottom edge: columns c0+d-1 .. c0-d going left
         if (r0 + d < R) {
             const int first = min(c0 + d - 1, C - 1), last = max(c0 - d, 0);
-            if (first >= last) mf_segment(m, r0 + d, first, 0, -1, first - last + 1, 3, tab, outv, ppad, chunk_cells);
+            if (first >= last) mf_segment(m, r0 + d, first, 0, -1, first - last + 1, 3, tab, outv, comp, corners, ppad, chunk_cells);
         }
         // left edge: rows r0+d-1 .. r0-d going up
         if (c0 - d >= 0) {
@@ -402,19 +494,19 @@ manifold_kernel(const float* __restrict__ score, int32_t* chosen, int P, int R, 
                 // an earlier cell of this very segment - finish the segment at row 1 and do row 0 on its own
                 const bool wrap = last == 0 && first == R - 1 && R > 1;
                 const int n = first - last + 1 - (wrap ? 1 : 0);
-                if (n > 0) mf_segment(m, first, c0 - d, -1, 0, n, 1, tab, outv, ppad, chunk_cells);
+                if (n > 0) mf_segment(m, first, c0 - d, -1, 0, n, 1, tab, outv, comp, corners, ppad, chunk_cells);
                 if (wrap) mf_single(m, 0, c0 - d);
             }
         }
         // top edge: columns c0-d+1 .. c0+d going right
         if (r0 - d >= 0) {
             const int first = max(c0 - d + 1, 0), last = min(c0 + d, C - 1);
-            if (first <= last) mf_segment(m, r0 - d, first, 0, 1, last - first + 1, 2, tab, outv, ppad, chunk_cells);
+            if (first <= last) mf_segment(m, r0 - d, first, 0, 1, last - first + 1, 2, tab, outv, comp, corners, ppad, chunk_cells);
         }
         // right edge, upper half: rows r0-d+1 .. r0-1 going down
         if (c0 + d < C) {
             const int first = max(r0 - d + 1, 0), last = r0 - 1;
-            if (first <= last) mf_segment(m, first, c0 + d, 1, 0, last - first + 1, 0, tab, outv, ppad, chunk_cells);
+            if (first <= last) mf_segment(m, first, c0 + d, 1, 0, last - first + 1, 0, tab, outv, comp, corners, ppad, chunk_cells);
         }
     }
     // height-map range for the band stage's IndexError rule
@@ -452,12 +544,12 @@ int launch_manifold(tsp_handle* h, const float* d_score, int32_t* d_chosen, int 
     if (blocks > (size_t)h->sm_count * 16) blocks = (size_t)h->sm_count * 16;
     argmax3d_kernel<<<(int)blocks, 256, 0, s>>>(d_score, n, best);
     TSP_LAUNCH_CHECK(h);
-    const int ppad = (P + 3) / 4 * 4;
+    const int ppad = ((P + 3) / 4 | 1) * 4;      // bytes per table: whole words, an odd number of them
     int chunk_cells = kMfTableBytes / (ppad + 1);
     const int longest = R > C ? R : C;
     if (chunk_cells > longest) chunk_cells = longest;
     chunk_cells = (chunk_cells + 15) / 16 * 16;
-    const size_t smem = (size_t)chunk_cells * ppad + chunk_cells;
+    const size_t smem = (size_t)chunk_cells * ppad + chunk_cells + (size_t)32 * ppad;
     {
         std::lock_guard<std::mutex> lock(h->mu);
         if (!h->manifold_attr) {
