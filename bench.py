@@ -457,16 +457,20 @@ def run_movie_leg(args, torch, nat, mv, device, index, rank, world, barrier, max
                                         mode=args.mode, frame_pipeline=pipe16)
         barrier()
         job_s = max_over_ranks(time.perf_counter() - t0)
+        job_phases = {k: round(v, 4) for k, v in sp.last_job_timings.items()}
         # the projection part alone (project_movie: read, stage, project, gather on rank 0), without the driver's
         # np.save / np.load / concatenate of the resume files
-        proj = np.zeros((MOVIE_FRAMES, 1, 1, Ym, Xm), dtype=np.uint16)
-        zmap = np.zeros((MOVIE_FRAMES, 1, 1, Ym, Xm), dtype=np.uint16)
+        outs = mv.allocate_outputs([((MOVIE_FRAMES, 1, 1, Ym, Xm), np.uint16), ((MOVIE_FRAMES, 1, 1, Ym, Xm), np.uint16)])
+        proj, zmap = outs.arrays
         barrier()
         t0 = time.perf_counter()
         pipe16.project_movie("bench_movie.czi", 0, proj, zmap, gather="root", reference_channel=0, airyscan=False,
                              atoh_shift=0, min_z=0, max_z=0)
         barrier()
         proj_s = max_over_ranks(time.perf_counter() - t0)
+        shared_outputs = outs.shared
+        del proj, zmap
+        outs.close()
     finally:
         bim.open_image, sp.tiff_writer = old_open, old_writer
         if rank == 0:
@@ -476,8 +480,11 @@ def run_movie_leg(args, torch, nat, mv, device, index, rank, world, barrier, max
             "fixed_job": {"frames": MOVIE_FRAMES, "scaling": "strong",
                           "api": "movie_surface_projection(files, ..., frame_pipeline=FramePipeline(out_dtype='uint16')) on an "
                                  "in-memory image source whose frames are ordinary (pageable) arrays: staged into pinned "
-                                 "buffers by host threads, projected, uint16 on the device, assembled on rank 0, resume "
-                                 ".npy files + TIFF hook + zmap written by rank 0",
+                                 "buffers by host threads, projected, uint16 on the device, scattered by every rank into "
+                                 "the job's output arrays (one shared-memory mapping on a single host; gloo assembly "
+                                 "otherwise), resume .npy files + TIFF hook + zmap written by rank 0",
+                          "shared_output_arrays": bool(shared_outputs),
+                          "rank0_phase_seconds": job_phases,
                           "seconds": job_s, "frames_per_s": MOVIE_FRAMES / job_s,
                           "projection_seconds": proj_s, "projection_frames_per_s": MOVIE_FRAMES / proj_s,
                           "outputs": written[-1:] if rank == 0 else None},

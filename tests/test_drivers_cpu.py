@@ -84,10 +84,12 @@ def test_frame_partition_is_a_partition():
         assert counts.max() - counts.min() <= 1
 
 
-def _gloo_worker(rank, world, port, tmp):
+def _gloo_worker(rank, world, port, tmp, shared):
     import torch.distributed as dist
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    if not shared:
+        os.environ["TSP_NO_SHARED_OUTPUTS"] = "1"
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from tests.fake_image import FakeAICSImage, install
     from tissue_image_processing_b200 import basic_image_manipulations as bim
@@ -119,15 +121,45 @@ def _gloo_worker(rank, world, port, tmp):
     if rank == 0:
         np.save(os.path.join(tmp, "tif1.npy"), written[os.path.join(out, "position1.tif")][0])
         np.save(os.path.join(tmp, "tif2.npy"), written[os.path.join(out, "position2.tif")][0])
+    # the job's output arrays: one mapping shared by the ranks of a single-host job (no assembly step), per-rank
+    # arrays + gloo otherwise; nothing may stay behind in /dev/shm
+    from tissue_image_processing_b200 import movie as mv
+    outs = mv.allocate_outputs([((3, 4), np.uint16), ((2, 2), np.float64)])
+    assert outs.shared == (shared and os.path.isdir("/dev/shm")), outs.shared
+    a, b = outs.arrays
+    assert a.dtype == np.uint16 and b.dtype == np.float64 and not a.any() and not b.any()
+    dist.barrier(group=mv.host_group())                   # (everyone has seen the zeros)
+    a[rank] = rank + 1                                    # both ranks write their own row ...
+    assert mv.finish_outputs([a, b], [rank]) == (rank == 0 or outs.shared)
+    if rank == 0:                                         # ... and rank 0 holds both afterwards, either way
+        assert a[0, 0] == 1 and a[1, 0] == 2 and a[2, 0] == 0
+    mv.host_group() and dist.barrier(group=mv.host_group())
+    outs.close()
+    # the tiled driver under two ranks: tiles claimed from the shared counter, assembled on rank 0
+    big = synth.synth_stack(6, 40, 48, C=2, seed=9)[None]
+    install(bim, {os.path.join(tmp, "big.tif"): FakeAICSImage([big])})
+    open(os.path.join(tmp, "big.tif"), "a").close()
+    written.clear()
+    pipe_ref = FramePipeline(operator=orc.time_point_surface_projection)
+    sp.large_image_projection(tmp, out, "big.tif", position=1, reference_channel=0, chunk_size=24, airyscan=False,
+                              frame_pipeline=pipe_ref)
+    if rank == 0:
+        np.save(os.path.join(tmp, "big_tif.npy"), written[os.path.join(out, "big_projection.tif")][0])
+    dist.barrier(group=mv.host_group())
+    if rank == 0:
+        left = [f for f in os.listdir("/dev/shm") if f.startswith("tsp_b200_out_")] if os.path.isdir("/dev/shm") else []
+        assert left == [], left
     dist.destroy_process_group()
 
 
-def test_movie_partition_world_size_2_gloo(tmp_path):
+@pytest.mark.parametrize("shared", [True, False], ids=["shared_outputs", "gloo_assembly"])
+def test_movie_partition_world_size_2_gloo(tmp_path, shared):
     """Two ranks each project the time points they claim from the shared counter; assembling the arrays is the
-    only exchange.  The operator is the oracle here - this checks the host logic, not the kernels."""
+    only exchange (none at all when the job's output arrays are one shared mapping).  The operator is the oracle
+    here - this checks the host logic, not the kernels."""
     import torch.multiprocessing as mp
-    port = 29500 + os.getpid() % 2000
-    mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    port = 29500 + (os.getpid() + (7 if shared else 0)) % 2000
+    mp.spawn(_gloo_worker, args=(2, port, str(tmp_path), shared), nprocs=2, join=True)
     movie = np.stack([synth.synth_stack(6, 24, 28, C=2, seed=3, t=t) for t in range(5)])
     claims = np.concatenate([np.load(tmp_path / ("claims%d.npy" % r)) for r in range(2)])
     assert sorted(claims.tolist()) == list(range(37))
@@ -148,12 +180,66 @@ def test_movie_partition_world_size_2_gloo(tmp_path):
     assert np.array_equal(np.load(tmp_path / "tif1.npy"), np.stack(want1))
     assert np.array_equal(np.load(tmp_path / "tif2.npy"), np.stack(want2))
     left = sorted(os.listdir(tmp_path / "driver"))
-    assert left == ["stage_locations_position1.pkl", "stage_locations_position2.pkl", "zmap_position1.npy",
-                    "zmap_position2.npy"], left
+    assert left == ["big_zmap.npy", "stage_locations_position1.pkl", "stage_locations_position2.pkl",
+                    "zmap_position1.npy", "zmap_position2.npy"], left
+    # tiled driver: four independent 24 x 24 (x 20 / 24) tiles, each with its own percentile and edges (BIM:104-149)
+    big = synth.synth_stack(6, 40, 48, C=2, seed=9)[None]
+    want_zmap = np.zeros((40, 48))
+    want_proj = np.zeros((2, 40, 48))
+    for y0 in (0, 24):
+        for x0 in (0, 24):
+            p, z = orc.time_point_surface_projection(big[:, :, :, y0:y0 + 24, x0:x0 + 24], "TCZYX", 0, airyscan=False,
+                                                     z_map=True)
+            want_proj[:, y0:y0 + 24, x0:x0 + 24] = p
+            want_zmap[y0:y0 + 24, x0:x0 + 24] = z
+    assert np.array_equal(np.load(tmp_path / "driver" / "big_zmap.npy")[0], want_zmap)
+    want_u16 = np.round(want_proj / want_proj.max() * 65535).astype("uint16")
+    assert np.array_equal(np.load(tmp_path / "big_tif.npy"), want_u16)
     import pickle
     with open(tmp_path / "driver" / "stage_locations_position1.pkl", "rb") as f:
         assert len(pickle.load(f)["x"]) == 8
     assert np.load(tmp_path / "driver" / "zmap_position1.npy").shape == (8, 1, 1, 24, 28)
+
+
+def test_movie_driver_resumes_after_an_interrupted_run(monkeypatch, tmp_path):
+    """SP:193-200: a (movie, position) job whose two resume files exist is not projected again.  The files of every
+    job but the last are written as soon as the job is done (the last job's would be deleted a moment later by the
+    clean-up, they are not written); a run that dies in the final TIFF write restarts at the last job only."""
+    from tissue_image_processing_b200 import basic_image_manipulations as bim
+    from tissue_image_processing_b200 import surface_projection as sp
+    from tissue_image_processing_b200.movie import FramePipeline
+    m1 = np.stack([synth.synth_stack(5, 16, 20, C=1, seed=1, t=t) for t in range(3)])
+    m2 = np.stack([synth.synth_stack(5, 16, 20, C=1, seed=2, t=t) for t in range(2)])
+    install(monkeypatch, {"m1.czi": FakeAICSImage([m1]), "m2.czi": FakeAICSImage([m2])})
+    calls = []
+
+    def operator(chunk, **kw):
+        calls.append(int(chunk.sum()))
+        return _toy_operator(chunk)
+
+    def run(out, writer):
+        monkeypatch.setattr(sp, "tiff_writer", writer)
+        sp.movie_surface_projection(["m1.czi", "m2.czi"], 0, [2], 1, str(out), "max_averages", 1, False, 0, 0, 0, False,
+                                    frame_pipeline=FramePipeline(operator=operator, out_dtype="uint16"))
+
+    clean, broken = tmp_path / "clean", tmp_path / "broken"
+    clean.mkdir()
+    broken.mkdir()
+    kept = {}
+    run(clean, lambda path, image, axes, metadata: kept.update(clean=np.array(image)))
+    assert len(calls) == 5 and kept["clean"].shape == (5, 1, 16, 20)
+
+    def dies(path, image, axes, metadata):
+        raise OSError("disk full")
+    with pytest.raises(OSError):
+        run(broken, dies)
+    assert sorted(os.listdir(broken)) == ["position0_movie0_projection.npy", "position0_movie0_zmap.npy"]
+    del calls[:]
+    run(broken, lambda path, image, axes, metadata: kept.update(resumed=np.array(image)))
+    assert len(calls) == 2                                   # only the two frames of the second movie
+    assert np.array_equal(kept["resumed"], kept["clean"])
+    assert np.array_equal(np.load(broken / "zmap_position1.npy"), np.load(clean / "zmap_position1.npy"))
+    assert sorted(os.listdir(broken)) == sorted(os.listdir(clean)) == ["stage_locations_position1.pkl", "zmap_position1.npy"]
 
 
 def test_cli_flags_and_dispatch(monkeypatch, tmp_path):

@@ -24,15 +24,17 @@ from __future__ import annotations
 
 import os
 import pickle
+import time
 
 import numpy as np
 
 from . import _native
 from . import basic_image_manipulations as bim
 from .basic_image_manipulations import put_channel_axis_first, read_image_in_chunks  # noqa: F401
-from .movie import as_uint16_stack, rank_world
+from .movie import allocate_outputs, as_uint16_stack, finish_outputs, rank_world
 
 DEFAULT_MODE = os.environ.get("TSP_MODE", "fast")
+last_job_timings = {}        # seconds of the last movie_surface_projection call on this rank, by phase (diagnostics)
 
 
 def _as_uint16_stack(image):
@@ -221,10 +223,11 @@ def movie_surface_projection(files, reference_channel, position_final_movie, ini
     frames_of = {p: 0 for p in chosen}
     resume = {p: ([], []) for p in range(initial_positions_number)}
     fresh = {}                                         # arrays computed in this run: no need to read them back
+    outputs = []                                       # their backing (shared by the ranks of a single-host job)
     dims_of = {}
-    for f, series, position in movie_schedule(len(files), position_final_movie, initial_positions_number):
-        if position not in chosen:
-            continue
+    timings = {"project_s": 0.0, "resume_save_s": 0.0, "assemble_write_s": 0.0}
+    jobs = [job for job in movie_schedule(len(files), position_final_movie, initial_positions_number) if job[2] in chosen]
+    for job_index, (f, series, position) in enumerate(jobs):
         if f not in dims_of:
             dims_of[f] = bim.get_image_dimensions(files[f])
         dims = dims_of[f]
@@ -241,16 +244,25 @@ def movie_surface_projection(files, reference_channel, position_final_movie, ini
         if done:
             continue
         reference_channel = min(reference_channel, dims.C - 1)       # SP:203-204 (sticks for the later jobs too)
-        proj = np.zeros((dims.T, dims.C, 1, dims.Y, dims.X), dtype=out_dtype)
-        zmap = np.zeros((dims.T, 1, 1, dims.Y, dims.X), dtype=out_dtype)
+        outputs.append(allocate_outputs([((dims.T, dims.C, 1, dims.Y, dims.X), out_dtype),
+                                         ((dims.T, 1, 1, dims.Y, dims.X), out_dtype)]))
+        proj, zmap = outputs[-1].arrays
+        t0 = time.perf_counter()
         pipeline.project_movie(files[f], series, proj, zmap, mode=mode, gather="root",
                                reference_channel=reference_channel, method=method, bin_size=bin_size, atoh_shift=0,
                                build_manifold=build_manifold, min_z=zmin, max_z=zmax, airyscan=airyscan)
+        timings["project_s"] += time.perf_counter() - t0
         if root:
+            t0 = time.perf_counter()
             fresh[proj_path] = proj.reshape((dims.T, dims.C, dims.Y, dims.X))
             fresh[zmap_path] = zmap
-            np.save(proj_path, fresh[proj_path])
-            np.save(zmap_path, zmap)
+            # the resume files of SP:193-194 exist to restart an interrupted run at the next job; those of the very
+            # last job would be deleted a moment later by the clean-up below (SP:235-237) - they are not written
+            if job_index + 1 < len(jobs):
+                np.save(proj_path, fresh[proj_path])
+                np.save(zmap_path, zmap)
+            timings["resume_save_s"] += time.perf_counter() - t0
+    t0 = time.perf_counter()
     if root:
         for position in chosen:
             proj_files, zmap_files = resume[position]
@@ -265,8 +277,15 @@ def movie_surface_projection(files, reference_channel, position_final_movie, ini
                              only_position=only_position, output_name=output_name)
         for proj_files, zmap_files in resume.values():
             for path in proj_files + zmap_files:
-                os.remove(path)
+                if os.path.exists(path):
+                    os.remove(path)
+    timings["assemble_write_s"] = time.perf_counter() - t0
     _job_barrier()                                     # nobody returns before the outputs are on disk
+    last_job_timings.clear()
+    last_job_timings.update(timings)
+    fresh.clear()
+    for out in outputs:
+        out.close()
 
 
 def _broadcast_flag(flag):
@@ -303,13 +322,14 @@ def large_image_projection(input_dir, output_dir, input_file_name, position=1, r
     dims = bim.get_image_dimensions(path)
     postfix = '.' + input_file_name.split('.')[-1]
     for pos in (position if many else [position]):
-        projection = np.zeros((dims.T, dims.C, 1, dims.Y, dims.X))
-        zmap = np.zeros((dims.T, 1, 1, dims.Y, dims.X))
+        outputs = allocate_outputs([((dims.T, dims.C, 1, dims.Y, dims.X), np.float64),
+                                    ((dims.T, 1, 1, dims.Y, dims.X), np.float64)])
+        projection, zmap = outputs.arrays
         img = bim.open_image(path)
         img.set_scene(int(pos - 1))
         data = img.get_image_dask_data()
         tiles = [(t,) + tile for t in range(dims.T) for tile in _tiles(dims.Y, dims.X, chunk_size)]
-        from .movie import SharedFrameCounter, gather_frames
+        from .movie import SharedFrameCounter
         counter = SharedFrameCounter("tiles")
         mine = []
 
@@ -328,7 +348,9 @@ def large_image_projection(input_dir, output_dir, input_file_name, position=1, r
         pipeline.project_frames(source(), sink, mode=mode, reference_channel=reference_channel, min_z=min_z,
                                 max_z=max_z, method=method, bin_size=bin_size, atoh_shift=channels_shift,
                                 build_manifold=build_manifold, airyscan=airyscan)
-        if _multi_rank():
+        if outputs.shared:
+            finish_outputs([projection, zmap], mine)   # every rank wrote its tiles into the job's arrays: a barrier
+        elif _multi_rank():
             # tiles are scattered inside frames: ship whole arrays of the tiles' frames as a sum of disjoint parts
             _merge_disjoint([projection, zmap])
         if rank == 0:
@@ -338,6 +360,7 @@ def large_image_projection(input_dir, output_dir, input_file_name, position=1, r
                       axes="TCYX" if dims.T > 1 else "CYX", data_type="uint16")
             np.save(os.path.join(output_dir, input_file_name.replace(postfix, tag + "_zmap.npy")),
                     zmap.reshape((dims.T, dims.Y, dims.X)))
+        outputs.close()                                # rank 0 has saved the arrays: their backing can go
     _job_barrier()
 
 
