@@ -382,7 +382,12 @@ class FramePipeline:
         self.devices = list(devices) if devices is not None else [0]
         self.slots = max(1, min(int(slots), _native.MAX_SLOTS))
         if copy_threads is None:
-            copy_threads = max(1, min(8, len(os.sched_getaffinity(0)) // max(1, len(self.devices))))
+            # measured on the 16-CPU B200 box (tools/staging_probe.py, one 96 MiB frame into pinned memory): 1 thread
+            # 13.8 GB/s, 8 threads 33.8, 16 threads 48.2 - the host link takes 47-54: the CPUs this process can use,
+            # shared with the other GPUs it feeds and with the other ranks of the node, up to 16
+            local_world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")) or 1)
+            share = max(1, len(self.devices)) * max(1, local_world)
+            copy_threads = max(1, min(16, len(os.sched_getaffinity(0)) // share))
         self.copy_threads = int(copy_threads)
         self.h2d_bytes = 0                       # bytes handed to the GPUs so far (bench.py reports GB/s from it)
 
