@@ -336,6 +336,10 @@ class _Staging:
         except (TypeError, ValueError, RuntimeError):
             return False
 
+    def owns(self, slot, arr):
+        """True when ``arr`` is the staging buffer of ``slot`` (False: the frame was pinned already and passed through)."""
+        return self.bufs[slot] is not None and arr is self.bufs[slot]
+
     def stage(self, slot, stack):
         """-> C-contiguous uint16 (C,Z,Y,X) array in pinned memory holding ``stack`` (itself when already pinned)."""
         stack = as_uint16_stack(stack)
@@ -411,38 +415,78 @@ class FramePipeline:
 
     def _run_device(self, device, frames, params, sink):
         """frames: iterable of (key, stack) with stack a uint8/uint16 (C,Z,Y,X) host array.
-        sink(key, proj (C,Y,X), zmap (Y,X), status)."""
+        sink(key, proj (C,Y,X), zmap (Y,X), status).
+
+        Two host threads: a feeder reads the next frame and copies it into a free pinned staging buffer (slots + 2 of
+        them: one per frame in flight, one in this thread's hands, one being filled) while this thread submits staged
+        frames to the GPU's frame slots, waits for finished ones and hands them to ``sink`` - reading / staging frame
+        t+1 overlaps everything else of frames t, t-1.  The feeder inherits the CPU affinity of the thread that runs
+        this method (its staging buffers are first touched next to the GPU)."""
         kw = self._operator_kwargs(params, device)
         pdt, zdt = (np.uint16, np.uint16) if self.out_dtype == "uint16" else (np.float64, np.int64)
-        inflight = [None] * self.slots          # (key, pinned stack, proj, zmap) per slot
+        inflight = [None] * self.slots          # (key, pinned stack, staging id, proj, zmap) per slot
         bufs = [None] * self.slots              # pinned output buffers per slot, reused while the shape holds
-        staging = _Staging(self.slots, self.copy_threads)
+        nstage = self.slots + 2
+        staging = _Staging(nstage, self.copy_threads)
+        free_ids = queue.Queue()
+        for b in range(nstage):
+            free_ids.put(b)
+        staged = queue.Queue(maxsize=nstage)
+        stop = threading.Event()
+
+        def feeder():
+            try:
+                for key, stack in frames:
+                    b = None
+                    while b is None:
+                        if stop.is_set():
+                            return
+                        try:
+                            b = free_ids.get(timeout=0.1)
+                        except queue.Empty:
+                            pass
+                    staged.put((key, staging.stage(b, stack), b, None))
+                staged.put(None)
+            except BaseException as exc:                 # noqa: BLE001 - re-raised by the consumer
+                staged.put((None, None, None, exc))
 
         def drain(slot):
             if inflight[slot] is None:
                 return
-            key, _, proj, zmap = inflight[slot]
+            key, pinned, b, proj, zmap = inflight[slot]
             status = _native.frame_wait(slot, device)
             inflight[slot] = None
+            if b is not None:
+                free_ids.put(b)
             sink(key, proj, zmap, status)
 
+        th = threading.Thread(target=feeder, daemon=True)
+        th.start()
         i = 0
         try:
-            for key, stack in frames:
+            while True:
+                item = staged.get()
+                if item is None:
+                    break
+                key, pinned, b, exc = item
+                if exc is not None:
+                    raise exc
                 slot = i % self.slots
                 drain(slot)
-                pinned = staging.stage(slot, stack)
                 Cn, _, Y, X = pinned.shape
                 if bufs[slot] is None or bufs[slot][0].shape != (Cn, Y, X):
                     bufs[slot] = (_native.pinned_empty((Cn, Y, X), pdt), _native.pinned_empty((Y, X), zdt))
                 proj, zmap = bufs[slot]
                 _native.frame_submit(slot, pinned, proj, zmap, **kw)
                 self.h2d_bytes += pinned.nbytes
-                inflight[slot] = (key, pinned, proj, zmap)
+                inflight[slot] = (key, pinned, b if staging.owns(b, pinned) else None, proj, zmap)
+                if inflight[slot][2] is None:
+                    free_ids.put(b)                  # the frame was already pinned: its staging buffer was not used
                 i += 1
             for k in range(self.slots):
                 drain((i + k) % self.slots)
         finally:
+            stop.set()
             for slot in range(self.slots):           # never leave a slot busy behind an exception
                 if inflight[slot] is not None:
                     try:
@@ -450,6 +494,12 @@ class FramePipeline:
                     except Exception:                # noqa: BLE001
                         pass
                     inflight[slot] = None
+            while th.is_alive():                     # unblock a feeder waiting on a full queue
+                try:
+                    staged.get_nowait()
+                except queue.Empty:
+                    pass
+                th.join(timeout=0.05)
             staging.close()
 
     # ---- public ------------------------------------------------------------------------------------
