@@ -601,6 +601,19 @@ def run_gpu(args, rank, world, local_rank):
         p64, z64 = tsp.time_point_surface_projection(host_frames[i % nframes], "TCZYX", **kw)
     barrier()
     single_s = max_over_ranks(time.perf_counter() - t0)
+    # the same call on an ordinary (pageable) numpy array - what a reader hands to the reference's operator: the
+    # library stages it through pinned chunks with a pool of host threads (api.cu: staged_copy_in)
+    pageable_frame = np.array(host_frames[0])
+    for i in range(2):
+        tsp.time_point_surface_projection(pageable_frame, "TCZYX", **kw)
+    barrier()
+    t0 = time.perf_counter()
+    nsingle = max(3, args.steps // 4)
+    for i in range(nsingle):
+        p64, z64 = tsp.time_point_surface_projection(pageable_frame, "TCZYX", **kw)
+    barrier()
+    single_pageable_s = max_over_ranks(time.perf_counter() - t0) / nsingle
+    del pageable_frame
     # the movie API: same frames through the slot pipeline (copy-in of frame t+1 overlaps the kernels of frame t)
     pipe = mv.FramePipeline(devices=[index], slots=args.slots, mode=args.mode)
     checksum = [0.0]
@@ -681,7 +694,10 @@ def run_gpu(args, rank, world, local_rank):
                 "h2d_gbs_total": round(world * args.steps * vox * 2 / e2e_s / 1e9, 1),
                 "host_link_probe_gbs": topo.get("probe_gbs"),
                 "single_call_ms": single_s * 1e3 / args.steps,
-                "single_call_api": "time_point_surface_projection(frame, 'TCZYX', ...) one blocking call per frame"},
+                "single_call_api": "time_point_surface_projection(frame, 'TCZYX', ...) one blocking call per frame "
+                                   "(frame in pinned memory); single_call_pageable_ms: the same call on an ordinary "
+                                   "numpy array",
+                "single_call_pageable_ms": single_pageable_s * 1e3},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": stage_kernel.get(dom, dom), "stage": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,

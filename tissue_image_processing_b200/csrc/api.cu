@@ -1,5 +1,10 @@
 // C ABI of libtsp_b200 (see include/tsp_b200.h for the reference interfaces each entry replaces).
+#include <sched.h>
 #include <stdarg.h>
+
+#include <algorithm>
+#include <condition_variable>
+#include <thread>
 
 #include "common.cuh"
 
@@ -16,6 +21,8 @@ void set_error(const char* fmt, ...) {
 
 thread_local bool tl_chain_launches = true;
 std::atomic<bool> g_no_chain{false};
+std::atomic<int> g_chain_plain_mask{0};
+thread_local int tl_chain_site = 0;
 bool g_sync_launches = false;
 
 static const char* kStageNames[STG_COUNT] = {"percentile", "decimate", "coarse", "interp_argmax", "prepare",
@@ -212,6 +219,117 @@ static Workspace carve(const tsp_frame_desc* d, const Crop& c, const Params& pr,
     return w;
 }
 
+// ---- host buffers in pageable memory --------------------------------------------------------------
+// cudaMemcpyAsync from pageable memory is staged by the driver on one thread: 11 GB/s measured on the B200 box, 47 ms
+// for a 512 MiB stack the link moves in 10.  A caller of the reference's operator hands over whatever its reader
+// returned (an ordinary numpy array), so the library stages such a stack itself: 32 MiB chunks go through a ring of
+// pinned buffers, each chunk copied by a pool of host threads (48 GB/s on 16 threads) while the DMA of the chunk
+// before it runs.  Pinned / registered buffers take the direct path.
+struct CopyPool {
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    char* dst = nullptr;
+    const char* src = nullptr;
+    size_t bytes = 0, pending = 0;
+    uint64_t generation = 0;
+    bool quit = false;
+
+    explicit CopyPool(int n) {
+        for (int i = 0; i < n; ++i) workers.emplace_back([this, i] { loop(i); });
+    }
+    ~CopyPool() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            quit = true;
+        }
+        cv_work.notify_all();
+        for (auto& t : workers) t.join();
+    }
+    void copy(void* d, const void* s, size_t n) {
+        if (workers.size() < 2 || n < ((size_t)1 << 20)) {
+            memcpy(d, s, n);
+            return;
+        }
+        std::unique_lock<std::mutex> lk(mu);
+        dst = (char*)d;
+        src = (const char*)s;
+        bytes = n;
+        pending = workers.size();
+        ++generation;
+        cv_work.notify_all();
+        cv_done.wait(lk, [&] { return pending == 0; });
+    }
+    void loop(int i) {
+        uint64_t seen = 0;
+        for (;;) {
+            std::unique_lock<std::mutex> lk(mu);
+            cv_work.wait(lk, [&] { return quit || generation != seen; });
+            if (quit) return;
+            seen = generation;
+            char* d = dst;
+            const char* s = src;
+            const size_t n = bytes, parts = workers.size();
+            lk.unlock();
+            const size_t per = ((n + parts - 1) / parts + 4095) & ~(size_t)4095;
+            const size_t lo = std::min(n, (size_t)i * per), hi = std::min(n, lo + per);
+            if (hi > lo) memcpy(d + lo, s + lo, hi - lo);
+            lk.lock();
+            if (--pending == 0) cv_done.notify_one();
+        }
+    }
+};
+
+static int env_int_or(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+static int copy_pool_threads() {
+    int n = env_int_or("TSP_COPY_THREADS", 0);
+    if (n <= 0) {
+        cpu_set_t set;
+        CPU_ZERO(&set);
+        int cpus = sched_getaffinity(0, sizeof set, &set) == 0 ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
+        int share = env_int_or("LOCAL_WORLD_SIZE", 1);          // the ranks of a torchrun node share its CPUs
+        if (share < 1) share = 1;
+        n = cpus / share;
+    }
+    return n < 1 ? 1 : (n > 16 ? 16 : n);
+}
+
+static bool host_pointer_is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+constexpr size_t kStageChunk = (size_t)32 << 20;
+
+// d_dst[0, bytes) <- pageable h_src, enqueued on `s`; returns when the last chunk has been handed to the DMA engine
+static int staged_copy_in(tsp_handle* h, tsp_handle::Slot& sl, char* d_dst, const char* h_src, size_t bytes,
+                          cudaStream_t s) {
+    if (!h->copy_pool) h->copy_pool = new CopyPool(copy_pool_threads());
+    const int ring = tsp_handle::Slot::kStageRing;
+    for (int b = 0; b < ring; ++b) {
+        if (!sl.stage[b]) TSP_CUDA(cudaMallocHost(&sl.stage[b], kStageChunk));
+        if (!sl.stage_ev[b]) TSP_CUDA(cudaEventCreateWithFlags(&sl.stage_ev[b], cudaEventDisableTiming));
+    }
+    size_t off = 0;
+    for (int c = 0; off < bytes; ++c, off += kStageChunk) {
+        const int b = c % ring;
+        const size_t n = std::min(kStageChunk, bytes - off);
+        if (c >= ring) TSP_CUDA(cudaEventSynchronize(sl.stage_ev[b]));        // the DMA that read this buffer is done
+        h->copy_pool->copy(sl.stage[b], h_src + off, n);
+        TSP_CUDA(cudaMemcpyAsync(d_dst + off, sl.stage[b], n, cudaMemcpyHostToDevice, s));
+        TSP_CUDA(cudaEventRecord(sl.stage_ev[b], s));
+    }
+    return TSP_OK;
+}
+
 }  // namespace tsp
 
 using namespace tsp;
@@ -268,6 +386,7 @@ int tsp_debug_set(tsp_handle* h, const char* key, int value) {
     else if (!strcmp(key, "band_variant") && (value == 0 || value == 2 || value == 3)) h->dbg.band_variant = value;
     else if (!strcmp(key, "interp_rows") && (value == 2 || value == 4 || value == 8)) h->dbg.interp_rows = value;
     else if (!strcmp(key, "no_chain")) g_no_chain.store(value != 0);
+    else if (!strcmp(key, "chain_plain_mask")) g_chain_plain_mask.store(value);
     else if (!strcmp(key, "graphs")) h->dbg.graphs = value != 0;
     else if (!strcmp(key, "interp_global")) h->dbg.interp_global = value != 0;
     else {
@@ -290,8 +409,13 @@ int tsp_destroy(tsp_handle* h) {
         if (sl.stream) cudaStreamSynchronize(sl.stream);
         if (sl.d_mem) cudaFree(sl.d_mem);
         if (sl.h_status) cudaFreeHost(sl.h_status);
+        for (int b = 0; b < tsp_handle::Slot::kStageRing; ++b) {
+            if (sl.stage[b]) cudaFreeHost(sl.stage[b]);
+            if (sl.stage_ev[b]) cudaEventDestroy(sl.stage_ev[b]);
+        }
         if (sl.stream) cudaStreamDestroy(sl.stream);
     }
+    delete h->copy_pool;
     for (auto& g : h->graphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
     if (h->capture_stream) cudaStreamDestroy(h->capture_stream);
@@ -329,7 +453,7 @@ static int project_frame_eager(tsp_handle* h, const tsp_frame_desc* desc, const 
         return TSP_ERR_WORKSPACE;
     }
     struct ChainScope {          // launches happen on this thread: the flag covers exactly this frame's kernels
-        explicit ChainScope(bool on) { tl_chain_launches = on; }
+        explicit ChainScope(bool on) { tl_chain_launches = on; tl_chain_site = 0; }
         ~ChainScope() { tl_chain_launches = true; }
     } chain_scope((desc->flags & TSP_FRAME_CONCURRENT) == 0);
     const int Y = desc->rows, X = desc->cols, C = desc->channels;
@@ -702,7 +826,13 @@ static int submit_on_slot(tsp_handle* h, int slot, const tsp_frame_desc* desc, c
         cudaStreamSynchronize(s);
         return code;
     };
-    cudaError_t e = cudaMemcpyAsync(base + o_stack, h_stack, nstack * sizeof(uint16_t), cudaMemcpyHostToDevice, s);
+    cudaError_t e = cudaSuccess;
+    if (nstack * sizeof(uint16_t) >= ((size_t)4 << 20) && !host_pointer_is_pinned(h_stack)) {
+        rc = staged_copy_in(h, sl, base + o_stack, (const char*)h_stack, nstack * sizeof(uint16_t), s);
+        if (rc) return fail(rc);
+    } else {
+        e = cudaMemcpyAsync(base + o_stack, h_stack, nstack * sizeof(uint16_t), cudaMemcpyHostToDevice, s);
+    }
     if (e != cudaSuccess) {
         set_error("copy-in failed: %s", cudaGetErrorString(e));
         return fail(TSP_ERR_CUDA);

@@ -85,14 +85,14 @@ __global__ void zmap_range_init_kernel(int32_t* status) {
 // inclusive): any index >= Z raises IndexError; negative indices cannot occur.
 __global__ void band_check_kernel(int32_t* status, int Z, int shift, int decode) {
     if (decode) status[ST_ZMIN] = INT32_MAX - status[ST_ZMIN_INV];     // argmax kernels keep max(INT_MAX - z)
-    const int hi = status[ST_ZMAX];
+    const int hi = st_load(status, ST_ZMAX);
     int err = hi >= Z;
     if (shift != 0) {
         int hs = hi + shift;
         hs = hs < 0 ? 0 : (hs > Z ? Z : hs);
         err |= hs >= Z;
     }
-    if (status[ST_ZMIN] < 0) err = 1;
+    if (st_load(status, ST_ZMIN) < 0) err = 1;
     status[ST_BAND_ERR] = err;
 }
 
@@ -132,8 +132,8 @@ struct BandArgs {
 // any index >= Z raises IndexError; negative indices cannot occur.  Every CTA evaluates the rule from the range the
 // argmax stage left in the status block (ST_ZMAX, ST_ZMIN_INV = max(INT_MAX - z)); the first CTA records the verdict.
 __device__ __forceinline__ bool band_index_error(const BandArgs& a) {
-    if (!a.fused_check) return a.status[ST_BAND_ERR] != 0;
-    const int hi = a.status[ST_ZMAX], lo = INT32_MAX - a.status[ST_ZMIN_INV];
+    if (!a.fused_check) return st_load(a.status, ST_BAND_ERR) != 0;
+    const int hi = st_load(a.status, ST_ZMAX), lo = INT32_MAX - st_load(a.status, ST_ZMIN_INV);
     int err = hi >= a.Z;
     if (a.err_shift != 0) err |= min(max(hi + a.err_shift, 0), a.Z) >= a.Z;
     if (lo < 0) err = 1;
@@ -490,11 +490,11 @@ __global__ void __launch_bounds__(kB2Threads, 2) band_project3_kernel(const __gr
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // use_list: a small grid walks the tiles band_project4_kernel left behind; otherwise one tile per CTA
-    const int ntiles = a.use_list ? a.status[ST_WORK_COUNT] : 1;
+    const int ntiles = a.use_list ? st_load(a.status, ST_WORK_COUNT) : 1;
     for (int lin = a.use_list ? (int)blockIdx.x : 0; lin < ntiles; lin += a.use_list ? (int)gridDim.x : 1) {
     int bx = blockIdx.x, by = blockIdx.y;
     if (a.use_list) {
-        const int tile = a.worklist[lin];
+        const int tile = __ldcg(a.worklist + lin);
         bx = tile % a.tiles_x;
         by = tile / a.tiles_x;
     }
@@ -1331,7 +1331,7 @@ int launch_band_project_ex(tsp_handle* h, const uint16_t* d_stack, size_t channe
 // ---- bit-exact variant: materialise the one-hot volume and run the scipy-order passes ----------
 __global__ void onehot_kernel(const int32_t* __restrict__ zmap, float* __restrict__ vol, int Z, size_t plane,
                               int shift, const int32_t* __restrict__ status) {
-    if (status[ST_BAND_ERR]) return;
+    if (st_load(status, ST_BAND_ERR)) return;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < plane; p += stride) {
         int v = zmap[p];
@@ -1343,7 +1343,7 @@ __global__ void onehot_kernel(const int32_t* __restrict__ zmap, float* __restric
 __global__ void mulmax_kernel(const uint16_t* __restrict__ chan, const float* __restrict__ mask,
                               float* __restrict__ proj, int Z, size_t plane, int pedestal,
                               const int32_t* __restrict__ status) {
-    if (status[ST_BAND_ERR]) return;
+    if (st_load(status, ST_BAND_ERR)) return;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < plane; p += stride) {
         float best = -INFINITY;

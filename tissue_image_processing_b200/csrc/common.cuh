@@ -113,10 +113,26 @@ constexpr int kTapPad = 8;
 // launch latency and ramp at each of the frame's ten kernel boundaries.
 extern thread_local bool tl_chain_launches;      // false while a TSP_FRAME_CONCURRENT frame is being enqueued
 extern std::atomic<bool> g_no_chain;
+extern std::atomic<int> g_chain_plain_mask;      // debugging aid (tsp_debug_set "chain_plain_mask"): bit i = the i-th chained launch of a frame is a plain one
+extern thread_local int tl_chain_site;           // chained launches seen since the frame started
 extern bool g_sync_launches;                     // debugging aid (TSP_SYNC_LAUNCHES=1): device sync + error check per launch             // A/B switch (TSP_NO_CHAIN at tsp_create, tsp_debug_set "no_chain")
 #ifdef __CUDACC__
 __device__ __forceinline__ void chain_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// A chained kernel is resident - and the L1 flush of its launch long past - while its predecessors are still running,
+// and CTAs of those predecessors share the SM.  griddepcontrol.wait makes the predecessor's writes visible at L2, it
+// does NOT drop L1 lines this SM loaded earlier: a line read (through L1) before the producer's last write is served
+// stale afterwards.  Found with a 30 x 1024 x 1024 stack: from the second frame on coarse_xy_kernel took the
+// percentile from a status line cached before window_count_kernel wrote it (fixed-point scale of an un-clipped frame):
+// every height map wrong, deterministically.  Rules for chained kernels:
+//   * words of the status block are read with st_load() (ld.global.cg: L2, never L1);
+//   * memory that is re-written within the frame after an earlier stage read it (the accumulation volume, whose
+//     memory the z-mixed volume re-uses) is read with __ldcg by the earlier stage, so no L1 line of it exists;
+//   * everything else a stage reads was last read before the frame's first kernel, which is launched the ordinary way
+//     (a full boundary: L1 dropped).
+// (A gpu-scope fence behind the wait - CCTL.IVALL - also cures it, at +19 us in the decimation kernel, whose 9 728
+// warps each pass the wait.)
 __device__ __forceinline__ void chain_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ int32_t st_load(const int32_t* status, int word) { return __ldcg(status + word); }
 
 // launch_after_copy(): the same launch WITHOUT the attribute, for a kernel whose predecessor on the stream is a memset
 // or copy rather than a kernel: there is no prologue to overlap with, and inside a captured graph an early start
@@ -146,7 +162,9 @@ inline cudaError_t launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 bloc
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = !g_no_chain.load(std::memory_order_relaxed) && tl_chain_launches ? 1 : 0;
+    const int site = tl_chain_site++;
+    const bool plain = site < 31 && ((g_chain_plain_mask.load(std::memory_order_relaxed) >> site) & 1);
+    cfg.numAttrs = !g_no_chain.load(std::memory_order_relaxed) && tl_chain_launches && !plain ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 #endif
@@ -208,6 +226,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 int get_tensor_map_encoder(EncodeTiledFn* out);
 
+struct CopyPool;           // host threads of the staged copy-in (api.cu)
 }  // namespace tsp
 
 struct tsp_handle {
@@ -254,7 +273,13 @@ struct tsp_handle {
         size_t bytes = 0;
         int32_t* h_status = nullptr;
         std::atomic<bool> busy{false};
+        // pageable host buffers: ring of pinned chunks the stack is staged through (api.cu: staged_copy_in),
+        // allocated on first use
+        static constexpr int kStageRing = 3;
+        void* stage[kStageRing] = {nullptr, nullptr, nullptr};
+        cudaEvent_t stage_ev[kStageRing] = {nullptr, nullptr, nullptr};
     };
+    tsp::CopyPool* copy_pool = nullptr;        // host threads of the staged copies (api.cu), created on first use
     Slot slots[TSP_MAX_SLOTS + 1];       // the last one belongs to tsp_project_frame_host
     // per-device one-time setup done (constant memory, function attributes)
     size_t interp_smem_set = 0;

@@ -833,8 +833,8 @@ __global__ void __launch_bounds__(256) prep_fir_z_march_kernel(const uint16_t* _
                                                                int pedestal, const int32_t* __restrict__ status) {
     const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= plane4) return;
-    const bool clip = status[ST_HAS_NONZERO] != 0;
-    const float p95 = clip ? __int_as_float(status[ST_P95_BITS]) : 3.0e38f;
+    const bool clip = st_load(status, ST_HAS_NONZERO) != 0;
+    const float p95 = clip ? __int_as_float(st_load(status, ST_P95_BITS)) : 3.0e38f;
     const uint2* src = reinterpret_cast<const uint2*>(in) + p;
     float4* dst = reinterpret_cast<float4*>(out) + p;
     auto load = [&](int z) {

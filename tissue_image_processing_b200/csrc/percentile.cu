@@ -280,7 +280,7 @@ hist_percentile_kernel(const uint16_t* __restrict__ vol, size_t count, uint32_t*
                        int all_voxels, float q) {
     chain_release();
     chain_wait();
-    if (gate && *gate == 0) return;
+    if (gate && __ldcg(gate) == 0) return;
     extern __shared__ uint32_t sh[];
     hist_full_body(vol, count, ghist, sh);
     if (!is_last_block(ticket)) return;
@@ -468,7 +468,7 @@ __device__ void window_finalize(const uint32_t* __restrict__ gwin, const unsigne
         if (threadIdx.x == 0) write_result(status, 0, 0.f);
         return;
     }
-    const uint32_t wn = (uint32_t)status[ST_WIN_N];
+    const uint32_t wn = (uint32_t)st_load(status, ST_WIN_N);
     const int k = 32 - __clz(wn);                        // wn = 2^k - 1
     const unsigned long long zeros = count - n;          // voxels <= pedestal (they are all below the window)
     const bool sane = clamp_sum >= share_all && ((clamp_sum - share_all) & ((1ull << k) - 1)) == 0;
@@ -494,7 +494,7 @@ __device__ void window_finalize(const uint32_t* __restrict__ gwin, const unsigne
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        const int lo = status[ST_WIN_LO];
+        const int lo = st_load(status, ST_WIN_LO);
         if (!ok || found[0] < 0 || found[1] < 0 || rp.prev < below_nz) {
             status[ST_NEED_FULL] = 1;               // the sample window missed: exact fallback
         } else {
@@ -517,8 +517,8 @@ window_count_kernel(const uint16_t* __restrict__ vol, size_t count, int pedestal
     if (threadIdx.x < 2) blk[threadIdx.x] = 0;
     if (threadIdx.x == 0) qtail = 0;
     chain_wait();                // the shared-memory clears above overlap the sample kernel's last CTA
-    if (status[ST_WIN_OK] == 0) return;
-    const uint32_t lo = (uint32_t)status[ST_WIN_LO], wn = (uint32_t)status[ST_WIN_N];     // wn = 2^k - 1, lo >= 1
+    if (st_load(status, ST_WIN_OK) == 0) return;
+    const uint32_t lo = (uint32_t)st_load(status, ST_WIN_LO), wn = (uint32_t)st_load(status, ST_WIN_N);     // wn = 2^k - 1, lo >= 1
     const uint32_t ped = (uint32_t)pedestal;
     __syncthreads();
 
@@ -735,8 +735,8 @@ int launch_percentile_all(tsp_handle* h, const uint16_t* d_vol, size_t count, in
 // ---- K0: uint16 -> float32 with pedestal and p95 clip (SP:26-36) ------------------------------
 __global__ void prepare_kernel(const uint16_t* __restrict__ in, float* __restrict__ out, size_t count,
                                int pedestal, const int32_t* __restrict__ status) {
-    const bool clip = status[ST_HAS_NONZERO] != 0;
-    const float p = __int_as_float(status[ST_P95_BITS]);
+    const bool clip = st_load(status, ST_HAS_NONZERO) != 0;
+    const float p = __int_as_float(st_load(status, ST_P95_BITS));
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
         int v = (int)in[i] - pedestal;
