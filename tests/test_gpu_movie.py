@@ -391,3 +391,36 @@ def test_repeated_frames_on_one_projector_agree(tsp, shape):
                 assert abs(float(zmap.float().mean()) - Z * 0.4) < 1.5          # the bright sheet sits at 0.4 Z
             else:
                 assert torch.equal(got[0], first[0]) and torch.equal(got[1], first[1]), (mode, fill)
+
+
+@pytest.mark.parametrize("shape,C,shift,airy", [((8, 256, 256), 1, 0, False), ((16, 512, 512), 2, 0, False),
+                                                 ((20, 768, 1024), 1, 0, True), ((24, 1024, 1024), 2, 1, False),
+                                                 ((40, 1024, 1024), 1, 0, False), ((28, 2048, 1024), 1, 0, False),
+                                                 ((36, 1024, 2048), 2, -1, True), ((30, 1024, 1024), 1, 0, False)])
+def test_alternating_frames_on_one_projector_equal_fresh_projectors(tsp, shape, C, shift, airy):
+    """Two different stacks A, B, A, B, A through ONE projector (the life of a frame slot in a movie): every result
+    must equal what a fresh projector returns for that stack on its first call - nothing of a frame (workspace
+    contents, cached lines, graph state) may leak into the next one."""
+    import torch
+    from tissue_image_processing_b200 import _native as nat
+    Z, Y, X = shape
+
+    def stack(seed, peak):
+        g = torch.Generator(device="cuda").manual_seed(seed)
+        zz = torch.arange(Z, device="cuda", dtype=torch.float32)[None, :, None, None]
+        v = torch.rand((C, Z, Y, X), device="cuda", generator=g) * 2500 + 1200 * torch.exp(-(zz - peak) ** 2 / 6)
+        return (v + (10000 if airy else 0)).to(torch.int32).to(torch.uint16).contiguous()
+
+    kw = dict(airyscan=airy, atoh_shift=shift, mode="fast")
+    frames = {"A": stack(3, Z * 0.3), "B": stack(4, Z * 0.6)}
+    want = {}
+    for name, vol in frames.items():
+        proj, zmap = nat.DeviceProjector(C, Z, Y, X, **kw).run(vol)
+        torch.cuda.synchronize()
+        want[name] = (zmap.clone(), proj.clone())
+    assert not torch.equal(want["A"][0], want["B"][0])
+    p = nat.DeviceProjector(C, Z, Y, X, **kw)
+    for k, name in enumerate("ABABA"):
+        proj, zmap = p.run(frames[name])
+        torch.cuda.synchronize()
+        assert torch.equal(zmap, want[name][0]) and torch.equal(proj, want[name][1]), (k, name)
