@@ -12,8 +12,10 @@
  * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative
  * TSP_ERR_* code and never throws; tsp_last_error() gives the text for the calling thread.
  * "d_" pointers are device memory on the handle's GPU, "h_" pointers are host memory (pinned
- * host memory makes the copies asynchronous DMA; pageable memory works but is staged by the
- * driver).  Stacks are uint16, C-contiguous (C, Z, Y, X) with X fastest - the layout the
+ * host memory makes the copies asynchronous DMA; an input stack in pageable memory is staged by
+ * the library through pinned chunks with a pool of host threads - TSP_COPY_THREADS, default the
+ * CPUs of the process / LOCAL_WORLD_SIZE, at most 16 - and the submitting call returns when the
+ * last chunk has been handed to the DMA engine).  Stacks are uint16, C-contiguous (C, Z, Y, X) with X fastest - the layout the
  * reference operator works on after BIM:199-231 / SP:21-26.
  */
 #ifndef TSP_B200_H
