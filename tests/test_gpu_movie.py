@@ -354,6 +354,17 @@ def test_pageable_host_stack_is_staged_and_gives_the_same_frame(tsp):
         assert np.array_equal(got_z, want_z) and np.array_equal(got_p, want_p)
     proj, zmap = tsp.time_point_surface_projection(big[None], "TCZYX", 0, airyscan=False, z_map=True)
     assert np.array_equal(zmap, want_z) and np.array_equal(proj, want_p)
+    # pageable RESULT arrays too (what the ctypes stub of INTEGRATION.md passes): staged through the slot's pinned block
+    out_p = np.full(want_p.shape, -1.0)
+    out_z = np.full(want_z.shape, -1, dtype=np.int64)
+    for _ in range(2):
+        got_p, got_z, st = nat.project_frame_host(np.array(big), 0, mode="fast", out_proj=out_p, out_zmap=out_z)
+        assert got_p is out_p and np.array_equal(out_z, want_z) and np.array_equal(out_p, want_p)
+        out_p[...] = -1.0
+        out_z[...] = -1
+    u16 = nat.project_frame_host(np.array(big), 0, mode="fast", out_u16=True, out_proj=np.zeros(want_p.shape, np.uint16),
+                                 out_zmap=np.zeros(want_z.shape, np.uint16))
+    assert np.array_equal(u16[1], want_z.astype(np.uint16)) and np.array_equal(u16[0], want_p.astype(np.uint16))
     small = rng.integers(0, 3000, size=(1, 6, 40, 48)).astype(np.uint16)      # below the staging threshold
     a = nat.project_frame_host(small, 0, mode="exact")
     ps = nat.pinned_empty(small.shape, np.uint16)

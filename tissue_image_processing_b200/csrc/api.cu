@@ -246,11 +246,13 @@ struct CopyPool {
         cv_work.notify_all();
         for (auto& t : workers) t.join();
     }
+    std::mutex call_mu;          // one copy at a time (callers of different frame slots may arrive together)
     void copy(void* d, const void* s, size_t n) {
         if (workers.size() < 2 || n < ((size_t)1 << 20)) {
             memcpy(d, s, n);
             return;
         }
+        std::lock_guard<std::mutex> turn(call_mu);
         std::unique_lock<std::mutex> lk(mu);
         dst = (char*)d;
         src = (const char*)s;
@@ -409,6 +411,7 @@ int tsp_destroy(tsp_handle* h) {
         if (sl.stream) cudaStreamSynchronize(sl.stream);
         if (sl.d_mem) cudaFree(sl.d_mem);
         if (sl.h_status) cudaFreeHost(sl.h_status);
+        if (sl.h_out) cudaFreeHost(sl.h_out);
         for (int b = 0; b < tsp_handle::Slot::kStageRing; ++b) {
             if (sl.stage[b]) cudaFreeHost(sl.stage[b]);
             if (sl.stage_ev[b]) cudaEventDestroy(sl.stage_ev[b]);
@@ -850,8 +853,33 @@ static int submit_on_slot(tsp_handle* h, int slot, const tsp_frame_desc* desc, c
                                       (double*)(base + o_projx), (int64_t*)(base + o_zmapx), nproj, plane, s);
         if (rc) return fail(rc);
         e = cudaMemcpyAsync(sl.h_status, base + o_ws, kStatusWords * sizeof(int32_t), cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(h_proj, base + o_projx, proj_out, cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(h_zmap, base + o_zmapx, zmap_out, cudaMemcpyDeviceToHost, s);
+        // results into pageable arrays (the ctypes stub of INTEGRATION.md allocates them with np.empty): through a
+        // pinned block of the slot, handed over by the host threads in tsp_frame_wait - the driver's own staging of a
+        // pageable destination runs at ~10 GB/s on one thread
+        void* dst_proj = h_proj;
+        void* dst_zmap = h_zmap;
+        sl.user_proj = sl.user_zmap = nullptr;
+        if (proj_out + zmap_out >= ((size_t)1 << 20) && !(host_pointer_is_pinned(h_proj) && host_pointer_is_pinned(h_zmap))) {
+            const size_t need = align_up(proj_out, 256) + zmap_out;
+            if (sl.h_out_bytes < need) {
+                if (sl.h_out) cudaFreeHost(sl.h_out);
+                sl.h_out = nullptr;
+                sl.h_out_bytes = 0;
+                if (cudaMallocHost(&sl.h_out, need) == cudaSuccess) sl.h_out_bytes = need;
+                else cudaGetLastError();
+            }
+            if (sl.h_out) {
+                if (!h->copy_pool) h->copy_pool = new CopyPool(copy_pool_threads());
+                dst_proj = sl.h_out;
+                dst_zmap = (char*)sl.h_out + align_up(proj_out, 256);
+                sl.user_proj = h_proj;
+                sl.user_zmap = h_zmap;
+                sl.user_proj_bytes = proj_out;
+                sl.user_zmap_bytes = zmap_out;
+            }
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(dst_proj, base + o_projx, proj_out, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(dst_zmap, base + o_zmapx, zmap_out, cudaMemcpyDeviceToHost, s);
         if (e != cudaSuccess) {
             set_error("copy-out failed: %s", cudaGetErrorString(e));
             return fail(TSP_ERR_CUDA);
@@ -871,6 +899,13 @@ static int wait_on_slot(tsp_handle* h, int slot, tsp_frame_status* status) {
     cudaError_t e = cudaStreamSynchronize(sl.stream);
     tsp_frame_status st;
     if (e == cudaSuccess) fill_status(sl.h_status, &st);
+    if (sl.user_proj) {                       // results staged in the slot's pinned block: hand them over
+        if (e == cudaSuccess && h->copy_pool) {
+            h->copy_pool->copy(sl.user_proj, sl.h_out, sl.user_proj_bytes);
+            h->copy_pool->copy(sl.user_zmap, (char*)sl.h_out + align_up(sl.user_proj_bytes, 256), sl.user_zmap_bytes);
+        }
+        sl.user_proj = sl.user_zmap = nullptr;
+    }
     sl.busy.store(false);
     if (e != cudaSuccess) {
         set_error("cudaStreamSynchronize failed: %s", cudaGetErrorString(e));

@@ -278,6 +278,13 @@ struct tsp_handle {
         static constexpr int kStageRing = 3;
         void* stage[kStageRing] = {nullptr, nullptr, nullptr};
         cudaEvent_t stage_ev[kStageRing] = {nullptr, nullptr, nullptr};
+        // pageable result buffers: the frame's outputs land in this pinned block and are copied to the caller's
+        // arrays by the host threads when the frame is waited for
+        void* h_out = nullptr;
+        size_t h_out_bytes = 0;
+        void* user_proj = nullptr;
+        void* user_zmap = nullptr;
+        size_t user_proj_bytes = 0, user_zmap_bytes = 0;
     };
     tsp::CopyPool* copy_pool = nullptr;        // host threads of the staged copies (api.cu), created on first use
     Slot slots[TSP_MAX_SLOTS + 1];       // the last one belongs to tsp_project_frame_host
