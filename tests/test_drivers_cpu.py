@@ -242,6 +242,80 @@ def test_movie_driver_resumes_after_an_interrupted_run(monkeypatch, tmp_path):
     assert sorted(os.listdir(broken)) == sorted(os.listdir(clean)) == ["stage_locations_position1.pkl", "zmap_position1.npy"]
 
 
+class _FakeNative:
+    """Stands in for the C ABI under movie.FramePipeline._run_device: a frame slot computes a toy projection when the
+    frame is waited for (so a buffer recycled too early shows up as a wrong result)."""
+    MAX_SLOTS = 4
+    METHODS = ("max_averages", "max_std", "multi_channel")
+    PARAM_KEYS = ()
+
+    def __init__(self):
+        self.slots = {}
+        self.submitted = []
+
+    def pinned_empty(self, shape, dtype):
+        return np.empty(shape, dtype=dtype)
+
+    def bind_host_thread_to_gpu(self, device=None):
+        return None
+
+    def frame_submit(self, slot, stack, proj, zmap, **kw):
+        assert slot not in self.slots, "slot re-used before it was waited for"
+        self.slots[slot] = (stack, proj, zmap)
+        self.submitted.append(int(stack[0, 0, 0, 0]))
+
+    def frame_wait(self, slot, device=None):
+        stack, proj, zmap = self.slots.pop(slot)
+        proj[...] = stack.max(axis=1)
+        zmap[...] = stack[0].argmax(axis=0)
+        return {"band_index_error": False}
+
+
+def test_frame_pipeline_feeder_keeps_order_recycles_buffers_and_propagates_errors(monkeypatch):
+    """movie.FramePipeline._run_device without a GPU: the feeder thread stages frames ahead (slots + 2 buffers), the
+    submitting thread keeps `slots` frames in flight; results arrive in order and intact, errors of the frame source
+    and of the sink reach the caller, and nothing is left hanging."""
+    import threading
+    from tissue_image_processing_b200 import movie
+    fake = _FakeNative()
+    monkeypatch.setattr(movie, "_native", fake)
+    monkeypatch.setattr(movie._Staging, "is_pinned", staticmethod(lambda arr: False))
+    pipe = movie.FramePipeline.__new__(movie.FramePipeline)
+    pipe.operator, pipe.mode, pipe.out_dtype, pipe.devices, pipe.slots, pipe.copy_threads, pipe.h2d_bytes = (
+        None, "fast", "uint16", [0], 2, 3, 0)
+    rng = np.random.default_rng(0)
+    stacks = [rng.integers(0, 60000, size=(1, 4, 64, 96)).astype(np.uint16) for _ in range(11)]
+    for t, st in enumerate(stacks):
+        st[0, 0, 0, 0] = t                                   # tag
+    got = []
+    pipe._run_device(0, ((t, st) for t, st in enumerate(stacks)),
+                     dict(reference_channel=0, airyscan=False), lambda k, p, z, s: got.append((k, p.copy(), z.copy())))
+    assert [k for k, _, _ in got] == list(range(11)) and fake.submitted == list(range(11))
+    for k, p, z in got:
+        assert np.array_equal(p, stacks[k].max(axis=1).astype(np.uint16))
+        assert np.array_equal(z, stacks[k][0].argmax(axis=0).astype(np.uint16))
+    assert pipe.h2d_bytes == sum(st.nbytes for st in stacks) and not fake.slots
+
+    def broken_source():
+        yield 0, stacks[0]
+        yield 1, stacks[1]
+        raise OSError("reader failed")
+    with pytest.raises(OSError, match="reader failed"):
+        pipe._run_device(0, broken_source(), dict(reference_channel=0, airyscan=False), lambda *a: None)
+    assert not fake.slots                                    # frames in flight were waited for
+
+    def bad_sink(k, p, z, s):
+        if k == 3:
+            raise ValueError("sink failed")
+    with pytest.raises(ValueError, match="sink failed"):
+        pipe._run_device(0, ((t, st) for t, st in enumerate(stacks)), dict(reference_channel=0, airyscan=False), bad_sink)
+    assert not fake.slots
+    with pytest.raises(TypeError):                           # a float stack is refused by the feeder, seen by the caller
+        pipe._run_device(0, iter([(0, stacks[0].astype(np.float32))]), dict(reference_channel=0, airyscan=False),
+                         lambda *a: None)
+    assert not [t for t in threading.enumerate() if t.name.startswith("tsp-feeder") and t.is_alive()]
+
+
 def test_cli_flags_and_dispatch(monkeypatch, tmp_path):
     """SP:329-423: same flags and defaults, same dispatch to the three drivers."""
     import numpy as np

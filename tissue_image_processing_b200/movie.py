@@ -460,7 +460,7 @@ class FramePipeline:
                 free_ids.put(b)
             sink(key, proj, zmap, status)
 
-        th = threading.Thread(target=feeder, daemon=True)
+        th = threading.Thread(target=feeder, daemon=True, name="tsp-feeder-gpu%s" % device)
         th.start()
         i = 0
         try:
