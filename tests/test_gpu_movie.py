@@ -435,3 +435,47 @@ def test_alternating_frames_on_one_projector_equal_fresh_projectors(tsp, shape, 
         proj, zmap = p.run(frames[name])
         torch.cuda.synchronize()
         assert torch.equal(zmap, want[name][0]) and torch.equal(proj, want[name][1]), (k, name)
+
+
+def test_drivers_on_real_tiff_files(tsp, tmp_path, monkeypatch):
+    """Both drivers from TIFF files on disk to TIFF files on disk with the package's own reader / writer (tiff_io, no
+    hook installed beyond routing ``open_image`` to it): the time points come out of the file mapping as read-only
+    views and are staged into pinned memory by the pipeline; the tiles of the large image are gathered plane by
+    plane.  bitexact mode, so the files must hold exactly the oracle's values."""
+    from tissue_image_processing_b200 import basic_image_manipulations as bim
+    from tissue_image_processing_b200 import surface_projection as sp
+    from tissue_image_processing_b200 import tiff_io
+    monkeypatch.setattr(bim, "open_image", tiff_io.TiffImage)
+    monkeypatch.setattr(sp, "tiff_writer", tiff_io.hook_writer)
+    movie = _movie(T=4, C=2, Z=8, Y=40, X=56, seed=21)
+    src, out = tmp_path / "in", tmp_path / "out"
+    src.mkdir(), out.mkdir()
+    tiff_io.write_tiff(str(src / "m1.tif"), movie, "TCZYX")
+    sp.movie_surface_projection([str(src / "m1.tif")], 0, [1], 1, str(out), "max_averages", 1, False, 0, 0, 0, False,
+                                mode="bitexact")
+    got = tiff_io.TiffImage(str(out / "position1.tif"))
+    assert got.shape5 == (4, 2, 1, 40, 56) and got.dtype == np.uint16 and got.dimension_order == "XYCTZ"
+    zmap = np.load(out / "zmap_position1.npy")
+    for t in range(4):
+        want_p, want_z = orc.time_point_surface_projection(movie[t:t + 1], "TCZYX", 0, airyscan=False, z_map=True)
+        assert np.array_equal(got.get_image_dask_data()[t, :, 0].compute(), want_p.astype(np.uint16)), t
+        assert np.array_equal(zmap[t, 0, 0], want_z.astype(np.uint16)), t
+    # the blocking operator straight on a read-only frame view of the mapping
+    frame = tiff_io.TiffImage(str(src / "m1.tif")).get_image_dask_data()[2:3].compute()
+    assert not frame.flags.writeable
+    p, z = tsp.time_point_surface_projection(frame, "TCZYX", 0, airyscan=False, z_map=True, mode="bitexact")
+    want_p, want_z = orc.time_point_surface_projection(movie[2:3], "TCZYX", 0, airyscan=False, z_map=True)
+    assert np.array_equal(p, want_p) and np.array_equal(z, want_z)
+    # tiled driver
+    big = synth.synth_stack(9, 70, 100, C=2, seed=9)[None]
+    tiff_io.write_tiff(str(src / "big.tif"), big, "TCZYX")
+    sp.large_image_projection(str(src), str(out), "big.tif", position=1, reference_channel=0, chunk_size=48,
+                              airyscan=False, mode="bitexact")
+    want = np.zeros((2, 70, 100))
+    for y in range(0, 70, 48):
+        for x in range(0, 100, 48):
+            want[:, y:y + 48, x:x + 48] = orc.time_point_surface_projection(big[:, :, :, y:y + 48, x:x + 48], "TCZYX", 0,
+                                                                            airyscan=False)
+    tif = tiff_io.TiffImage(str(out / "big_projection.tif"))
+    assert tif.shape5 == (1, 2, 1, 70, 100)
+    assert np.array_equal(tif.get_image_data()[0, :, 0], np.round(want / want.max() * 65535).astype(np.uint16))

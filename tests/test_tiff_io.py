@@ -1,0 +1,256 @@
+"""The package's own TIFF reader / writer (tiff_io.py) and the drivers running on real files through it, on CPU.
+Pillow (an independent TIFF implementation) is the cross-check in both directions."""
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from oracle import synth
+from oracle import surface_projection_oracle as orc
+
+PIL_Image = pytest.importorskip("PIL.Image")
+
+
+def _pil_pages(path):
+    im = PIL_Image.open(path)
+    out = []
+    for k in range(im.n_frames):
+        im.seek(k)
+        out.append(np.array(im))
+    return np.stack(out)
+
+
+@pytest.mark.parametrize("axes,shape,order", [("TCZYX", (3, 2, 4, 17, 23), "XYZCT"), ("TCYX", (5, 2, 9, 11), "XYCTZ"),
+                                              ("CYX", (2, 8, 8), "XYCZT"), ("ZYX", (6, 5, 7), "XYZCT"),
+                                              ("YX", (12, 10), "XYCZT")])
+@pytest.mark.parametrize("dtype", ["uint8", "uint16", "float32"])
+@pytest.mark.parametrize("bigtiff", [False, True])
+def test_written_files_read_back_and_pillow_agrees(tmp_path, axes, shape, order, dtype, bigtiff):
+    from tissue_image_processing_b200 import tiff_io
+    rng = np.random.default_rng(len(axes))
+    a = (rng.random(shape) * 250).astype(dtype)
+    path = str(tmp_path / "a.tif")
+    tiff_io.write_tiff(path, a, axes, bigtiff=bigtiff)
+    with open(path, "rb") as f:
+        assert struct.unpack("<2sH", f.read(4)) == (b"II", 43 if bigtiff else 42)
+    img = tiff_io.TiffImage(path)
+    assert img.dimension_order == order == tiff_io.dimension_order(axes)
+    sizes = dict(zip("TCZYX", (1,) * 5), **dict(zip(axes, shape)))
+    assert (img.dims.T, img.dims.C, img.dims.Z, img.dims.Y, img.dims.X) == tuple(sizes[k] for k in "TCZYX")
+    full = img.get_image_dask_data().compute()
+    assert full.dtype == a.dtype and np.array_equal(full, a.reshape(full.shape))
+    assert np.array_equal(_pil_pages(path), a.reshape((-1,) + shape[-2:]))          # pages in C order of the array
+    img.close() if full.flags.owndata else None
+
+
+def test_lazy_indexing_matches_numpy_and_frames_are_views(tmp_path):
+    from tissue_image_processing_b200 import tiff_io
+    a = np.random.default_rng(1).integers(0, 65535, (4, 2, 5, 16, 24), dtype=np.uint16)
+    path = str(tmp_path / "m.tif")
+    tiff_io.write_tiff(path, a, "TCZYX")
+    data = tiff_io.TiffImage(path).get_image_dask_data()
+    assert data.shape == a.shape and data[1:3].shape == (2, 2, 5, 16, 24) and data[2, 1].shape == (5, 16, 24)
+    for idx in [np.s_[1:2], np.s_[2], np.s_[:, 1], np.s_[1:2, :, :, 3:9, 5:20], np.s_[3, 0, ::2, ::-1, ::3],
+                np.s_[..., 4:8, :], np.s_[0:1, :, :, 8:16, :], np.s_[1, :, 2:4], np.s_[0, 1, 4, 5, 6]]:
+        assert np.array_equal(np.asarray(data[idx].compute()), a[idx]), idx
+    assert np.array_equal(data[1:3][1][:, 2:].compute(), a[1:3][1][:, 2:])       # indexing composes
+    frame = data[1:2].compute()                      # what project_movie reads per time point: no copy, read-only
+    assert not frame.flags.owndata and not frame.flags.writeable
+    tile = data[0:1, :, :, 0:8, 0:12].compute()      # an XY tile is gathered plane by plane
+    assert tile.flags.writeable and np.array_equal(tile, a[0:1, :, :, 0:8, 0:12])
+    with pytest.raises(TypeError):
+        data[[0, 1]]
+    with pytest.raises(IndexError):
+        data[0, 0, 0, 0, 0, 0]
+
+
+def test_files_written_by_pillow_strips_imagej_order_and_refusals(tmp_path):
+    """Reader against an independent writer: an ImageJ hyperstack description (channels vary fastest), a file with no
+    description, and the formats the reader refuses."""
+    from tissue_image_processing_b200 import tiff_io
+    rng = np.random.default_rng(2)
+    T, Z, C, Y, X = 2, 3, 2, 300, 280
+    a = rng.integers(0, 65535, (T, Z, C, Y, X), dtype=np.uint16)             # ImageJ order: T, Z, C
+    pages = [PIL_Image.fromarray(p) for p in a.reshape(-1, Y, X)]
+    path = str(tmp_path / "ij.tif")
+    desc = "ImageJ=1.53\nimages=%d\nchannels=%d\nslices=%d\nframes=%d\nhyperstack=true\nspacing=0.5\n" % (T * Z * C, C, Z, T)
+    pages[0].save(path, save_all=True, append_images=pages[1:], description=desc)
+    img = tiff_io.TiffImage(path)
+    assert img.dimension_order == "XYCZT" and img.shape5 == (T, C, Z, Y, X)
+    assert img.metadata.images[0].pixels.physical_size_z == 0.5
+    got = img.get_image_dask_data()
+    assert np.array_equal(got.compute(), a.transpose(0, 2, 1, 3, 4))
+    assert np.array_equal(got[1, :, 2, 10:50, 5:9].compute(), a[1, 2, :, 10:50, 5:9])
+    # no description: the pages are the planes of one z stack
+    plain = str(tmp_path / "plain.tif")
+    pages[0].save(plain, save_all=True, append_images=pages[1:5])
+    assert tiff_io.TiffImage(plain).shape5 == (1, 1, 5, Y, X)
+    packed = str(tmp_path / "lzw.tif")
+    pages[0].save(packed, compression="tiff_lzw")
+    with pytest.raises(NotImplementedError, match="compressed"):
+        tiff_io.TiffImage(packed)
+    rgb = str(tmp_path / "rgb.tif")
+    PIL_Image.fromarray(rng.integers(0, 255, (8, 8, 3), dtype=np.uint8)).save(rgb)
+    with pytest.raises(NotImplementedError, match="samples per pixel"):
+        tiff_io.TiffImage(rgb)
+    junk = str(tmp_path / "junk.tif")
+    with open(junk, "wb") as f:
+        f.write(b"not a tiff at all")
+    with pytest.raises(ValueError, match="not a TIFF"):
+        tiff_io.TiffImage(junk)
+    with pytest.raises(IndexError):
+        img.set_scene(1)
+
+
+def test_big_endian_file(tmp_path):
+    """A hand-made 'MM' classic TIFF: two 2x3 uint16 pages."""
+    from tissue_image_processing_b200 import tiff_io
+    planes = [(np.arange(6).reshape(2, 3) + 256).astype(">u2"), (np.arange(6).reshape(2, 3) * 1000).astype(">u2")]
+
+    def ifd(data_at, nxt):
+        tags = [(256, 3, 1, 3), (257, 3, 1, 2), (258, 3, 1, 16), (259, 3, 1, 1), (262, 3, 1, 1), (273, 4, 1, data_at),
+                (277, 3, 1, 1), (278, 3, 1, 2), (279, 4, 1, 12)]
+        body = b"".join(struct.pack(">HHI", t, ty, n) + (struct.pack(">HH", v, 0) if ty == 3 else struct.pack(">I", v))
+                        for t, ty, n, v in tags)
+        return struct.pack(">H", len(tags)) + body + struct.pack(">I", nxt)
+
+    size = 2 + 12 * 9 + 4
+    blob = struct.pack(">2sHI", b"MM", 42, 8 + 24) + planes[0].tobytes() + planes[1].tobytes()
+    blob += ifd(8, 8 + 24 + size) + ifd(20, 0)
+    path = str(tmp_path / "mm.tif")
+    with open(path, "wb") as f:
+        f.write(blob)
+    img = tiff_io.TiffImage(path)
+    out = img.get_image_dask_data().compute()
+    assert out.dtype == np.uint16 and out.dtype.isnative and out.shape == (1, 1, 2, 2, 3)
+    assert np.array_equal(out[0, 0], np.stack(planes).astype(np.uint16))
+
+
+def test_page_cut_into_strips_stored_out_of_order(tmp_path):
+    """Two pages of 4 x 3 uint8, each cut into two strips of two rows; the strips of page 0 lie in the file in
+    reverse order (not adjacent: the page is assembled), those of page 1 in order (adjacent: served as a view)."""
+    from tissue_image_processing_b200 import tiff_io
+    planes = np.arange(24, dtype=np.uint8).reshape(2, 4, 3) + 7
+
+    def ifd(offsets_at, counts_at, nxt):
+        tags = [(256, 3, 1, 3), (257, 3, 1, 4), (258, 3, 1, 8), (259, 3, 1, 1), (262, 3, 1, 1), (273, 4, 2, offsets_at),
+                (277, 3, 1, 1), (278, 3, 1, 2), (279, 4, 2, counts_at)]
+        body = b"".join(struct.pack("<HHI", t, ty, n) + (struct.pack("<HH", v, 0) if ty == 3 else struct.pack("<I", v))
+                        for t, ty, n, v in tags)
+        return struct.pack("<H", len(tags)) + body + struct.pack("<I", nxt)
+
+    data_at = 8
+    data = planes[0, 2:].tobytes() + planes[0, :2].tobytes() + planes[1].tobytes()           # 6 + 6 + 12 bytes
+    tables_at = data_at + len(data)
+    tables = struct.pack("<8I", data_at + 6, data_at, 6, 6, data_at + 12, data_at + 18, 6, 6)
+    ifd_at = tables_at + len(tables)
+    size = 2 + 12 * 9 + 4
+    blob = struct.pack("<2sHI", b"II", 42, ifd_at) + data + tables
+    blob += ifd(tables_at, tables_at + 8, ifd_at + size) + ifd(tables_at + 16, tables_at + 24, 0)
+    path = str(tmp_path / "strips.tif")
+    with open(path, "wb") as f:
+        f.write(blob)
+    img = tiff_io.TiffImage(path)
+    assert [len(s) for s in img._strips] == [2, 2] and img._plane_at[0] is None and img._plane_at[1] == data_at + 12
+    assert not img._packed
+    assert np.array_equal(img.get_image_data()[0, 0], planes)
+    assert np.array_equal(_pil_pages(path), planes)
+    assert np.array_equal(img.get_image_dask_data()[0, 0, 1, 1:3].compute(), planes[1, 1:3])
+
+
+def test_metadata_round_trip_and_dimension_order_rules(tmp_path):
+    from types import SimpleNamespace as NS
+    from tissue_image_processing_b200 import tiff_io
+    meta = NS(images=[NS(name='position<3> "a&b"', pixels=NS(physical_size_x=0.25, physical_size_y=0.25,
+                                                            physical_size_z=None))])
+    path = str(tmp_path / "p.tif")
+    tiff_io.hook_writer(path, np.zeros((2, 3, 4, 5), np.uint16), "TCYX", meta)
+    im = tiff_io.TiffImage(path).metadata.images[0]
+    assert im.pixels.physical_size_x == 0.25 and im.pixels.physical_size_z is None and im.pixels.type == "uint16"
+    assert im.pixels.size_t == 2 and im.pixels.size_c == 3 and len(im.pixels.planes) == 6
+    assert im.name.startswith("position")
+    for bad in ("TCXY", "TTYX", "QYX", "YXC"):
+        with pytest.raises(ValueError):
+            tiff_io.dimension_order(bad)
+    with pytest.raises(ValueError):
+        tiff_io.write_tiff(path, np.zeros((2, 3, 4)), "TCYX")
+    with pytest.raises(TypeError):
+        tiff_io.write_tiff(path, np.zeros((2, 3), dtype=np.complex64))
+
+
+def test_tiled_driver_on_a_real_tiff_with_the_default_reader_and_writer(tmp_path, monkeypatch):
+    """large_image_projection (SP:279-316) from a .tif on disk to ``*_projection.tif`` / ``*_zmap.npy`` with no I/O
+    hook installed: aicsimageio is absent here, so the default ``open_image`` falls back to TiffImage and the default
+    writer is tiff_io.  The operator seam runs the oracle - this is the host path, not the kernels."""
+    pytest.importorskip("torch")
+    from tissue_image_processing_b200 import basic_image_manipulations as bim
+    from tissue_image_processing_b200 import surface_projection as sp
+    from tissue_image_processing_b200 import tiff_io
+    from tissue_image_processing_b200.movie import FramePipeline
+    try:
+        import aicsimageio  # noqa: F401
+        pytest.skip("aicsimageio installed: the default reader is the reference's")
+    except ImportError:
+        pass
+    monkeypatch.setattr(bim, "open_image", bim._default_open_image)
+    monkeypatch.setattr(sp, "tiff_writer", sp._default_tiff_writer)
+    big = synth.synth_stack(6, 40, 48, C=2, seed=9)[None]                  # (1, C, Z, Y, X)
+    src, out = tmp_path / "in", tmp_path / "out"
+    src.mkdir(), out.mkdir()
+    tiff_io.write_tiff(str(src / "big.tif"), big, "TCZYX")
+    pipe = FramePipeline(operator=orc.time_point_surface_projection)
+    sp.large_image_projection(str(src), str(out), "big.tif", position=1, reference_channel=0, chunk_size=24,
+                              airyscan=False, frame_pipeline=pipe)
+    want_p = np.zeros((2, 40, 48))
+    want_z = np.zeros((1, 40, 48))
+    for y in (0, 24):
+        for x in (0, 24):
+            p, z = orc.time_point_surface_projection(big[:, :, :, y:y + 24, x:x + 24], "TCZYX", 0, airyscan=False,
+                                                     z_map=True)
+            want_p[:, y:y + 24, x:x + 24] = p
+            want_z[0, y:y + 24, x:x + 24] = z
+    want_u16 = np.round(want_p / want_p.max() * 65535).astype(np.uint16)          # BIM:183-186
+    got = tiff_io.TiffImage(str(out / "big_projection.tif"))
+    assert got.dimension_order == "XYCZT" and got.shape5 == (1, 2, 1, 40, 48) and got.dtype == np.uint16
+    assert np.array_equal(got.get_image_data()[0, :, 0], want_u16)
+    assert np.array_equal(_pil_pages(str(out / "big_projection.tif")), want_u16)
+    assert np.array_equal(np.load(out / "big_zmap.npy"), want_z)
+    with pytest.raises(ImportError, match="aicsimageio"):
+        bim.open_image(str(src / "movie.czi"))
+
+
+def test_movie_driver_writes_a_real_ome_tiff(tmp_path, monkeypatch):
+    """movie_surface_projection with the default writer: ``position1.tif`` is a (T,C,Y,X) uint16 TIFF in XYCTZ plane
+    order (SP:323) that both readers open, and it equals the truncated oracle projections (BIM:481)."""
+    pytest.importorskip("torch")
+    from tests.fake_image import FakeAICSImage, install
+    from tissue_image_processing_b200 import surface_projection as sp
+    from tissue_image_processing_b200 import tiff_io
+    from tissue_image_processing_b200.movie import FramePipeline
+    movie = np.stack([synth.synth_stack(6, 24, 28, C=2, seed=3, t=t) for t in range(3)])
+    install(monkeypatch, {"m1.czi": FakeAICSImage([movie])})
+    monkeypatch.setattr(sp, "tiff_writer", sp._default_tiff_writer)
+    pipe = FramePipeline(operator=orc.time_point_surface_projection, out_dtype="uint16")
+    sp.movie_surface_projection(["m1.czi"], 0, [1], 1, str(tmp_path), "max_averages", 1, False, 0, 0, 0, False,
+                                frame_pipeline=pipe)
+    want = np.stack([orc.time_point_surface_projection(movie[t:t + 1], "TCZYX", 0, airyscan=False).astype("uint16")
+                     for t in range(3)])
+    got = tiff_io.TiffImage(os.path.join(str(tmp_path), "position1.tif"))
+    assert got.dimension_order == "XYCTZ" and got.shape5 == (3, 2, 1, 24, 28)
+    assert got.metadata.images[0].name == "position0" and got.metadata.images[0].pixels.physical_size_x == 0.1
+    assert np.array_equal(got.get_image_data()[:, :, 0], want)
+    assert np.array_equal(_pil_pages(os.path.join(str(tmp_path), "position1.tif")), want.reshape(-1, 24, 28))
+
+
+def test_classic_files_switch_to_bigtiff_at_the_offset_limit(tmp_path, monkeypatch):
+    from tissue_image_processing_b200 import tiff_io
+    a = np.random.default_rng(5).integers(0, 65535, (6, 64, 64), dtype=np.uint16)
+    small, large = str(tmp_path / "s.tif"), str(tmp_path / "l.tif")
+    tiff_io.write_tiff(small, a, "ZYX")
+    monkeypatch.setattr(tiff_io, "_CLASSIC_LIMIT", 40000)            # stands for 4 GiB
+    tiff_io.write_tiff(large, a, "ZYX")
+    magic = [struct.unpack("<2sH", open(p, "rb").read(4))[1] for p in (small, large)]
+    assert magic == [42, 43]
+    assert np.array_equal(tiff_io.TiffImage(large).get_image_data()[0, 0], a)
+    assert np.array_equal(_pil_pages(large), a)

@@ -2,10 +2,10 @@
 B200-backed: ``blur_image`` (BIM:373-390), ``put_channel_axis_first`` (BIM:199-231) and the chunked
 operator host ``read_image_in_chunks`` (BIM:89-159).
 
-File formats (Bio-Formats / aicsimageio) are out of scope: ``open_image`` is a hook.  By default
-it imports aicsimageio like the reference; tests install an in-memory image object with the same
-surface (``dims.{T,C,Z,Y,X}``, ``set_scene``, ``get_image_dask_data()`` -> sliceable with
-``.compute()``).
+File formats: ``open_image`` is a hook.  By default it imports aicsimageio + Bio-Formats like the reference
+(BIM:79-87); where that stack is absent, plain TIFF / BigTIFF files are read by ``tiff_io.TiffImage`` (same surface:
+``dims.{T,C,Z,Y,X}``, ``set_scene``, ``get_image_dask_data()`` -> sliceable with ``.compute()``, ``metadata``), every
+other format needs the hook.  Tests install an in-memory image object with that surface.
 """
 from __future__ import annotations
 
@@ -15,8 +15,15 @@ from . import _native
 
 
 def _default_open_image(path):
-    from aicsimageio import AICSImage                       # noqa: WPS433 (optional dependency)
-    from aicsimageio.readers import bioformats_reader
+    try:
+        from aicsimageio import AICSImage                   # noqa: WPS433 (optional dependency)
+        from aicsimageio.readers import bioformats_reader
+    except ImportError as exc:
+        from . import tiff_io
+        if tiff_io.is_tiff_path(path):
+            return tiff_io.TiffImage(path)
+        raise ImportError("reading %r needs aicsimageio + Bio-Formats (only TIFF files are read without them): "
+                          "install them or set basic_image_manipulations.open_image" % (path,)) from exc
     return AICSImage(path, reader=bioformats_reader.BioformatsReader)
 
 

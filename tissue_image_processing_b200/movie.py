@@ -331,6 +331,8 @@ class _Staging:
     @staticmethod
     def is_pinned(arr):
         import torch
+        if not arr.flags.writeable:            # a read-only view of a file mapping (tiff_io) is never pinned memory
+            return False
         try:
             return arr.flags.c_contiguous and torch.from_numpy(arr).is_pinned()
         except (TypeError, ValueError, RuntimeError):

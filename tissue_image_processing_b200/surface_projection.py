@@ -7,7 +7,8 @@
 conventions, but are built around ``movie.FramePipeline``: a frame source (time points of a movie file, XY tiles
 of a large image) feeds the GPU frame slots through pinned staging buffers, the results come back in the dtype
 that is written to disk (uint16 converted on the device for movies).  File I/O goes through the hooks of
-``basic_image_manipulations`` (the reference's Bio-Formats stack is out of scope).
+``basic_image_manipulations`` / ``tiff_writer`` (defaults: the reference's aicsimageio stack when installed, else the
+package's own TIFF reader; the package's own OME-TIFF writer).
 
 ``bin_size > 1`` (SP:39-53, methods max_averages / max_std / multi_channel) and ``build_manifold`` (SP:87-165)
 run on the GPU too; they use the direct-FIR score (``mode="fast"`` behaves like "exact" for them).
@@ -114,8 +115,9 @@ def concatenate_time_points(files, fresh=None):
 
 
 def save_tiff(path, image, metadata=None, axes="", data_type=""):
-    """BIM:162-189 dtype convention + pluggable writer.  uint8/uint16 targets rescale to the
-    global maximum; the writer hook defaults to tifffile when installed."""
+    """BIM:162-189: dtype convention (uint8 / uint16 targets rescale to the global maximum) + a pluggable writer.
+    The default writer is the package's own OME-flavoured TIFF / BigTIFF writer (``tiff_io.write_tiff``: the
+    reference's ``OmeTiffWriter`` needs aicsimageio)."""
     if data_type and image.dtype != data_type and data_type in ("uint8", "uint16"):
         top = 255 if data_type == "uint8" else 65535
         image = np.round((image / np.max(image)) * top).astype(data_type)
@@ -123,11 +125,8 @@ def save_tiff(path, image, metadata=None, axes="", data_type=""):
 
 
 def _default_tiff_writer(path, image, axes, metadata):
-    try:
-        import tifffile
-    except ImportError as exc:                           # pragma: no cover - depends on the box
-        raise ImportError("no TIFF writer available: set surface_projection.tiff_writer") from exc
-    tifffile.imwrite(path, image, metadata={"axes": axes})
+    from . import tiff_io
+    tiff_io.write_tiff(path, image, axes=axes, metadata=metadata)
 
 
 tiff_writer = _default_tiff_writer        # replaceable hook: callable(path, image, axes, metadata)

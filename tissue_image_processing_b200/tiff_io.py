@@ -1,0 +1,431 @@
+"""Self-contained TIFF / BigTIFF (OME-TIFF flavoured) reader and writer for the projection drivers.
+
+The reference reads its inputs through aicsimageio + Bio-Formats (BIM:79-87, BIM:103-104: a Java stack that is not
+on a B200 box) and writes its outputs with aicsimageio's ``OmeTiffWriter`` (BIM:187-188).  The drivers of
+``surface_projection`` only need a small slice of that: an image object with ``dims.{T,C,Z,Y,X}``, ``set_scene``,
+``get_image_dask_data()`` (lazily sliceable, ``.compute()`` -> ndarray) and ``metadata`` on the input side, and
+"store this (T,C,Y,X) uint16 array as ``position%d.tif``" on the output side.  This module is that slice for plain
+uncompressed TIFF files, with no dependency besides numpy:
+
+  * ``write_tiff``  one strip per plane, the pixel data of all planes in ONE contiguous block right behind the header
+    (a single large write; the IFD chain follows it), classic TIFF below 4 GiB and BigTIFF above, an OME-XML block in
+    the first page's ImageDescription (DimensionOrder derived from the array's axes, so ``TCYX`` becomes the
+    ``XYCTZ`` of SP:323), physical pixel sizes taken from the metadata object when it carries them;
+  * ``TiffImage``   parses classic / BigTIFF, either byte order, uncompressed strips; plane order from the OME-XML or
+    ImageJ description (else: the pages are the z planes of one stack).  The planes are served from one read-only
+    memory mapping of the file: a (C,Z,Y,X) frame whose planes lie next to each other in the file comes back as a
+    VIEW of the mapping, so the pipeline's staging threads copy it from the page cache straight into pinned memory
+    (one host copy per frame, the same as for an array the caller already holds).
+
+Compressed, tiled or multi-sample (RGB) files are refused with a clear message - convert them first.
+"""
+from __future__ import annotations
+
+import mmap
+import os
+import re
+import struct
+import types
+
+import numpy as np
+
+_TYPE_SIZE = {1: 1, 2: 1, 3: 2, 4: 4, 5: 8, 6: 1, 7: 1, 8: 2, 9: 4, 10: 8, 11: 4, 12: 8, 13: 4, 16: 8, 17: 8, 18: 8}
+_TYPE_CODE = {1: "B", 2: "c", 3: "H", 4: "I", 6: "b", 7: "B", 8: "h", 9: "i", 11: "f", 12: "d", 13: "I", 16: "Q",
+              17: "q", 18: "Q"}
+_SAMPLE_FORMAT = {"u": 1, "i": 2, "f": 3}
+_OME_TYPE = {"uint8": "uint8", "uint16": "uint16", "uint32": "uint32", "int8": "int8", "int16": "int16",
+             "int32": "int32", "float32": "float", "float64": "double"}
+_OME_TYPE_BACK = {v: k for k, v in _OME_TYPE.items()}
+_CLASSIC_LIMIT = (1 << 32) - (1 << 16)            # stay clear of the 4 GiB offset limit of classic TIFF
+
+IMAGE_WIDTH, IMAGE_LENGTH, BITS, COMPRESSION, PHOTOMETRIC, DESCRIPTION, STRIP_OFFSETS = 256, 257, 258, 259, 262, 270, 273
+SAMPLES, ROWS_PER_STRIP, STRIP_COUNTS, PLANAR, SAMPLE_FORMAT, TILE_WIDTH = 277, 278, 279, 284, 339, 322
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# plane order
+# ----------------------------------------------------------------------------------------------------------------
+def dimension_order(axes):
+    """OME DimensionOrder of a C-ordered array with these axes: ``TCYX`` -> ``XYCTZ`` (the last non-XY axis varies
+    fastest from plane to plane; axes the array does not have are appended, they have size 1)."""
+    axes = axes.upper()
+    if not axes.endswith("YX") or len(set(axes)) != len(axes) or set(axes) - set("TCZYX"):
+        raise ValueError("axes must be a selection of T, C, Z followed by YX (got %r)" % axes)
+    lead = axes[:-2][::-1]
+    return "XY" + lead + "".join(a for a in "CZT" if a not in lead)
+
+
+def _plane_strides(order, sizes):
+    """{axis: plane-index stride} for an OME DimensionOrder string."""
+    strides, step = {}, 1
+    for a in order[2:]:
+        strides[a] = step
+        step *= sizes[a]
+    return strides
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# writer
+# ----------------------------------------------------------------------------------------------------------------
+def _attr(value):
+    return str(value).replace("&", "&amp;").replace('"', "&quot;").replace("<", "&lt;")
+
+
+def ome_xml(shape5, order, dtype, name="image", metadata=None):
+    """A minimal OME-XML block for one image of ``shape5`` = {axis: size}."""
+    phys = ""
+    pixels = getattr(getattr(metadata, "images", [None])[0], "pixels", None) if metadata is not None else None
+    for key, attr in (("physical_size_x", "PhysicalSizeX"), ("physical_size_y", "PhysicalSizeY"),
+                      ("physical_size_z", "PhysicalSizeZ")):
+        value = getattr(pixels, key, None)
+        if isinstance(value, (int, float)):
+            phys += ' %s="%r"' % (attr, float(value))
+    if metadata is not None and getattr(metadata, "images", None):
+        name = getattr(metadata.images[0], "name", name) or name
+    channels = "".join('<Channel ID="Channel:0:%d" SamplesPerPixel="1"/>' % c for c in range(shape5["C"]))
+    return ('<?xml version="1.0" encoding="UTF-8"?>'
+            '<OME xmlns="http://www.openmicroscopy.org/Schemas/OME/2016-06" Creator="tissue_image_processing_b200">'
+            '<Image ID="Image:0" Name="%s"><Pixels ID="Pixels:0" DimensionOrder="%s" Type="%s" BigEndian="false" '
+            'SizeX="%d" SizeY="%d" SizeZ="%d" SizeC="%d" SizeT="%d"%s>%s<TiffData/></Pixels></Image></OME>'
+            % (_attr(name), order, _OME_TYPE[str(np.dtype(dtype))], shape5["X"], shape5["Y"], shape5["Z"], shape5["C"],
+               shape5["T"], phys, channels))
+
+
+def write_tiff(path, image, axes="", metadata=None, bigtiff=None):
+    """Store ``image`` (axes = a selection of T, C, Z followed by YX; default: the trailing letters of TCZYX) as an
+    uncompressed little-endian TIFF, one page per YX plane in C order.  Has the signature of the
+    ``surface_projection.tiff_writer`` hook apart from the argument order (see ``hook_writer``)."""
+    image = np.asarray(image)
+    if str(image.dtype) not in _OME_TYPE:
+        raise TypeError("write_tiff: unsupported dtype %s" % image.dtype)
+    if image.ndim < 2 or image.ndim > 5:
+        raise ValueError("write_tiff takes 2-D to 5-D arrays")
+    axes = (axes or "TCZYX"[5 - image.ndim:]).upper()
+    if len(axes) != image.ndim:
+        raise ValueError("axes %r do not match a %d-D array" % (axes, image.ndim))
+    order = dimension_order(axes)
+    sizes = {a: 1 for a in "TCZYX"}
+    sizes.update(zip(axes, image.shape))
+    if image.dtype.byteorder == ">":
+        image = image.astype(image.dtype.newbyteorder("<"))
+    image = np.ascontiguousarray(image)
+    Y, X = sizes["Y"], sizes["X"]
+    planes = int(np.prod(image.shape[:-2], dtype=np.int64)) if image.ndim > 2 else 1
+    plane_bytes = Y * X * image.dtype.itemsize
+    desc = ome_xml(sizes, order, image.dtype, os.path.splitext(os.path.basename(path))[0], metadata).encode() + b"\0"
+    if bigtiff is None:
+        bigtiff = planes * plane_bytes + planes * 256 + len(desc) + 4096 > _CLASSIC_LIMIT
+    head = 16 if bigtiff else 8
+    desc_at = head
+    data_at = (desc_at + len(desc) + 63) // 64 * 64
+    ifd_at = (data_at + planes * plane_bytes + 15) // 16 * 16
+    if bigtiff:
+        count_fmt, entry_fmt, next_fmt, off_type = "<Q", "<HHQ8s", "<Q", 16
+    else:
+        count_fmt, entry_fmt, next_fmt, off_type = "<H", "<HHI4s", "<I", 4
+    inline = 8 if bigtiff else 4
+
+    def entry(tag, typ, count, value):
+        code = _TYPE_CODE[typ]
+        if typ == 2:
+            raw = value                                   # bytes, only ever stored out of line here
+        else:
+            raw = struct.pack("<%d%s" % (count, code), *([value] if count == 1 else value))
+        if len(raw) > inline:
+            raise ValueError("out-of-line value")         # pragma: no cover - the writer only emits inline values
+        return struct.pack(entry_fmt, tag, typ, count, raw.ljust(inline, b"\0"))
+
+    def page(k):
+        tags = [entry(IMAGE_WIDTH, 4, 1, X), entry(IMAGE_LENGTH, 4, 1, Y), entry(BITS, 3, 1, image.dtype.itemsize * 8),
+                entry(COMPRESSION, 3, 1, 1), entry(PHOTOMETRIC, 3, 1, 1)]
+        if k == 0:                                        # ASCII value out of line: count + offset
+            tags.append(struct.pack(entry_fmt, DESCRIPTION, 2, len(desc), struct.pack("<Q" if bigtiff else "<I", desc_at)))
+        tags += [entry(STRIP_OFFSETS, off_type, 1, data_at + k * plane_bytes), entry(SAMPLES, 3, 1, 1),
+                 entry(ROWS_PER_STRIP, 4, 1, Y), entry(STRIP_COUNTS, off_type, 1, plane_bytes),
+                 entry(SAMPLE_FORMAT, 3, 1, _SAMPLE_FORMAT[image.dtype.kind])]
+        return tags
+
+    ifds, at = [], ifd_at
+    for k in range(planes):
+        tags = page(k)
+        size = struct.calcsize(count_fmt) + sum(len(t) for t in tags) + struct.calcsize(next_fmt)
+        nxt = at + size if k + 1 < planes else 0
+        ifds.append(struct.pack(count_fmt, len(tags)) + b"".join(tags) + struct.pack(next_fmt, nxt))
+        at += size
+    if not bigtiff and at > _CLASSIC_LIMIT:
+        return write_tiff(path, image, axes, metadata, bigtiff=True)
+    with open(path, "wb") as f:
+        f.write(struct.pack("<2sHHHQ", b"II", 43, 8, 0, ifd_at) if bigtiff else struct.pack("<2sHI", b"II", 42, ifd_at))
+        f.write(desc)
+        f.write(b"\0" * (data_at - desc_at - len(desc)))
+        f.write(memoryview(image).cast("B"))
+        f.write(b"\0" * (ifd_at - data_at - planes * plane_bytes))
+        f.write(b"".join(ifds))
+    return path
+
+
+def hook_writer(path, image, axes, metadata):
+    """``surface_projection.tiff_writer`` hook: callable(path, image, axes, metadata)."""
+    write_tiff(path, image, axes=axes, metadata=metadata)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# reader
+# ----------------------------------------------------------------------------------------------------------------
+class TiffFormatError(ValueError):
+    pass
+
+
+def _parse_ifds(buf):
+    """[{tag: value(s)}] for every page of the TIFF in ``buf`` (bytes-like), plus the byte-order prefix."""
+    if len(buf) < 8 or bytes(buf[:2]) not in (b"II", b"MM"):
+        raise TiffFormatError("not a TIFF file")
+    bo = "<" if bytes(buf[:2]) == b"II" else ">"
+    magic = struct.unpack_from(bo + "H", buf, 2)[0]
+    if magic == 42:
+        big, at = False, struct.unpack_from(bo + "I", buf, 4)[0]
+    elif magic == 43:
+        big, at = True, struct.unpack_from(bo + "Q", buf, 8)[0]
+    else:
+        raise TiffFormatError("not a TIFF file (magic %d)" % magic)
+    count_fmt, entry_size, inline, off_fmt = (bo + "Q", 20, 8, bo + "Q") if big else (bo + "H", 12, 4, bo + "I")
+    pages, seen = [], set()
+    while at:
+        if at in seen or at + struct.calcsize(count_fmt) > len(buf):
+            raise TiffFormatError("corrupt IFD chain")
+        seen.add(at)
+        n = struct.unpack_from(count_fmt, buf, at)[0]
+        pos = at + struct.calcsize(count_fmt)
+        tags = {}
+        for _ in range(n):
+            tag, typ = struct.unpack_from(bo + "HH", buf, pos)
+            count = struct.unpack_from(off_fmt, buf, pos + 4)[0]
+            size = _TYPE_SIZE.get(typ)
+            if size is not None:
+                where = pos + 4 + struct.calcsize(off_fmt)
+                if size * count > inline:
+                    where = struct.unpack_from(off_fmt, buf, where)[0]
+                if where + size * count > len(buf):
+                    raise TiffFormatError("tag %d points outside the file" % tag)
+                if typ == 2:
+                    tags[tag] = bytes(buf[where:where + count]).split(b"\0")[0].decode("utf-8", "replace")
+                elif typ in (5, 10):                     # rationals: not needed, keep the raw pairs
+                    tags[tag] = struct.unpack_from(bo + "%d%s" % (2 * count, "I" if typ == 5 else "i"), buf, where)
+                else:
+                    vals = struct.unpack_from(bo + "%d%s" % (count, _TYPE_CODE[typ]), buf, where)
+                    tags[tag] = vals[0] if count == 1 else vals
+            pos += entry_size
+        pages.append(tags)
+        at = struct.unpack_from(off_fmt, buf, pos)[0]
+    if not pages:
+        raise TiffFormatError("TIFF without pages")
+    return pages, bo
+
+
+def _as_tuple(v):
+    return tuple(v) if isinstance(v, (tuple, list)) else (v,)
+
+
+def _describe(description, n_pages):
+    """(sizes {T,C,Z}, DimensionOrder, extra metadata) from the first page's ImageDescription."""
+    text = description or ""
+    m = re.search(r"<Pixels\b[^>]*>", text)
+    if m:
+        attrs = dict(re.findall(r'(\w+)="([^"]*)"', m.group(0)))
+        try:
+            sizes = {a: int(attrs["Size" + a]) for a in "TCZ"}
+            order = attrs.get("DimensionOrder", "XYZCT").upper()
+            if sorted(order) == sorted("XYZCT") and order.startswith("XY") and \
+                    sizes["T"] * sizes["C"] * sizes["Z"] == n_pages:
+                phys = {k: float(attrs[v]) for k, v in (("physical_size_x", "PhysicalSizeX"),
+                                                        ("physical_size_y", "PhysicalSizeY"),
+                                                        ("physical_size_z", "PhysicalSizeZ")) if v in attrs}
+                name = re.search(r'<Image\b[^>]*\bName="([^"]*)"', text)
+                return sizes, order, dict(phys, name=name.group(1) if name else None)
+        except (KeyError, ValueError):
+            pass
+    if text.startswith("ImageJ="):
+        kv = dict(line.split("=", 1) for line in text.splitlines() if "=" in line)
+        try:
+            sizes = {"C": int(kv.get("channels", 1)), "Z": int(kv.get("slices", 1)), "T": int(kv.get("frames", 1))}
+            if sizes["T"] * sizes["C"] * sizes["Z"] == n_pages:
+                extra = {}
+                if "spacing" in kv:
+                    extra["physical_size_z"] = float(kv["spacing"])
+                return sizes, "XYCZT", extra
+        except ValueError:
+            pass
+    return {"T": 1, "C": 1, "Z": n_pages}, "XYZCT", {}
+
+
+class _LazyPlanes:
+    """The (T,C,Z,Y,X) view ``get_image_dask_data()`` hands out: indexing with ints / slices narrows it, ``compute()``
+    reads the planes.  Nothing is copied before ``compute``; a block whose planes are adjacent in the file (and whose
+    rows are whole) is returned as a read-only view of the file mapping."""
+
+    def __init__(self, image, index=None):
+        self._image = image
+        self._index = index if index is not None else [np.arange(n) for n in image.shape5]
+
+    @property
+    def shape(self):
+        return tuple(len(ix) for ix in self._index if not isinstance(ix, (int, np.integer)))
+
+    ndim = property(lambda self: len(self.shape))
+    dtype = property(lambda self: self._image.dtype)
+
+    def __getitem__(self, idx):
+        idx = idx if isinstance(idx, tuple) else (idx,)
+        if any(i is Ellipsis for i in idx):
+            k = idx.index(Ellipsis)
+            idx = idx[:k] + (slice(None),) * (self.ndim - len(idx) + 1) + idx[k + 1:]
+        if len(idx) > self.ndim:
+            raise IndexError("too many indices")
+        new, it = [], iter(idx)
+        for ix in self._index:
+            if isinstance(ix, (int, np.integer)):
+                new.append(ix)
+                continue
+            sel = next(it, slice(None))
+            if isinstance(sel, (int, np.integer)):
+                new.append(int(ix[sel]))
+            elif isinstance(sel, slice):
+                new.append(ix[sel])
+            else:
+                raise TypeError("only integers and slices index a lazy TIFF stack")
+        return _LazyPlanes(self._image, new)
+
+    def compute(self):
+        return self._image._read(self._index)
+
+    def __array__(self, dtype=None, copy=None):
+        out = self.compute()
+        return out.astype(dtype) if dtype is not None and out.dtype != dtype else out
+
+
+class TiffImage:
+    """The surface of ``aicsimageio.AICSImage`` the drivers use, for one uncompressed TIFF / BigTIFF file (one
+    scene)."""
+
+    def __init__(self, path):
+        self.path = path
+        with open(path, "rb") as f:
+            self._map = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
+        pages, bo = _parse_ifds(self._map)
+        first = pages[0]
+        for tags in pages:
+            if tags.get(COMPRESSION, 1) != 1:
+                raise NotImplementedError("%s: compressed TIFF (scheme %s) - store it uncompressed" % (path, tags[COMPRESSION]))
+            if TILE_WIDTH in tags:
+                raise NotImplementedError("%s: tiled TIFF - store it in strips" % path)
+            if tags.get(SAMPLES, 1) != 1:
+                raise NotImplementedError("%s: %d samples per pixel (RGB?) - one sample per pixel expected"
+                                          % (path, tags[SAMPLES]))
+            if any(tags.get(k) != first.get(k) for k in (IMAGE_WIDTH, IMAGE_LENGTH, BITS, SAMPLE_FORMAT)):
+                raise NotImplementedError("%s: pages of different shape or type" % path)
+        bits, fmt = first.get(BITS, 1), first.get(SAMPLE_FORMAT, 1)
+        kind = {1: "u", 2: "i", 3: "f"}.get(fmt)
+        if kind is None or bits not in (8, 16, 32, 64):
+            raise NotImplementedError("%s: %d-bit samples of format %d" % (path, bits, fmt))
+        self.dtype = np.dtype("%s%s%d" % (bo, kind, bits // 8))
+        self.Y, self.X = int(first[IMAGE_LENGTH]), int(first[IMAGE_WIDTH])
+        self._strips = []                                # per page: [(offset, bytes)]
+        for tags in pages:
+            offs, cnts = _as_tuple(tags[STRIP_OFFSETS]), _as_tuple(tags[STRIP_COUNTS])
+            if len(offs) != len(cnts) or sum(cnts) != self.Y * self.X * self.dtype.itemsize:
+                raise TiffFormatError("%s: strip sizes do not add up to a plane" % path)
+            self._strips.append(list(zip(offs, cnts)))
+        sizes, order, extra = _describe(first.get(DESCRIPTION), len(pages))
+        self._sizes, self.dimension_order, self._extra = sizes, order, extra
+        self._strides = _plane_strides(order, sizes)
+        self.shape5 = (sizes["T"], sizes["C"], sizes["Z"], self.Y, self.X)
+        plane_bytes = self.Y * self.X * self.dtype.itemsize
+        # the common layout (and the one write_tiff produces): every plane one run of bytes, plane k+1 right behind k
+        starts = [s[0][0] if all(a[0] + a[1] == b[0] for a, b in zip(s, s[1:])) else None for s in self._strips]
+        self._plane_at = starts
+        self._packed = all(s is not None for s in starts) and \
+            all(starts[k] + plane_bytes == starts[k + 1] for k in range(len(starts) - 1))
+        self.scene = 0
+
+    # ---- AICSImage surface ---------------------------------------------------------------------------
+    def set_scene(self, i):
+        if int(i) != 0:
+            raise IndexError("%s holds one scene (asked for %d)" % (self.path, int(i)))
+        self.scene = 0
+
+    @property
+    def dims(self):
+        T, C, Z, Y, X = self.shape5
+        return types.SimpleNamespace(T=T, C=C, Z=Z, Y=Y, X=X, order="TCZYX", shape=self.shape5)
+
+    def get_image_dask_data(self):
+        return _LazyPlanes(self)
+
+    def get_image_data(self):
+        return self.get_image_dask_data().compute()
+
+    @property
+    def metadata(self):
+        """An object shaped like the OME model the drivers touch (images[i].name / .pixels / .stage_label); what the
+        file does not say is None."""
+        T, C, Z, _, _ = self.shape5
+        pixels = types.SimpleNamespace(
+            size_t=T, size_c=C, size_z=Z, size_y=self.Y, size_x=self.X, dimension_order=self.dimension_order,
+            type=_OME_TYPE.get(str(self.dtype.newbyteorder("=")), str(self.dtype)),
+            physical_size_x=self._extra.get("physical_size_x"), physical_size_y=self._extra.get("physical_size_y"),
+            physical_size_z=self._extra.get("physical_size_z"), planes=list(range(T * C * Z)))
+        stage = types.SimpleNamespace(x=None, y=None, z=None, x_unit=None, y_unit=None, z_unit=None)
+        name = self._extra.get("name") or os.path.splitext(os.path.basename(self.path))[0]
+        return types.SimpleNamespace(images=[types.SimpleNamespace(name=name, pixels=pixels, stage_label=stage)])
+
+    def close(self):
+        self._map.close()
+
+    # ---- planes --------------------------------------------------------------------------------------
+    def _plane(self, k):
+        """Plane k as a (Y, X) array: a view of the mapping when its strips are adjacent, else assembled."""
+        at = self._plane_at[k]
+        if at is not None:
+            return np.frombuffer(self._map, dtype=self.dtype, count=self.Y * self.X, offset=at).reshape(self.Y, self.X)
+        raw = b"".join(self._map[o:o + n] for o, n in self._strips[k])
+        return np.frombuffer(raw, dtype=self.dtype).reshape(self.Y, self.X)
+
+    def _read(self, index):
+        t_ix, c_ix, z_ix, y_ix, x_ix = index
+        lead = [np.atleast_1d(ix) for ix in (t_ix, c_ix, z_ix)]
+        keep = [not isinstance(ix, (int, np.integer)) for ix in index]
+        planes = (lead[0][:, None, None] * self._strides["T"] + lead[1][None, :, None] * self._strides["C"]
+                  + lead[2][None, None, :] * self._strides["Z"])
+        ys, xs = np.atleast_1d(y_ix), np.atleast_1d(x_ix)
+        out_shape = tuple(n for n, k in zip(planes.shape + (len(ys), len(xs)), keep) if k)
+        native = self.dtype.newbyteorder("=")
+        flat = planes.reshape(-1)
+        whole_rows = len(xs) == self.X and len(ys) > 0 and np.array_equal(ys, np.arange(ys[0], ys[0] + len(ys)))
+        if (self._packed and self.dtype.isnative and whole_rows and flat.size > 0 and
+                (flat.size == 1 or (len(ys) == self.Y and np.array_equal(flat, np.arange(flat[0], flat[0] + flat.size))))):
+            base = self._plane_at[int(flat[0])] + int(ys[0]) * self.X * self.dtype.itemsize
+            count = (flat.size - 1) * self.Y * self.X + len(ys) * self.X
+            return np.frombuffer(self._map, dtype=self.dtype, count=count, offset=base).reshape(out_shape)
+        out = np.empty(planes.shape + (len(ys), len(xs)), dtype=native)
+        row, col = _selector(ys), _selector(xs)
+        if not isinstance(row, slice) and not isinstance(col, slice):
+            row, col = np.ix_(row, col)
+        for pos in np.ndindex(*planes.shape):
+            out[pos] = self._plane(int(planes[pos]))[row, col]
+        return out.reshape(out_shape)
+
+
+def _selector(ix):
+    """A slice for an increasing arithmetic progression of indices (the usual case: a tile), else the index array."""
+    if len(ix) == 0:
+        return slice(0, 0)
+    if len(ix) == 1:
+        return slice(int(ix[0]), int(ix[0]) + 1)
+    step = int(ix[1] - ix[0])
+    if step > 0 and np.array_equal(ix, np.arange(ix[0], ix[0] + step * len(ix), step)):
+        return slice(int(ix[0]), int(ix[-1]) + 1, step)
+    return np.asarray(ix)
+
+
+def is_tiff_path(path):
+    return str(path).lower().endswith((".tif", ".tiff", ".btf", ".tf8"))
