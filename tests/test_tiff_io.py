@@ -181,18 +181,16 @@ def test_metadata_round_trip_and_dimension_order_rules(tmp_path):
 
 def test_tiled_driver_on_a_real_tiff_with_the_default_reader_and_writer(tmp_path, monkeypatch):
     """large_image_projection (SP:279-316) from a .tif on disk to ``*_projection.tif`` / ``*_zmap.npy`` with no I/O
-    hook installed: aicsimageio is absent here, so the default ``open_image`` falls back to TiffImage and the default
+    hook installed: without aicsimageio the default ``open_image`` falls back to TiffImage and the default
     writer is tiff_io.  The operator seam runs the oracle - this is the host path, not the kernels."""
     pytest.importorskip("torch")
     from tissue_image_processing_b200 import basic_image_manipulations as bim
     from tissue_image_processing_b200 import surface_projection as sp
     from tissue_image_processing_b200 import tiff_io
     from tissue_image_processing_b200.movie import FramePipeline
-    try:
-        import aicsimageio  # noqa: F401
-        pytest.skip("aicsimageio installed: the default reader is the reference's")
-    except ImportError:
-        pass
+    import sys
+    for name in ("aicsimageio", "aicsimageio.readers"):       # absent here (other tests may have stubbed them)
+        monkeypatch.setitem(sys.modules, name, None)
     monkeypatch.setattr(bim, "open_image", bim._default_open_image)
     monkeypatch.setattr(sp, "tiff_writer", sp._default_tiff_writer)
     big = synth.synth_stack(6, 40, 48, C=2, seed=9)[None]                  # (1, C, Z, Y, X)
@@ -254,3 +252,36 @@ def test_classic_files_switch_to_bigtiff_at_the_offset_limit(tmp_path, monkeypat
     assert magic == [42, 43]
     assert np.array_equal(tiff_io.TiffImage(large).get_image_data()[0, 0], a)
     assert np.array_equal(_pil_pages(large), a)
+
+
+def test_command_line_runs_on_tiff_movies(tmp_path, monkeypatch):
+    """``python -m tissue_image_processing_b200.surface_projection -i DIR -m 2 -r 0`` on a directory that holds
+    m1.tif / m2.tif instead of the reference's m1.czi / m2.czi (SP:413): default reader, default writer, the whole
+    driver - only the GPU call is replaced by the oracle."""
+    pytest.importorskip("torch")
+    import sys
+    from tissue_image_processing_b200 import basic_image_manipulations as bim
+    from tissue_image_processing_b200 import surface_projection as sp
+    from tissue_image_processing_b200 import tiff_io
+    from tissue_image_processing_b200.movie import FramePipeline
+    for name in ("aicsimageio", "aicsimageio.readers"):
+        monkeypatch.setitem(sys.modules, name, None)
+    monkeypatch.setattr(bim, "open_image", bim._default_open_image)
+    monkeypatch.setattr(sp, "tiff_writer", sp._default_tiff_writer)
+    monkeypatch.setattr(sp, "_default_pipeline", lambda mode, out_dtype: FramePipeline(
+        operator=orc.time_point_surface_projection, out_dtype=out_dtype))
+    movies = [np.stack([synth.synth_stack(6, 24, 28, C=1, seed=30 + k, t=t) for t in range(n)]) for k, n in ((0, 3), (1, 2))]
+    for k, m in enumerate(movies):
+        tiff_io.write_tiff(str(tmp_path / ("m%d.tif" % (k + 1))), m, "TCZYX")
+    out = tmp_path / "out"
+    out.mkdir()
+    assert sp._movie_file(str(tmp_path), 3).endswith("m3.czi")              # nothing there: the reference's name
+    assert sp.main(["-i", str(tmp_path), "-o", str(out), "-m", "2", "-r", "0"]) == 0
+    got = tiff_io.TiffImage(str(out / "position1.tif"))
+    assert got.shape5 == (5, 1, 1, 24, 28)
+    frames = list(movies[0]) + list(movies[1])
+    want = np.stack([orc.time_point_surface_projection(f[None], "TCZYX", 0, airyscan=False).astype("uint16")
+                     for f in frames])
+    assert np.array_equal(got.get_image_data()[:, :, 0], want)
+    assert np.load(out / "zmap_position1.npy").shape == (5, 1, 1, 24, 28)
+    assert sorted(os.listdir(out)) == ["position1.tif", "stage_locations_position1.pkl", "zmap_position1.npy"]

@@ -416,6 +416,18 @@ def getOptions(argv=None):
     return parser.parse_known_args(argv)
 
 
+def _movie_file(input_dir, number):
+    """``m<number>.czi`` as in SP:413; when that file does not exist but ``m<number>.tif`` / ``.tiff`` does (a movie
+    converted for the package's own TIFF reader), that one."""
+    czi = os.path.join(input_dir, "m%d.czi" % number)
+    if not os.path.exists(czi):
+        for ext in (".tif", ".tiff"):
+            other = os.path.join(input_dir, "m%d%s" % (number, ext))
+            if os.path.exists(other):
+                return other
+    return czi
+
+
 def main(argv=None):
     """SP:381-423: dispatch to the fixed-sample, per-file or movie driver exactly as the reference's __main__."""
     from ast import literal_eval
@@ -441,7 +453,7 @@ def main(argv=None):
             final = list(literal_eval(options.position_final_movie))
         else:
             final = [options.movie_number] * options.position_number
-        files = [os.path.join(input_dir, "m%d.czi" % (i + 1)) for i in range(options.movie_number)]
+        files = [_movie_file(input_dir, i + 1) for i in range(options.movie_number)]
         movie_surface_projection(files, options.reference_channel, final, options.position_number, output_dir,
                                  options.method, options.bin_size, options.build_manifold, options.only_position,
                                  options.zmin, options.zmax, options.airyscan)

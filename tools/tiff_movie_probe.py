@@ -1,0 +1,72 @@
+"""Development probe: the movie driver from a real TIFF file on disk to real output files (tiff_io reader / writer,
+no I/O hook), timed end to end.
+    python tools/tiff_movie_probe.py [T Z Y X] [--oracle]
+Writes a (T,1,Z,Y,X) uint16 movie (default 40 x 48 x 1024 x 1024 = BASELINE configs[2] frames, 3.8 GB) to a
+temporary directory, runs movie_surface_projection on it twice (the first run warms the GPU path and the page cache)
+and prints the seconds of the second run: frames come out of the file mapping (page cache) as read-only views, are
+staged into pinned memory by the pipeline's host threads, projected, returned as uint16 and written as
+position1.tif + zmap_position1.npy.  --oracle replaces the GPU by the CPU oracle (host-logic dry run, small sizes)."""
+import contextlib
+import io
+import os
+import shutil
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tissue_image_processing_b200 import basic_image_manipulations as bim        # noqa: E402
+from tissue_image_processing_b200 import surface_projection as sp                # noqa: E402
+from tissue_image_processing_b200 import tiff_io                                 # noqa: E402
+from tissue_image_processing_b200.movie import FramePipeline                     # noqa: E402
+
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+oracle = "--oracle" in sys.argv
+T, Z, Y, X = (int(v) for v in args[:4]) if len(args) >= 4 else (40, 48, 1024, 1024)
+
+if oracle:
+    from oracle import surface_projection_oracle as orc
+    from oracle import synth
+    distinct = [synth.synth_stack(Z, Y, X, C=1, seed=3, t=t) for t in range(min(T, 4))]
+    pipe = FramePipeline(operator=orc.time_point_surface_projection, out_dtype="uint16")
+else:
+    import torch
+    import bench
+    dev = torch.device("cuda", 0)
+    distinct = [bench.synth_frame_device(torch, 70 + i, dev, (Z, Y, X)).cpu().numpy()[None] for i in range(min(T, 4))]
+    pipe = FramePipeline(out_dtype="uint16")
+movie = np.empty((T, 1, Z, Y, X), dtype=np.uint16)
+for t in range(T):
+    movie[t] = distinct[t % len(distinct)]
+work = tempfile.mkdtemp(prefix="tsp_tiff_probe_")
+try:
+    path = os.path.join(work, "m1.tif")
+    t0 = time.perf_counter()
+    tiff_io.write_tiff(path, movie, "TCZYX")
+    print("wrote %s: %.2f GB in %.2f s" % (path, os.path.getsize(path) / 1e9, time.perf_counter() - t0), flush=True)
+    bim.open_image = tiff_io.TiffImage
+    sp.tiff_writer = tiff_io.hook_writer
+    for run in ("warm", "timed"):
+        out = os.path.join(work, run)
+        os.mkdir(out)
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(io.StringIO()):
+            sp.movie_surface_projection([path], 0, [1], 1, out, "max_averages", 1, False, 0, 0, 0, False,
+                                        frame_pipeline=pipe)
+        s = time.perf_counter() - t0
+        print("%s run: %d frames of %dx%dx%d in %.3f s = %.0f frames/s  (%s), outputs %s" % (
+            run, T, Z, Y, X, s, T / s, {k: round(v, 3) for k, v in sp.last_job_timings.items()},
+            {f: os.path.getsize(os.path.join(out, f)) for f in sorted(os.listdir(out))}), flush=True)
+    got = tiff_io.TiffImage(os.path.join(work, "timed", "position1.tif"))
+    assert got.shape5 == (T, 1, 1, Y, X) and got.dtype == np.uint16, got.shape5
+    first = got.get_image_dask_data()[0, 0, 0].compute()
+    again = got.get_image_dask_data()[len(distinct), 0, 0].compute() if T > len(distinct) else first
+    assert first.any() and np.array_equal(first, again), "frames t and t + %d hold the same stack" % len(distinct)
+    if not oracle:
+        want = sp.time_point_surface_projection(movie[0:1], "TCZYX", 0, airyscan=False)
+        assert np.array_equal(first, want[0].astype(np.uint16)), "file differs from the blocking operator call"
+    print("output file checked", flush=True)
+finally:
+    shutil.rmtree(work, ignore_errors=True)
