@@ -285,3 +285,86 @@ def test_command_line_runs_on_tiff_movies(tmp_path, monkeypatch):
     assert np.array_equal(got.get_image_data()[:, :, 0], want)
     assert np.load(out / "zmap_position1.npy").shape == (5, 1, 1, 24, 28)
     assert sorted(os.listdir(out)) == ["position1.tif", "stage_locations_position1.pkl", "zmap_position1.npy"]
+
+
+@pytest.mark.parametrize("shape,dtype", [((3, 1, 1, 5, 7), "uint16"), ((0, 4), "float64"), ((), "int64"),
+                                         ((5, 1, 1, 1200, 1500), "uint16")])
+def test_save_npy_writes_the_bytes_np_save_writes(tmp_path, shape, dtype):
+    """The last case (18 MB) is cut into spans written by several threads."""
+    from tissue_image_processing_b200 import tiff_io
+    a = (np.random.default_rng(3).random(shape) * 60000).astype(dtype)
+    tiff_io.save_npy(str(tmp_path / "a.npy"), a, threads=5)
+    np.save(tmp_path / "b.npy", a)
+    assert (tmp_path / "a.npy").read_bytes() == (tmp_path / "b.npy").read_bytes()
+    f = np.asfortranarray(np.arange(12.0).reshape(3, 4))
+    tiff_io.save_npy(str(tmp_path / "f.npy"), f)
+    assert np.array_equal(np.load(tmp_path / "f.npy"), f)
+
+
+def test_spans_cover_the_range_once():
+    from tissue_image_processing_b200 import tiff_io
+    for nbytes in (1, 65535, 65536, 65537, 10 ** 6, (1 << 24) + 13):
+        for parts in (1, 2, 3, 8, 64):
+            spans = tiff_io._spans(nbytes, parts)
+            assert spans[0][0] == 0 and spans[-1][1] == nbytes and len(spans) <= parts
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:])) and all(b > a for a, b in spans)
+            assert all(a % 65536 == 0 for a, _ in spans)
+
+
+def test_threaded_write_and_read_into(tmp_path):
+    """An 18 MB movie: the writer's pixel block and ``read_into`` of a frame run on several threads; a frame is one
+    run of bytes of the file (preadv into the caller's buffer), an XY tile is gathered plane by plane."""
+    from concurrent.futures import ThreadPoolExecutor
+    from tissue_image_processing_b200 import tiff_io
+    a = np.random.default_rng(4).integers(0, 65535, (2, 1, 9, 1000, 1000), dtype=np.uint16)
+    path = str(tmp_path / "m.tif")
+    tiff_io.write_tiff(path, a, "TCZYX", threads=4)
+    img = tiff_io.TiffImage(path)
+    data = img.get_image_dask_data()
+    assert np.array_equal(data.compute(), a) and np.array_equal(_pil_pages(path)[11], a[1, 0, 2])
+    frame = data[1:2][0]
+    assert frame.shape == (1, 9, 1000, 1000) and frame.dtype == np.uint16
+    for kw in (dict(), dict(threads=3), dict(pool=ThreadPoolExecutor(4))):
+        out = np.zeros(frame.shape, np.uint16)
+        assert frame.read_into(out, **kw) is out and np.array_equal(out, a[1])
+    tile = data[0, :, :, 100:228, 64:192]
+    out = np.zeros(tile.shape, np.uint16)
+    tile.read_into(out, threads=3)
+    assert np.array_equal(out, a[0, :, :, 100:228, 64:192])
+    for bad in (np.zeros((1, 9, 1000, 999), np.uint16), np.zeros(frame.shape, np.int16),
+                np.zeros((1, 9, 1000, 2000), np.uint16)[..., ::2]):
+        with pytest.raises(ValueError):
+            frame.read_into(bad)
+    img.close()
+
+
+def test_pipeline_stages_tiff_frames_by_read_into(tmp_path, monkeypatch):
+    """movie.FramePipeline.project_movie on a TIFF movie, the C ABI replaced by the fake of test_drivers_cpu: the
+    frames reach the (here: ordinary-memory) staging buffers through ``read_into``, never as arrays; with
+    TSP_TIFF_MMAP=1 they travel as read-only views and are copied by the staging threads.  Same results."""
+    pytest.importorskip("torch")
+    from tests.test_drivers_cpu import _FakeNative
+    from tissue_image_processing_b200 import basic_image_manipulations as bim
+    from tissue_image_processing_b200 import movie, tiff_io
+    a = np.random.default_rng(6).integers(0, 60000, (7, 2, 4, 64, 96), dtype=np.uint16)
+    path = str(tmp_path / "m.tif")
+    tiff_io.write_tiff(path, a, "TCZYX")
+    monkeypatch.setattr(bim, "open_image", tiff_io.TiffImage)
+    monkeypatch.setattr(movie._Staging, "is_pinned", staticmethod(lambda arr: False))
+    reads = []
+    real = tiff_io._LazyPlanes.read_into
+    monkeypatch.setattr(tiff_io._LazyPlanes, "read_into", lambda self, out, **kw: (reads.append(out.shape), real(self, out, **kw))[1])
+    for env, n_reads in ((None, 7), ("1", 0)):
+        fake = _FakeNative()
+        monkeypatch.setattr(movie, "_native", fake)
+        if env:
+            monkeypatch.setenv("TSP_TIFF_MMAP", env)
+        pipe = movie.FramePipeline.__new__(movie.FramePipeline)
+        pipe.operator, pipe.mode, pipe.out_dtype, pipe.devices, pipe.slots, pipe.copy_threads, pipe.h2d_bytes = (
+            None, "fast", "uint16", [0], 2, 3, 0)
+        proj = np.zeros((7, 2, 1, 64, 96), np.uint16)
+        zmap = np.zeros((7, 1, 1, 64, 96), np.uint16)
+        del reads[:]
+        owned = pipe.project_movie(path, 0, proj, zmap, reference_channel=0, airyscan=False)
+        assert owned == list(range(7)) and len(reads) == n_reads and pipe.h2d_bytes == a.nbytes
+        assert np.array_equal(proj[:, :, 0], a.max(axis=2)) and np.array_equal(zmap[:, 0, 0], a[:, 0].argmax(axis=1))

@@ -343,7 +343,20 @@ class _Staging:
         return self.bufs[slot] is not None and arr is self.bufs[slot]
 
     def stage(self, slot, stack):
-        """-> C-contiguous uint16 (C,Z,Y,X) array in pinned memory holding ``stack`` (itself when already pinned)."""
+        """-> C-contiguous uint16 (C,Z,Y,X) array in pinned memory holding ``stack`` (itself when already pinned).
+        A lazy block of a file (``tiff_io``: has ``read_into``) is read straight into the pinned buffer by the copy
+        threads - the only host copy of that frame."""
+        if hasattr(stack, "read_into"):
+            if stack.ndim != 4:
+                raise RuntimeError("sequence argument must have length equal to input rank")
+            dt = np.dtype(stack.dtype)
+            if dt.kind == "u" and dt.itemsize == 2:
+                buf = self.bufs[slot]
+                if buf is None or buf.shape != tuple(stack.shape):
+                    buf = self.bufs[slot] = _native.pinned_empty(tuple(stack.shape), np.uint16)
+                stack.read_into(buf, threads=self.copy_threads, pool=self.pool)
+                return buf
+            stack = stack.compute()
         stack = as_uint16_stack(stack)
         if stack.ndim != 4:
             raise RuntimeError("sequence argument must have length equal to input rank")
@@ -590,7 +603,11 @@ class FramePipeline:
 
         def frames():
             for t in counter.claims(T):
-                yield t, np.asarray(data[t:t + 1].compute())[0]          # (C, Z, Y, X)
+                chunk = data[t:t + 1]
+                if hasattr(chunk, "read_into") and self.operator is None and not os.environ.get("TSP_TIFF_MMAP"):
+                    yield t, chunk[0]          # lazy (C, Z, Y, X) block of a TIFF: staged by preadv into pinned memory
+                else:
+                    yield t, np.asarray(chunk.compute())[0]              # (C, Z, Y, X)
 
         def sink(t, proj, zmap, status):
             out_projection[t, :, 0] = proj

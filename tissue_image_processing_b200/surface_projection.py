@@ -33,6 +33,7 @@ from . import _native
 from . import basic_image_manipulations as bim
 from .basic_image_manipulations import put_channel_axis_first, read_image_in_chunks  # noqa: F401
 from .movie import allocate_outputs, as_uint16_stack, finish_outputs, rank_world
+from .tiff_io import save_npy
 
 DEFAULT_MODE = os.environ.get("TSP_MODE", "fast")
 last_job_timings = {}        # seconds of the last movie_surface_projection call on this rank, by phase (diagnostics)
@@ -258,8 +259,8 @@ def movie_surface_projection(files, reference_channel, position_final_movie, ini
             # the resume files of SP:193-194 exist to restart an interrupted run at the next job; those of the very
             # last job would be deleted a moment later by the clean-up below (SP:235-237) - they are not written
             if job_index + 1 < len(jobs):
-                np.save(proj_path, fresh[proj_path])
-                np.save(zmap_path, zmap)
+                save_npy(proj_path, fresh[proj_path])
+                save_npy(zmap_path, zmap)
             timings["resume_save_s"] += time.perf_counter() - t0
     t0 = time.perf_counter()
     if root:
@@ -270,8 +271,8 @@ def movie_surface_projection(files, reference_channel, position_final_movie, ini
             save_tiff(os.path.join(output_dir, output_name + "position%d.tif" % (position + 1)),
                       concatenate_time_points(proj_files, fresh), metadata=metadata, axes="TCYX", data_type="uint16")
             zmaps = [_load_uint16(z, fresh) for z in zmap_files]
-            np.save(os.path.join(output_dir, output_name + "zmap_position%d.npy" % (position + 1)),
-                    zmaps[0] if len(zmaps) == 1 else np.concatenate(zmaps, axis=0))
+            save_npy(os.path.join(output_dir, output_name + "zmap_position%d.npy" % (position + 1)),
+                     zmaps[0] if len(zmaps) == 1 else np.concatenate(zmaps, axis=0))
         save_stage_positions(files, position_final_movie, initial_positions_number, output_dir,
                              only_position=only_position, output_name=output_name)
         for proj_files, zmap_files in resume.values():
@@ -357,8 +358,8 @@ def large_image_projection(input_dir, output_dir, input_file_name, position=1, r
             out_proj = projection.reshape((dims.T, dims.C, dims.Y, dims.X) if dims.T > 1 else (dims.C, dims.Y, dims.X))
             save_tiff(os.path.join(output_dir, input_file_name.replace(postfix, tag + "_projection.tif")), out_proj,
                       axes="TCYX" if dims.T > 1 else "CYX", data_type="uint16")
-            np.save(os.path.join(output_dir, input_file_name.replace(postfix, tag + "_zmap.npy")),
-                    zmap.reshape((dims.T, dims.Y, dims.X)))
+            save_npy(os.path.join(output_dir, input_file_name.replace(postfix, tag + "_zmap.npy")),
+                     zmap.reshape((dims.T, dims.Y, dims.X)))
         outputs.close()                                # rank 0 has saved the arrays: their backing can go
     _job_barrier()
 

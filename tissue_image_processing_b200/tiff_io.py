@@ -43,6 +43,81 @@ SAMPLES, ROWS_PER_STRIP, STRIP_COUNTS, PLANAR, SAMPLE_FORMAT, TILE_WIDTH = 277, 
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# bulk file I/O on several host threads
+# ----------------------------------------------------------------------------------------------------------------
+_BULK_MIN = 16 << 20                              # below this one call does it
+
+
+def _spans(nbytes, parts, align=1 << 16):
+    """Cut [0, nbytes) into at most ``parts`` contiguous spans whose inner boundaries are multiples of ``align``."""
+    parts = max(1, min(int(parts), (nbytes + align - 1) // align))
+    cuts = sorted({min(nbytes, (nbytes * k // parts + align - 1) // align * align) for k in range(parts + 1)} | {0, nbytes})
+    return [(a, b) for a, b in zip(cuts, cuts[1:]) if b > a]
+
+
+def _pwrite_span(fd, mv, at):
+    done = 0
+    while done < len(mv):
+        done += os.pwrite(fd, mv[done:done + (1 << 30)], at + done)
+
+
+def _pread_span(fd, mv, at):
+    done = 0
+    while done < len(mv):
+        n = os.preadv(fd, [mv[done:done + (1 << 30)]], at + done)
+        if n <= 0:
+            raise OSError("short read at offset %d" % (at + done))
+        done += n
+
+
+def _bulk(op, fd, mv, at, threads=1, pool=None):
+    """Run ``op`` (a span writer / reader) over the bytes of ``mv`` at file offset ``at``.  The kernel's copy between
+    the page cache and user memory runs at ~2 GB/s on one thread; spans on several threads (the calls release the
+    GIL) add up until the memory system is the limit."""
+    mv = memoryview(mv).cast("B")
+    if (threads <= 1 and pool is None) or len(mv) < _BULK_MIN:
+        op(fd, mv, at)
+        return
+    spans = _spans(len(mv), threads)
+    if pool is not None:
+        list(pool.map(lambda ab: op(fd, mv[ab[0]:ab[1]], at + ab[0]), spans))
+        return
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=len(spans)) as own:
+        list(own.map(lambda ab: op(fd, mv[ab[0]:ab[1]], at + ab[0]), spans))
+
+
+def io_threads():
+    """Host threads for one bulk read / write: the CPUs of this process, at most 8."""
+    try:
+        return max(1, min(8, len(os.sched_getaffinity(0))))
+    except AttributeError:                                # pragma: no cover - not Linux
+        return 4
+
+
+def save_npy(path, array, threads=None):
+    """``np.save(path, array)`` - the same bytes - with the data block written by several threads (the 400 MB height
+    maps of a 200-frame movie: 0.2 s -> a few tens of ms)."""
+    import io
+    array = np.asarray(array)
+    if not array.flags.c_contiguous:
+        array = np.ascontiguousarray(array)
+    if array.dtype.hasobject:
+        np.save(path, array)
+        return
+    head = io.BytesIO()
+    np.lib.format.write_array_header_1_0(head, np.lib.format.header_data_from_array_1_0(array))
+    head = head.getvalue()
+    fd = os.open(path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o666)
+    try:
+        os.pwrite(fd, head, 0)
+        if array.nbytes:
+            _bulk(_pwrite_span, fd, array.reshape(-1).view(np.uint8), len(head), io_threads() if threads is None else threads)
+    finally:
+        os.close(fd)
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # plane order
 # ----------------------------------------------------------------------------------------------------------------
 def dimension_order(axes):
@@ -91,10 +166,10 @@ def ome_xml(shape5, order, dtype, name="image", metadata=None):
                shape5["T"], phys, channels))
 
 
-def write_tiff(path, image, axes="", metadata=None, bigtiff=None):
+def write_tiff(path, image, axes="", metadata=None, bigtiff=None, threads=None):
     """Store ``image`` (axes = a selection of T, C, Z followed by YX; default: the trailing letters of TCZYX) as an
-    uncompressed little-endian TIFF, one page per YX plane in C order.  Has the signature of the
-    ``surface_projection.tiff_writer`` hook apart from the argument order (see ``hook_writer``)."""
+    uncompressed little-endian TIFF, one page per YX plane in C order.  The pixel block is written by ``threads``
+    host threads (default: ``io_threads()``).  ``hook_writer`` is the ``surface_projection.tiff_writer`` form."""
     image = np.asarray(image)
     if str(image.dtype) not in _OME_TYPE:
         raise TypeError("write_tiff: unsupported dtype %s" % image.dtype)
@@ -153,14 +228,17 @@ def write_tiff(path, image, axes="", metadata=None, bigtiff=None):
         ifds.append(struct.pack(count_fmt, len(tags)) + b"".join(tags) + struct.pack(next_fmt, nxt))
         at += size
     if not bigtiff and at > _CLASSIC_LIMIT:
-        return write_tiff(path, image, axes, metadata, bigtiff=True)
-    with open(path, "wb") as f:
-        f.write(struct.pack("<2sHHHQ", b"II", 43, 8, 0, ifd_at) if bigtiff else struct.pack("<2sHI", b"II", 42, ifd_at))
-        f.write(desc)
-        f.write(b"\0" * (data_at - desc_at - len(desc)))
-        f.write(memoryview(image).cast("B"))
-        f.write(b"\0" * (ifd_at - data_at - planes * plane_bytes))
-        f.write(b"".join(ifds))
+        return write_tiff(path, image, axes, metadata, bigtiff=True, threads=threads)
+    head = struct.pack("<2sHHHQ", b"II", 43, 8, 0, ifd_at) if bigtiff else struct.pack("<2sHI", b"II", 42, ifd_at)
+    fd = os.open(path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o666)
+    try:
+        os.pwrite(fd, head + desc + b"\0" * (data_at - desc_at - len(desc)), 0)
+        if image.nbytes:
+            _bulk(_pwrite_span, fd, image.reshape(-1).view(np.uint8), data_at, io_threads() if threads is None else threads)
+        _pwrite_span(fd, memoryview(b"\0" * (ifd_at - data_at - planes * plane_bytes) + b"".join(ifds)),
+                     data_at + planes * plane_bytes)
+    finally:
+        os.close(fd)
     return path
 
 
@@ -298,6 +376,12 @@ class _LazyPlanes:
     def compute(self):
         return self._image._read(self._index)
 
+    def read_into(self, out, threads=1, pool=None):
+        """Fill ``out`` (C-contiguous, this block's shape, the file's dtype in native byte order) with the block."""
+        if tuple(out.shape) != self.shape or out.dtype != self.dtype.newbyteorder("=") or not out.flags.c_contiguous:
+            raise ValueError("read_into: need a C-contiguous %s array of shape %s" % (self.dtype, self.shape))
+        return self._image._read(self._index, into=out, threads=threads, pool=pool)
+
     def __array__(self, dtype=None, copy=None):
         out = self.compute()
         return out.astype(dtype) if dtype is not None and out.dtype != dtype else out
@@ -309,8 +393,13 @@ class TiffImage:
 
     def __init__(self, path):
         self.path = path
-        with open(path, "rb") as f:
-            self._map = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
+        self._fd = os.open(path, os.O_RDONLY)
+        try:
+            self._map = mmap.mmap(self._fd, 0, access=mmap.ACCESS_READ)
+        except BaseException:
+            os.close(self._fd)
+            self._fd = -1
+            raise
         pages, bo = _parse_ifds(self._map)
         first = pages[0]
         for tags in pages:
@@ -380,6 +469,17 @@ class TiffImage:
 
     def close(self):
         self._map.close()
+        if self._fd >= 0:
+            os.close(self._fd)
+            self._fd = -1
+
+    def __del__(self):
+        fd, self._fd = getattr(self, "_fd", -1), -1
+        if fd >= 0:
+            try:
+                os.close(fd)
+            except OSError:                               # pragma: no cover
+                pass
 
     # ---- planes --------------------------------------------------------------------------------------
     def _plane(self, k):
@@ -390,7 +490,21 @@ class TiffImage:
         raw = b"".join(self._map[o:o + n] for o, n in self._strips[k])
         return np.frombuffer(raw, dtype=self.dtype).reshape(self.Y, self.X)
 
-    def _read(self, index):
+    def _byte_run(self, flat, ys, xs):
+        """(file offset, element count) when the selected planes / rows are ONE run of bytes of the file in native
+        byte order (a whole frame of a file written plane after plane, a band of rows of one plane), else None."""
+        whole_rows = len(xs) == self.X and len(ys) > 0 and np.array_equal(ys, np.arange(ys[0], ys[0] + len(ys)))
+        if not (self._packed and self.dtype.isnative and whole_rows and flat.size > 0):
+            return None
+        if flat.size > 1 and not (len(ys) == self.Y and np.array_equal(flat, np.arange(flat[0], flat[0] + flat.size))):
+            return None
+        base = self._plane_at[int(flat[0])] + int(ys[0]) * self.X * self.dtype.itemsize
+        return base, (flat.size - 1) * self.Y * self.X + len(ys) * self.X
+
+    def _read(self, index, into=None, threads=1, pool=None):
+        """The selected block as an array.  ``into`` (a C-contiguous array of the block's shape and native dtype, e.g.
+        pinned memory): filled and returned instead - a single run of bytes is read straight into it with
+        ``preadv`` on ``threads`` / ``pool`` host threads (no mapping, no page faults, no intermediate copy)."""
         t_ix, c_ix, z_ix, y_ix, x_ix = index
         lead = [np.atleast_1d(ix) for ix in (t_ix, c_ix, z_ix)]
         keep = [not isinstance(ix, (int, np.integer)) for ix in index]
@@ -399,20 +513,20 @@ class TiffImage:
         ys, xs = np.atleast_1d(y_ix), np.atleast_1d(x_ix)
         out_shape = tuple(n for n, k in zip(planes.shape + (len(ys), len(xs)), keep) if k)
         native = self.dtype.newbyteorder("=")
-        flat = planes.reshape(-1)
-        whole_rows = len(xs) == self.X and len(ys) > 0 and np.array_equal(ys, np.arange(ys[0], ys[0] + len(ys)))
-        if (self._packed and self.dtype.isnative and whole_rows and flat.size > 0 and
-                (flat.size == 1 or (len(ys) == self.Y and np.array_equal(flat, np.arange(flat[0], flat[0] + flat.size))))):
-            base = self._plane_at[int(flat[0])] + int(ys[0]) * self.X * self.dtype.itemsize
-            count = (flat.size - 1) * self.Y * self.X + len(ys) * self.X
-            return np.frombuffer(self._map, dtype=self.dtype, count=count, offset=base).reshape(out_shape)
-        out = np.empty(planes.shape + (len(ys), len(xs)), dtype=native)
+        run = self._byte_run(planes.reshape(-1), ys, xs)
+        if run is not None:
+            if into is not None:
+                _bulk(_pread_span, self._fd, into.reshape(-1).view(np.uint8), run[0], threads, pool)
+                return into
+            return np.frombuffer(self._map, dtype=self.dtype, count=run[1], offset=run[0]).reshape(out_shape)
+        full = planes.shape + (len(ys), len(xs))
+        out = into.reshape(full) if into is not None else np.empty(full, dtype=native)
         row, col = _selector(ys), _selector(xs)
         if not isinstance(row, slice) and not isinstance(col, slice):
             row, col = np.ix_(row, col)
         for pos in np.ndindex(*planes.shape):
             out[pos] = self._plane(int(planes[pos]))[row, col]
-        return out.reshape(out_shape)
+        return into if into is not None else out.reshape(out_shape)
 
 
 def _selector(ix):

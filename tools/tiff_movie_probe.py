@@ -3,9 +3,10 @@ no I/O hook), timed end to end.
     python tools/tiff_movie_probe.py [T Z Y X] [--oracle]
 Writes a (T,1,Z,Y,X) uint16 movie (default 40 x 48 x 1024 x 1024 = BASELINE configs[2] frames, 3.8 GB) to a
 temporary directory, runs movie_surface_projection on it twice (the first run warms the GPU path and the page cache)
-and prints the seconds of the second run: frames come out of the file mapping (page cache) as read-only views, are
-staged into pinned memory by the pipeline's host threads, projected, returned as uint16 and written as
-position1.tif + zmap_position1.npy.  --oracle replaces the GPU by the CPU oracle (host-logic dry run, small sizes)."""
+and prints the seconds of the second run: frames are read from the file (page cache) straight into the pipeline's
+pinned staging buffers by its host threads (preadv), projected, returned as uint16 and written as position1.tif +
+zmap_position1.npy by several threads; a third run takes the frames as views of the file mapping instead (A/B).
+--oracle replaces the GPU by the CPU oracle (host-logic dry run, small sizes)."""
 import contextlib
 import io
 import os
@@ -48,8 +49,10 @@ try:
     print("wrote %s: %.2f GB in %.2f s" % (path, os.path.getsize(path) / 1e9, time.perf_counter() - t0), flush=True)
     bim.open_image = tiff_io.TiffImage
     sp.tiff_writer = tiff_io.hook_writer
-    for run in ("warm", "timed"):
+    for run in ("warm", "timed", "timed_mmap_views"):
         out = os.path.join(work, run)
+        if run == "timed_mmap_views":            # A/B: frames as views of the file mapping, copied by the staging threads
+            os.environ["TSP_TIFF_MMAP"] = "1"
         os.mkdir(out)
         t0 = time.perf_counter()
         with contextlib.redirect_stdout(io.StringIO()):
@@ -68,5 +71,31 @@ try:
         want = sp.time_point_surface_projection(movie[0:1], "TCZYX", 0, airyscan=False)
         assert np.array_equal(first, want[0].astype(np.uint16)), "file differs from the blocking operator call"
     print("output file checked", flush=True)
+    # A/B of the output writes: threads per file, and the two files of a position one after the other / side by side
+    from concurrent.futures import ThreadPoolExecutor
+    proj = np.ascontiguousarray(got.get_image_data()[:, :, 0])
+    zmap = np.load(os.path.join(work, "timed", "zmap_position1.npy"))
+    tif, npy = os.path.join(work, "ab.tif"), os.path.join(work, "ab.npy")
+
+    def both(th, side_by_side):
+        for f in (tif, npy):
+            if os.path.exists(f):
+                os.remove(f)
+        t0 = time.perf_counter()
+        jobs = [lambda: tiff_io.write_tiff(tif, proj, "TCYX", threads=th), lambda: tiff_io.save_npy(npy, zmap, threads=th)]
+        if side_by_side:
+            with ThreadPoolExecutor(2) as pool:
+                list(pool.map(lambda j: j(), jobs))
+        else:
+            for j in jobs:
+                j()
+        return time.perf_counter() - t0
+
+    for side in (False, True):
+        for th in (1, 2, 4, 8):
+            ts = sorted(both(th, side) for _ in range(3))
+            print("write %.0f MB tif + %.0f MB npy, %d thread(s) per file, %s: min %.3f s median %.3f s" % (
+                proj.nbytes / 1e6, zmap.nbytes / 1e6, th, "side by side" if side else "one after the other", ts[0], ts[1]),
+                flush=True)
 finally:
     shutil.rmtree(work, ignore_errors=True)
