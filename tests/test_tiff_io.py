@@ -368,3 +368,59 @@ def test_pipeline_stages_tiff_frames_by_read_into(tmp_path, monkeypatch):
         owned = pipe.project_movie(path, 0, proj, zmap, reference_channel=0, airyscan=False)
         assert owned == list(range(7)) and len(reads) == n_reads and pipe.h2d_bytes == a.nbytes
         assert np.array_equal(proj[:, :, 0], a.max(axis=2)) and np.array_equal(zmap[:, 0, 0], a[:, 0].argmax(axis=1))
+
+
+def test_regular_ifd_chains_parse_the_same_with_and_without_the_vectorised_pass(tmp_path, monkeypatch):
+    from tissue_image_processing_b200 import tiff_io
+    a = np.random.default_rng(8).integers(0, 65535, (3, 2, 4, 6, 5), dtype=np.uint16)
+    files = []
+    for big in (False, True):
+        files.append(str(tmp_path / ("c%d.tif" % big)))
+        tiff_io.write_tiff(files[-1], a, "TCZYX", bigtiff=big)
+    # big-endian chain of six 2 x 3 pages, IFDs back to back behind the data
+    planes = (np.arange(36).reshape(6, 2, 3) * 7).astype(">u2")
+    size = 2 + 12 * 9 + 4
+    ifd_at = 8 + planes.nbytes
+    blob = struct.pack(">2sHI", b"MM", 42, ifd_at) + planes.tobytes()
+    for k in range(6):
+        tags = [(256, 3, 3), (257, 3, 2), (258, 3, 16), (259, 3, 1), (262, 3, 1), (273, 4, 8 + 12 * k), (277, 3, 1),
+                (278, 3, 2), (279, 4, 12)]
+        blob += struct.pack(">H", 9) + b"".join(struct.pack(">HHI", t, ty, 1) + (struct.pack(">HH", v, 0) if ty == 3
+                                                else struct.pack(">I", v)) for t, ty, v in tags)
+        blob += struct.pack(">I", ifd_at + size * (k + 1) if k < 5 else 0)
+    files.append(str(tmp_path / "mm.tif"))
+    with open(files[-1], "wb") as f:
+        f.write(blob)
+    calls = []
+    real = tiff_io._regular_ifds
+    monkeypatch.setattr(tiff_io, "_regular_ifds", lambda *a: (calls.append(1), real(*a))[1])
+    fast = [tiff_io._parse_ifds(open(p, "rb").read()) for p in files]
+    assert len(calls) == 3                                           # one vectorised pass per file took the rest
+    monkeypatch.setattr(tiff_io, "_regular_ifds", lambda buf, bo, big, at, size, n: ([], at + size))
+    slow = [tiff_io._parse_ifds(open(p, "rb").read()) for p in files]
+    assert fast == slow and [len(f[0]) for f in fast] == [24, 24, 6]
+    monkeypatch.setattr(tiff_io, "_regular_ifds", real)
+    assert np.array_equal(tiff_io.TiffImage(files[2]).get_image_data()[0, 0], planes.astype(np.uint16))
+    # a chain that stops being regular half way (page 4 of 6 has another width): the pass ends there
+    broken = bytearray(blob)
+    struct.pack_into(">H", broken, ifd_at + size * 4 + 2 + 8, 4)
+    pages, _ = tiff_io._parse_ifds(bytes(broken))
+    assert [p[256] for p in pages] == [3, 3, 3, 3, 4, 3]
+
+
+def test_open_tiff_remembers_a_file_until_it_changes(tmp_path):
+    from tissue_image_processing_b200 import tiff_io
+    path = str(tmp_path / "m.tif")
+    tiff_io.write_tiff(path, np.zeros((3, 4, 5), np.uint16), "ZYX")
+    first = tiff_io.open_tiff(path)
+    assert tiff_io.open_tiff(path) is first and first.shape5 == (1, 1, 3, 4, 5)
+    tiff_io.write_tiff(path, np.zeros((7, 4, 5), np.uint16), "ZYX")
+    second = tiff_io.open_tiff(path)
+    assert second is not first and second.shape5 == (1, 1, 7, 4, 5)
+    second.close()
+    assert tiff_io.open_tiff(path) is not second                     # a closed image is not handed out again
+    for k in range(6):                                               # the cache stays small
+        other = str(tmp_path / ("o%d.tif" % k))
+        tiff_io.write_tiff(other, np.zeros((2, 2), np.uint8))
+        tiff_io.open_tiff(other)
+    assert len(tiff_io._open_cache) <= 4

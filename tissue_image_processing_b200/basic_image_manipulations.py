@@ -21,7 +21,7 @@ def _default_open_image(path):
     except ImportError as exc:
         from . import tiff_io
         if tiff_io.is_tiff_path(path):
-            return tiff_io.TiffImage(path)
+            return tiff_io.open_tiff(path)
         raise ImportError("reading %r needs aicsimageio + Bio-Formats (only TIFF files are read without them): "
                           "install them or set basic_image_manipulations.open_image" % (path,)) from exc
     return AICSImage(path, reader=bioformats_reader.BioformatsReader)

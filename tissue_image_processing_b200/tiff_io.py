@@ -88,16 +88,19 @@ def _bulk(op, fd, mv, at, threads=1, pool=None):
 
 
 def io_threads():
-    """Host threads for one bulk read / write: the CPUs of this process, at most 8."""
+    """Host threads for the pixel block of ONE file.  1 unless TSP_IO_THREADS says otherwise: buffered writes to a
+    single file are serialised by the file system (measured on the B200 box, ext4: 420 MB in 0.074 s with 1, 2, 4 or
+    8 threads - profiles/r2z_tiff_movie_probe_100frames_ab.txt); writing two FILES side by side does halve the time,
+    which is what the movie driver does with a position's TIFF and height-map file."""
     try:
-        return max(1, min(8, len(os.sched_getaffinity(0))))
-    except AttributeError:                                # pragma: no cover - not Linux
-        return 4
+        return max(1, int(os.environ.get("TSP_IO_THREADS", "1")))
+    except ValueError:
+        return 1
 
 
 def save_npy(path, array, threads=None):
-    """``np.save(path, array)`` - the same bytes - with the data block written by several threads (the 400 MB height
-    maps of a 200-frame movie: 0.2 s -> a few tens of ms)."""
+    """``np.save(path, array)`` - the same bytes - through one pwrite of the data block (no intermediate buffering;
+    ``threads`` > 1 cuts it into spans written concurrently, see ``io_threads``)."""
     import io
     array = np.asarray(array)
     if not array.flags.c_contiguous:
@@ -294,10 +297,55 @@ def _parse_ifds(buf):
                     tags[tag] = vals[0] if count == 1 else vals
             pos += entry_size
         pages.append(tags)
-        at = struct.unpack_from(off_fmt, buf, pos)[0]
+        nxt = struct.unpack_from(off_fmt, buf, pos)[0]
+        if nxt == pos + struct.calcsize(off_fmt) and len(pages) > 1:
+            # the next IFD lies right behind this one (a chain written in one block, like write_tiff's): take all
+            # the IFDs of the same layout that follow in one vectorised pass instead of ~10 unpacks per page
+            more, nxt = _regular_ifds(buf, bo, big, at, nxt - at, n)
+            seen.update(at + (k + 1) * (pos + struct.calcsize(off_fmt) - at) for k in range(len(more)))
+            pages.extend(more)
+        at = nxt
     if not pages:
         raise TiffFormatError("TIFF without pages")
     return pages, bo
+
+
+_NP_CODE = {1: "u1", 3: "u2", 4: "u4", 6: "i1", 8: "i2", 9: "i4", 11: "f4", 12: "f8", 13: "u4", 16: "u8", 17: "i8", 18: "u8"}
+
+
+def _regular_ifds(buf, bo, big, at, size, n):
+    """The IFD at ``at`` (``size`` bytes, ``n`` entries) is followed immediately by the next one.  Returns the pages
+    of the following IFDs as far as they (a) lie back to back, (b) have exactly the tags / types / counts of the one
+    at ``at`` and (c) hold every value inline with count 1 - parsed column-wise with numpy - and the offset the
+    chain continues at behind them (0: end of file's chain).  ([], at + size) when the fast path does not apply."""
+    cnt_b, ent_b, off_b = (8, 20, 8) if big else (2, 12, 4)
+    val_at = 4 + off_b                                   # of an entry: tag(2) type(2) count(off_b) value(off_b)
+    total = (len(buf) - at) // size
+    if total < 2:
+        return [], at + size
+    rec = np.frombuffer(buf, dtype=np.uint8, count=total * size, offset=at).reshape(total, size)
+    head = rec[0]
+    columns, layout = [], np.ones(size, dtype=bool)
+    for j in range(n):
+        e = cnt_b + j * ent_b
+        tag, typ = struct.unpack_from(bo + "HH", head, e)
+        count = struct.unpack_from(bo + ("Q" if big else "I"), head, e + 4)[0]
+        code = _NP_CODE.get(typ)
+        if code is None or count != 1:
+            return [], at + size
+        layout[e + val_at:e + ent_b] = False
+        columns.append((tag, e + val_at, np.dtype(bo + code)))
+    layout[size - off_b:] = False
+    same = (rec[:, layout] == head[layout]).all(axis=1)
+    nxt = np.ascontiguousarray(rec[:, size - off_b:]).view(bo + ("u8" if big else "u4")).reshape(-1)
+    chained = nxt[:-1] == at + size * np.arange(1, total, dtype=np.uint64)          # row k-1 points at row k
+    ok = same[1:] & chained
+    run = int(total - 1 if ok.all() else np.argmin(ok))                             # rows 1..run continue the chain
+    if run == 0:
+        return [], at + size
+    cols = [np.ascontiguousarray(rec[1:run + 1, o:o + dt.itemsize]).view(dt).reshape(-1).tolist() for _, o, dt in columns]
+    tags = [t for t, _, _ in columns]
+    return [dict(zip(tags, vals)) for vals in zip(*cols)], int(nxt[run])
 
 
 def _as_tuple(v):
@@ -402,7 +450,15 @@ class TiffImage:
             raise
         pages, bo = _parse_ifds(self._map)
         first = pages[0]
+
+        def signature(tags):
+            return (tags.get(COMPRESSION, 1), TILE_WIDTH in tags, tags.get(SAMPLES, 1), tags.get(IMAGE_WIDTH),
+                    tags.get(IMAGE_LENGTH), tags.get(BITS), tags.get(SAMPLE_FORMAT))
+
+        expect = signature(first)
         for tags in pages:
+            if tags is not first and signature(tags) == expect:
+                continue                                 # like page 0, which is checked in detail
             if tags.get(COMPRESSION, 1) != 1:
                 raise NotImplementedError("%s: compressed TIFF (scheme %s) - store it uncompressed" % (path, tags[COMPRESSION]))
             if TILE_WIDTH in tags:
@@ -419,21 +475,26 @@ class TiffImage:
         self.dtype = np.dtype("%s%s%d" % (bo, kind, bits // 8))
         self.Y, self.X = int(first[IMAGE_LENGTH]), int(first[IMAGE_WIDTH])
         self._strips = []                                # per page: [(offset, bytes)]
+        plane_bytes = self.Y * self.X * self.dtype.itemsize
         for tags in pages:
-            offs, cnts = _as_tuple(tags[STRIP_OFFSETS]), _as_tuple(tags[STRIP_COUNTS])
-            if len(offs) != len(cnts) or sum(cnts) != self.Y * self.X * self.dtype.itemsize:
+            offs, cnts = tags[STRIP_OFFSETS], tags[STRIP_COUNTS]
+            if cnts == plane_bytes and isinstance(offs, int):            # one strip per page
+                self._strips.append([(offs, cnts)])
+                continue
+            offs, cnts = _as_tuple(offs), _as_tuple(cnts)
+            if len(offs) != len(cnts) or sum(cnts) != plane_bytes:
                 raise TiffFormatError("%s: strip sizes do not add up to a plane" % path)
             self._strips.append(list(zip(offs, cnts)))
         sizes, order, extra = _describe(first.get(DESCRIPTION), len(pages))
         self._sizes, self.dimension_order, self._extra = sizes, order, extra
         self._strides = _plane_strides(order, sizes)
         self.shape5 = (sizes["T"], sizes["C"], sizes["Z"], self.Y, self.X)
-        plane_bytes = self.Y * self.X * self.dtype.itemsize
         # the common layout (and the one write_tiff produces): every plane one run of bytes, plane k+1 right behind k
-        starts = [s[0][0] if all(a[0] + a[1] == b[0] for a, b in zip(s, s[1:])) else None for s in self._strips]
+        starts = [s[0][0] if len(s) == 1 or all(a[0] + a[1] == b[0] for a, b in zip(s, s[1:])) else None
+                  for s in self._strips]
         self._plane_at = starts
         self._packed = all(s is not None for s in starts) and \
-            all(starts[k] + plane_bytes == starts[k + 1] for k in range(len(starts) - 1))
+            bool((np.diff(np.asarray(starts, dtype=np.int64)) == plane_bytes).all())
         self.scene = 0
 
     # ---- AICSImage surface ---------------------------------------------------------------------------
@@ -539,6 +600,30 @@ def _selector(ix):
     if step > 0 and np.array_equal(ix, np.arange(ix[0], ix[0] + step * len(ix), step)):
         return slice(int(ix[0]), int(ix[-1]) + 1, step)
     return np.asarray(ix)
+
+
+_open_lock = None
+_open_cache = {}                                  # (real path, mtime ns, size) -> TiffImage, the few most recent
+
+
+def open_tiff(path):
+    """``TiffImage(path)``, remembered while the file does not change: the drivers open a movie once for its
+    dimensions, once per job and twice for its metadata - the IFD chain of a 200-frame movie (9600 pages) is parsed
+    once instead of four times."""
+    global _open_lock
+    import threading
+    if _open_lock is None:
+        _open_lock = threading.Lock()
+    st = os.stat(path)
+    key = (os.path.realpath(path), st.st_mtime_ns, st.st_size)
+    with _open_lock:
+        img = _open_cache.get(key)
+        if img is None or img._fd < 0:
+            img = TiffImage(path)
+            for old in [k for k in _open_cache if k[0] == key[0]] + list(_open_cache)[:max(0, len(_open_cache) - 3)]:
+                _open_cache.pop(old, None)
+            _open_cache[key] = img
+        return img
 
 
 def is_tiff_path(path):

@@ -47,7 +47,7 @@ try:
     t0 = time.perf_counter()
     tiff_io.write_tiff(path, movie, "TCZYX")
     print("wrote %s: %.2f GB in %.2f s" % (path, os.path.getsize(path) / 1e9, time.perf_counter() - t0), flush=True)
-    bim.open_image = tiff_io.TiffImage
+    bim.open_image = tiff_io.open_tiff
     sp.tiff_writer = tiff_io.hook_writer
     for run in ("warm", "timed", "timed_mmap_views"):
         out = os.path.join(work, run)
