@@ -424,3 +424,38 @@ def test_open_tiff_remembers_a_file_until_it_changes(tmp_path):
         tiff_io.write_tiff(other, np.zeros((2, 2), np.uint8))
         tiff_io.open_tiff(other)
     assert len(tiff_io._open_cache) <= 4
+
+
+def test_tiled_driver_stages_tiff_tiles_by_read_into(tmp_path, monkeypatch):
+    """large_image_projection over a TIFF with the fake C ABI: every tile reaches its staging buffer through
+    ``read_into`` (planes gathered from the file mapping by the copy threads), ragged edge tiles included."""
+    pytest.importorskip("torch")
+    from tests.test_drivers_cpu import _FakeNative
+    from tissue_image_processing_b200 import basic_image_manipulations as bim
+    from tissue_image_processing_b200 import movie, tiff_io
+    from tissue_image_processing_b200 import surface_projection as sp
+    a = np.random.default_rng(7).integers(1, 60000, (2, 2, 5, 70, 100), dtype=np.uint16)
+    tiff_io.write_tiff(str(tmp_path / "big.tif"), a, "TCZYX")
+    monkeypatch.setattr(bim, "open_image", tiff_io.open_tiff)
+    monkeypatch.setattr(movie._Staging, "is_pinned", staticmethod(lambda arr: False))
+    monkeypatch.setattr(movie, "_native", _FakeNative())
+    monkeypatch.setattr(tiff_io, "_BULK_MIN", 1 << 10)               # small tiles still take the threaded gather
+    reads = []
+    real = tiff_io._LazyPlanes.read_into
+    monkeypatch.setattr(tiff_io._LazyPlanes, "read_into", lambda self, out, **kw: (reads.append(out.shape), real(self, out, **kw))[1])
+    written = {}
+    monkeypatch.setattr(sp, "tiff_writer", lambda path, image, axes, metadata: written.update({path: (image, axes)}))
+    pipe = movie.FramePipeline.__new__(movie.FramePipeline)
+    pipe.operator, pipe.mode, pipe.out_dtype, pipe.devices, pipe.slots, pipe.copy_threads, pipe.h2d_bytes = (
+        None, "fast", "reference", [0], 2, 3, 0)
+    sp.large_image_projection(str(tmp_path), str(tmp_path), "big.tif", position=1, chunk_size=48, frame_pipeline=pipe)
+    assert sorted(reads) == sorted([(2, 5, 48, 48)] * 4 + [(2, 5, 48, 4)] * 2 + [(2, 5, 22, 48)] * 4 + [(2, 5, 22, 4)] * 2)
+    tif, axes = written[str(tmp_path / "big_projection.tif")]
+    want = a.max(axis=2).astype(np.float64)
+    assert axes == "TCYX" and np.array_equal(tif, np.round(want / want.max() * 65535).astype(np.uint16))
+    zmap = np.load(tmp_path / "big_zmap.npy")
+    want_z = np.zeros((2, 70, 100))
+    for y in (0, 48):
+        for x in (0, 48, 96):
+            want_z[:, y:y + 48, x:x + 48] = a[:, 0, :, y:y + 48, x:x + 48].argmax(axis=1)   # the fake: argmax of channel 0
+    assert np.array_equal(zmap, want_z)

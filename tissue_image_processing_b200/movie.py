@@ -518,6 +518,14 @@ class FramePipeline:
             staging.close()
 
     # ---- public ------------------------------------------------------------------------------------
+    def frame_of(self, chunk):
+        """The (C,Z,Y,X) frame of a lazily sliced (1,C,Z,Y,X) chunk of an image: an ndarray (``.compute()``), or -
+        for a block of a TIFF file (``tiff_io``: has ``read_into``) on the GPU path - the lazy block itself, which
+        the staging threads read straight into pinned memory (TSP_TIFF_MMAP=1: a view of the file mapping instead)."""
+        if hasattr(chunk, "read_into") and self.operator is None and not os.environ.get("TSP_TIFF_MMAP"):
+            return chunk[0]
+        return np.asarray(chunk.compute())[0]
+
     def project_frames(self, frames, sink, **params):
         """Project ``frames`` (iterable of (key, stack)) and call ``sink(key, proj, zmap, status)`` for each.  The
         arrays handed to ``sink`` are reused for later frames: copy what must be kept.  With several devices one
@@ -603,11 +611,7 @@ class FramePipeline:
 
         def frames():
             for t in counter.claims(T):
-                chunk = data[t:t + 1]
-                if hasattr(chunk, "read_into") and self.operator is None and not os.environ.get("TSP_TIFF_MMAP"):
-                    yield t, chunk[0]          # lazy (C, Z, Y, X) block of a TIFF: staged by preadv into pinned memory
-                else:
-                    yield t, np.asarray(chunk.compute())[0]              # (C, Z, Y, X)
+                yield t, self.frame_of(data[t:t + 1])                    # (C, Z, Y, X)
 
         def sink(t, proj, zmap, status):
             out_projection[t, :, 0] = proj

@@ -350,7 +350,9 @@ def large_image_projection(input_dir, output_dir, input_file_name, position=1, r
         def source():
             for k in counter.claims(len(tiles)):
                 t, y0, y1, x0, x1 = tiles[k]
-                yield k, np.asarray(data[t:t + 1, :, :, y0:y1, x0:x1].compute())[0]
+                chunk = data[t:t + 1, :, :, y0:y1, x0:x1]
+                frame_of = getattr(pipeline, "frame_of", None)           # FramePipeline: TIFF tiles stay lazy
+                yield k, frame_of(chunk) if frame_of else np.asarray(chunk.compute())[0]
 
         def sink(k, proj, zm, status):
             t, y0, y1, x0, x1 = tiles[k]

@@ -565,7 +565,8 @@ class TiffImage:
     def _read(self, index, into=None, threads=1, pool=None):
         """The selected block as an array.  ``into`` (a C-contiguous array of the block's shape and native dtype, e.g.
         pinned memory): filled and returned instead - a single run of bytes is read straight into it with
-        ``preadv`` on ``threads`` / ``pool`` host threads (no mapping, no page faults, no intermediate copy)."""
+        ``preadv`` on ``threads`` / ``pool`` host threads (no mapping, no page faults, no intermediate copy); an XY tile
+        is gathered plane by plane from the mapping, the planes spread over ``pool``."""
         t_ix, c_ix, z_ix, y_ix, x_ix = index
         lead = [np.atleast_1d(ix) for ix in (t_ix, c_ix, z_ix)]
         keep = [not isinstance(ix, (int, np.integer)) for ix in index]
@@ -585,8 +586,14 @@ class TiffImage:
         row, col = _selector(ys), _selector(xs)
         if not isinstance(row, slice) and not isinstance(col, slice):
             row, col = np.ix_(row, col)
-        for pos in np.ndindex(*planes.shape):
+        def gather(pos):
             out[pos] = self._plane(int(planes[pos]))[row, col]
+
+        if pool is not None and planes.size > 1 and out.nbytes >= _BULK_MIN:
+            list(pool.map(gather, np.ndindex(*planes.shape)))        # plane copies release the GIL
+        else:
+            for pos in np.ndindex(*planes.shape):
+                gather(pos)
         return into if into is not None else out.reshape(out_shape)
 
 
