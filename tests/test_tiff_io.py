@@ -459,3 +459,84 @@ def test_tiled_driver_stages_tiff_tiles_by_read_into(tmp_path, monkeypatch):
         for x in (0, 48, 96):
             want_z[:, y:y + 48, x:x + 48] = a[:, 0, :, y:y + 48, x:x + 48].argmax(axis=1)   # the fake: argmax of channel 0
     assert np.array_equal(zmap, want_z)
+
+
+def _two_scene_file(path, same_dims=False):
+    """A multi-image OME-TIFF: position 0 = (T=3, C=1, Z=4) in XYZCT order; position 1 = (T=2, C=2, Z=3) in XYCZT
+    order (channels fastest) or - ``same_dims``, what the movie driver assumes of the positions of a file (SP:197) -
+    (T=3, C=1, Z=4) in XYTZC order (time fastest); stage labels on both; all planes 24 x 28."""
+    from tissue_image_processing_b200 import tiff_io
+    s0 = np.stack([synth.synth_stack(4, 24, 28, C=1, seed=40, t=t) for t in range(3)])            # (3,1,4,24,28)
+    if same_dims:
+        s1 = np.stack([synth.synth_stack(4, 24, 28, C=1, seed=41, t=t) for t in range(3)])
+        second, order1, (t1, c1, z1) = s1.transpose(1, 2, 0, 3, 4), "XYTZC", (3, 1, 4)
+    else:
+        s1 = np.stack([synth.synth_stack(3, 24, 28, C=2, seed=41, t=t) for t in range(2)])        # (2,2,3,24,28)
+        second, order1, (t1, c1, z1) = s1.transpose(0, 2, 1, 3, 4), "XYCZT", (2, 2, 3)
+    pages = np.concatenate([s0.reshape(-1, 24, 28), second.reshape(-1, 24, 28)])
+    xml = ('<?xml version="1.0"?><OME xmlns="http://www.openmicroscopy.org/Schemas/OME/2016-06">'
+           '<Image ID="Image:0" Name="left"><StageLabel Name="p0" X="10.5" XUnit="um" Y="-3" YUnit="um" Z="1.25"/>'
+           '<Pixels ID="Pixels:0" DimensionOrder="XYZCT" Type="uint16" SizeX="28" SizeY="24" SizeZ="4" SizeC="1" SizeT="3" '
+           'PhysicalSizeX="0.2" PhysicalSizeY="0.2" PhysicalSizeZ="0.7"><TiffData/></Pixels></Image>'
+           '<Image ID="Image:1" Name="right"><StageLabel Name="p1" X="99" Y="7" Z="2"/>'
+           '<Pixels ID="Pixels:1" DimensionOrder="%s" Type="uint16" SizeX="28" SizeY="24" SizeZ="%d" SizeC="%d" SizeT="%d">'
+           '<TiffData/></Pixels></Image></OME>' % (order1, z1, c1, t1))
+    tiff_io.write_tiff(path, pages, "ZYX", description=xml)
+    return s0, s1
+
+
+def test_multi_image_ome_tiff_scenes(tmp_path):
+    from tissue_image_processing_b200 import tiff_io
+    path = str(tmp_path / "two.tif")
+    s0, s1 = _two_scene_file(path)
+    img = tiff_io.TiffImage(path)
+    assert img.scenes == (0, 1) and img.shape5 == (3, 1, 4, 24, 28) and img.dimension_order == "XYZCT"
+    lazy0 = img.get_image_dask_data()
+    img.set_scene(1)
+    assert img.shape5 == (2, 2, 3, 24, 28) and img.dims.C == 2 and img.dimension_order == "XYCZT"
+    lazy1 = img.get_image_dask_data()
+    assert np.array_equal(lazy1.compute(), s1) and np.array_equal(lazy1[1, :, 2].compute(), s1[1, :, 2])
+    assert lazy0.shape == s0.shape and np.array_equal(lazy0[1:2].compute(), s0[1:2])       # bound to the scene it came from
+    out = np.zeros((1, 4, 24, 28), np.uint16)
+    lazy0[2:3][0].read_into(out)
+    assert np.array_equal(out, s0[2])
+    meta = img.metadata
+    assert [im.name for im in meta.images] == ["left", "right"]
+    assert (meta.images[0].stage_label.x, meta.images[0].stage_label.y, meta.images[0].stage_label.z) == (10.5, -3.0, 1.25)
+    assert meta.images[0].stage_label.x_unit == "um" and meta.images[1].stage_label.x_unit is None
+    assert meta.images[0].pixels.physical_size_z == 0.7 and meta.images[1].pixels.size_t == 2
+    with pytest.raises(IndexError):
+        img.set_scene(2)
+    # descriptions that do not account for every page fall back to one z stack
+    tiff_io.write_tiff(path, np.zeros((5, 4, 4), np.uint8), "ZYX", description=(
+        '<OME><Image ID="Image:0"><Pixels DimensionOrder="XYZCT" SizeX="4" SizeY="4" SizeZ="2" SizeC="1" SizeT="2"/>'
+        '</Image></OME>'))
+    assert tiff_io.TiffImage(path).shape5 == (1, 1, 5, 4, 4)
+
+
+def test_movie_driver_over_the_positions_of_one_ome_tiff(tmp_path, monkeypatch):
+    """movie_surface_projection with two initial positions = the two scenes of one OME-TIFF movie file: one output
+    TIFF, height-map file and stage pickle per position (SP:240-276 reads the stage labels of every scene)."""
+    pytest.importorskip("torch")
+    import pickle
+    from tissue_image_processing_b200 import basic_image_manipulations as bim
+    from tissue_image_processing_b200 import surface_projection as sp
+    from tissue_image_processing_b200 import tiff_io
+    from tissue_image_processing_b200.movie import FramePipeline
+    path = str(tmp_path / "m1.tif")
+    scenes = _two_scene_file(path, same_dims=True)
+    monkeypatch.setattr(bim, "open_image", tiff_io.open_tiff)
+    monkeypatch.setattr(sp, "tiff_writer", sp._default_tiff_writer)
+    out = tmp_path / "out"
+    out.mkdir()
+    pipe = FramePipeline(operator=orc.time_point_surface_projection, out_dtype="uint16")
+    sp.movie_surface_projection([path], 0, [1, 1], 2, str(out), "max_averages", 1, False, 0, 0, 0, False,
+                                frame_pipeline=pipe)
+    for p, movie in enumerate(scenes):
+        got = tiff_io.TiffImage(str(out / ("position%d.tif" % (p + 1))))
+        want = np.stack([orc.time_point_surface_projection(movie[t:t + 1], "TCZYX", 0, airyscan=False).astype("uint16")
+                         for t in range(len(movie))])
+        assert np.array_equal(got.get_image_data()[:, :, 0], want), p
+        with open(out / ("stage_locations_position%d.pkl" % (p + 1)), "rb") as f:
+            stage = pickle.load(f)
+        assert stage["x"] == [(10.5, 99.0)[p]] * len(movie) and stage["physical_size_x"] == (0.2, None)[p]

@@ -11,8 +11,9 @@ uncompressed TIFF files, with no dependency besides numpy:
     (a single large write; the IFD chain follows it), classic TIFF below 4 GiB and BigTIFF above, an OME-XML block in
     the first page's ImageDescription (DimensionOrder derived from the array's axes, so ``TCYX`` becomes the
     ``XYCTZ`` of SP:323), physical pixel sizes taken from the metadata object when it carries them;
-  * ``TiffImage``   parses classic / BigTIFF, either byte order, uncompressed strips; plane order from the OME-XML or
-    ImageJ description (else: the pages are the z planes of one stack).  The planes are served from one read-only
+  * ``TiffImage``   parses classic / BigTIFF, either byte order, uncompressed strips; plane order from the OME-XML
+    (one scene per ``<Image>``, stage labels and pixel sizes kept) or ImageJ description (else: the pages are the z
+    planes of one stack).  The planes are served from one read-only
     memory mapping of the file: a (C,Z,Y,X) frame whose planes lie next to each other in the file comes back as a
     VIEW of the mapping, so the pipeline's staging threads copy it from the page cache straight into pinned memory
     (one host copy per frame, the same as for an array the caller already holds).
@@ -169,10 +170,11 @@ def ome_xml(shape5, order, dtype, name="image", metadata=None):
                shape5["T"], phys, channels))
 
 
-def write_tiff(path, image, axes="", metadata=None, bigtiff=None, threads=None):
+def write_tiff(path, image, axes="", metadata=None, bigtiff=None, threads=None, description=None):
     """Store ``image`` (axes = a selection of T, C, Z followed by YX; default: the trailing letters of TCZYX) as an
     uncompressed little-endian TIFF, one page per YX plane in C order.  The pixel block is written by ``threads``
-    host threads (default: ``io_threads()``).  ``hook_writer`` is the ``surface_projection.tiff_writer`` form."""
+    host threads (default: ``io_threads()``).  ``description`` replaces the generated OME-XML block of the first page.
+    ``hook_writer`` is the ``surface_projection.tiff_writer`` form."""
     image = np.asarray(image)
     if str(image.dtype) not in _OME_TYPE:
         raise TypeError("write_tiff: unsupported dtype %s" % image.dtype)
@@ -190,7 +192,9 @@ def write_tiff(path, image, axes="", metadata=None, bigtiff=None, threads=None):
     Y, X = sizes["Y"], sizes["X"]
     planes = int(np.prod(image.shape[:-2], dtype=np.int64)) if image.ndim > 2 else 1
     plane_bytes = Y * X * image.dtype.itemsize
-    desc = ome_xml(sizes, order, image.dtype, os.path.splitext(os.path.basename(path))[0], metadata).encode() + b"\0"
+    if description is None:
+        description = ome_xml(sizes, order, image.dtype, os.path.splitext(os.path.basename(path))[0], metadata)
+    desc = (description.encode() if isinstance(description, str) else bytes(description)) + b"\0"
     if bigtiff is None:
         bigtiff = planes * plane_bytes + planes * 256 + len(desc) + 4096 > _CLASSIC_LIMIT
     head = 16 if bigtiff else 8
@@ -231,7 +235,7 @@ def write_tiff(path, image, axes="", metadata=None, bigtiff=None, threads=None):
         ifds.append(struct.pack(count_fmt, len(tags)) + b"".join(tags) + struct.pack(next_fmt, nxt))
         at += size
     if not bigtiff and at > _CLASSIC_LIMIT:
-        return write_tiff(path, image, axes, metadata, bigtiff=True, threads=threads)
+        return write_tiff(path, image, axes, metadata, bigtiff=True, threads=threads, description=description)
     head = struct.pack("<2sHHHQ", b"II", 43, 8, 0, ifd_at) if bigtiff else struct.pack("<2sHI", b"II", 42, ifd_at)
     fd = os.open(path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o666)
     try:
@@ -352,24 +356,48 @@ def _as_tuple(v):
     return tuple(v) if isinstance(v, (tuple, list)) else (v,)
 
 
+def _ome_image(block):
+    """(sizes, order, extra) of one OME ``<Image>`` block, or None."""
+    m = re.search(r"<Pixels\b[^>]*>", block)
+    if not m:
+        return None
+    attrs = dict(re.findall(r'(\w+)="([^"]*)"', m.group(0)))
+    try:
+        sizes = {a: int(attrs["Size" + a]) for a in "TCZ"}
+        order = attrs.get("DimensionOrder", "XYZCT").upper()
+        if sorted(order) != sorted("XYZCT") or not order.startswith("XY") or min(sizes.values()) < 1:
+            return None
+        extra = {k: float(attrs[v]) for k, v in (("physical_size_x", "PhysicalSizeX"), ("physical_size_y", "PhysicalSizeY"),
+                                                 ("physical_size_z", "PhysicalSizeZ")) if v in attrs}
+        name = re.search(r'<Image\b[^>]*\bName="([^"]*)"', block)
+        extra["name"] = name.group(1) if name else None
+        stage = re.search(r"<StageLabel\b[^>]*>", block)
+        if stage:
+            found = dict(re.findall(r'(\w+)="([^"]*)"', stage.group(0)))
+            for axis in "XYZ":
+                if axis in found:
+                    extra["stage_" + axis.lower()] = float(found[axis])
+                if axis + "Unit" in found:
+                    extra["stage_%s_unit" % axis.lower()] = found[axis + "Unit"]
+        return sizes, order, extra
+    except (KeyError, ValueError):
+        return None
+
+
 def _describe(description, n_pages):
-    """(sizes {T,C,Z}, DimensionOrder, extra metadata) from the first page's ImageDescription."""
+    """The scenes of the file from the first page's ImageDescription: [(sizes {T,C,Z}, DimensionOrder, extra
+    metadata, first page)].  OME-XML: one scene per ``<Image>`` (their planes follow each other in the file);
+    ImageJ hyperstack: one scene, channels fastest; anything else: the pages are the z planes of one stack."""
     text = description or ""
-    m = re.search(r"<Pixels\b[^>]*>", text)
-    if m:
-        attrs = dict(re.findall(r'(\w+)="([^"]*)"', m.group(0)))
-        try:
-            sizes = {a: int(attrs["Size" + a]) for a in "TCZ"}
-            order = attrs.get("DimensionOrder", "XYZCT").upper()
-            if sorted(order) == sorted("XYZCT") and order.startswith("XY") and \
-                    sizes["T"] * sizes["C"] * sizes["Z"] == n_pages:
-                phys = {k: float(attrs[v]) for k, v in (("physical_size_x", "PhysicalSizeX"),
-                                                        ("physical_size_y", "PhysicalSizeY"),
-                                                        ("physical_size_z", "PhysicalSizeZ")) if v in attrs}
-                name = re.search(r'<Image\b[^>]*\bName="([^"]*)"', text)
-                return sizes, order, dict(phys, name=name.group(1) if name else None)
-        except (KeyError, ValueError):
-            pass
+    blocks = re.findall(r"<Image\b.*?</Image>", text, flags=re.S) or ([text] if "<Pixels" in text else [])
+    images = [_ome_image(b) for b in blocks]
+    if images and all(im is not None for im in images):
+        scenes, at = [], 0
+        for sizes, order, extra in images:
+            scenes.append((sizes, order, extra, at))
+            at += sizes["T"] * sizes["C"] * sizes["Z"]
+        if at == n_pages:
+            return scenes
     if text.startswith("ImageJ="):
         kv = dict(line.split("=", 1) for line in text.splitlines() if "=" in line)
         try:
@@ -378,10 +406,10 @@ def _describe(description, n_pages):
                 extra = {}
                 if "spacing" in kv:
                     extra["physical_size_z"] = float(kv["spacing"])
-                return sizes, "XYCZT", extra
+                return [(sizes, "XYCZT", extra, 0)]
         except ValueError:
             pass
-    return {"T": 1, "C": 1, "Z": n_pages}, "XYZCT", {}
+    return [({"T": 1, "C": 1, "Z": n_pages}, "XYZCT", {}, 0)]
 
 
 class _LazyPlanes:
@@ -389,9 +417,10 @@ class _LazyPlanes:
     reads the planes.  Nothing is copied before ``compute``; a block whose planes are adjacent in the file (and whose
     rows are whole) is returned as a read-only view of the file mapping."""
 
-    def __init__(self, image, index=None):
+    def __init__(self, image, index=None, scene=None):
         self._image = image
-        self._index = index if index is not None else [np.arange(n) for n in image.shape5]
+        self._scene = image.scene if scene is None else scene          # bound now: set_scene later does not move it
+        self._index = index if index is not None else [np.arange(n) for n in image._shape_of(self._scene)]
 
     @property
     def shape(self):
@@ -419,16 +448,16 @@ class _LazyPlanes:
                 new.append(ix[sel])
             else:
                 raise TypeError("only integers and slices index a lazy TIFF stack")
-        return _LazyPlanes(self._image, new)
+        return _LazyPlanes(self._image, new, self._scene)
 
     def compute(self):
-        return self._image._read(self._index)
+        return self._image._read(self._index, self._scene)
 
     def read_into(self, out, threads=1, pool=None):
         """Fill ``out`` (C-contiguous, this block's shape, the file's dtype in native byte order) with the block."""
         if tuple(out.shape) != self.shape or out.dtype != self.dtype.newbyteorder("=") or not out.flags.c_contiguous:
             raise ValueError("read_into: need a C-contiguous %s array of shape %s" % (self.dtype, self.shape))
-        return self._image._read(self._index, into=out, threads=threads, pool=pool)
+        return self._image._read(self._index, self._scene, into=out, threads=threads, pool=pool)
 
     def __array__(self, dtype=None, copy=None):
         out = self.compute()
@@ -436,8 +465,8 @@ class _LazyPlanes:
 
 
 class TiffImage:
-    """The surface of ``aicsimageio.AICSImage`` the drivers use, for one uncompressed TIFF / BigTIFF file (one
-    scene)."""
+    """The surface of ``aicsimageio.AICSImage`` the drivers use, for one uncompressed TIFF / BigTIFF file (the
+    positions of a multi-image OME-TIFF are its scenes; all pages of a file share one shape and type)."""
 
     def __init__(self, path):
         self.path = path
@@ -485,10 +514,8 @@ class TiffImage:
             if len(offs) != len(cnts) or sum(cnts) != plane_bytes:
                 raise TiffFormatError("%s: strip sizes do not add up to a plane" % path)
             self._strips.append(list(zip(offs, cnts)))
-        sizes, order, extra = _describe(first.get(DESCRIPTION), len(pages))
-        self._sizes, self.dimension_order, self._extra = sizes, order, extra
-        self._strides = _plane_strides(order, sizes)
-        self.shape5 = (sizes["T"], sizes["C"], sizes["Z"], self.Y, self.X)
+        self._scenes = _describe(first.get(DESCRIPTION), len(pages))
+        self._scene_strides = [_plane_strides(order, sizes) for sizes, order, _, _ in self._scenes]
         # the common layout (and the one write_tiff produces): every plane one run of bytes, plane k+1 right behind k
         starts = [s[0][0] if len(s) == 1 or all(a[0] + a[1] == b[0] for a, b in zip(s, s[1:])) else None
                   for s in self._strips]
@@ -499,9 +526,18 @@ class TiffImage:
 
     # ---- AICSImage surface ---------------------------------------------------------------------------
     def set_scene(self, i):
-        if int(i) != 0:
-            raise IndexError("%s holds one scene (asked for %d)" % (self.path, int(i)))
-        self.scene = 0
+        if not 0 <= int(i) < len(self._scenes):
+            raise IndexError("%s holds %d scene(s) (asked for %d)" % (self.path, len(self._scenes), int(i)))
+        self.scene = int(i)
+
+    scenes = property(lambda self: tuple(range(len(self._scenes))))
+
+    def _shape_of(self, scene):
+        sizes = self._scenes[scene][0]
+        return (sizes["T"], sizes["C"], sizes["Z"], self.Y, self.X)
+
+    shape5 = property(lambda self: self._shape_of(self.scene))
+    dimension_order = property(lambda self: self._scenes[self.scene][1])
 
     @property
     def dims(self):
@@ -516,17 +552,22 @@ class TiffImage:
 
     @property
     def metadata(self):
-        """An object shaped like the OME model the drivers touch (images[i].name / .pixels / .stage_label); what the
-        file does not say is None."""
-        T, C, Z, _, _ = self.shape5
-        pixels = types.SimpleNamespace(
-            size_t=T, size_c=C, size_z=Z, size_y=self.Y, size_x=self.X, dimension_order=self.dimension_order,
-            type=_OME_TYPE.get(str(self.dtype.newbyteorder("=")), str(self.dtype)),
-            physical_size_x=self._extra.get("physical_size_x"), physical_size_y=self._extra.get("physical_size_y"),
-            physical_size_z=self._extra.get("physical_size_z"), planes=list(range(T * C * Z)))
-        stage = types.SimpleNamespace(x=None, y=None, z=None, x_unit=None, y_unit=None, z_unit=None)
-        name = self._extra.get("name") or os.path.splitext(os.path.basename(self.path))[0]
-        return types.SimpleNamespace(images=[types.SimpleNamespace(name=name, pixels=pixels, stage_label=stage)])
+        """An object shaped like the OME model the drivers touch (images[i].name / .pixels / .stage_label, one image
+        per scene); what the file does not say is None."""
+        images = []
+        for k, (sizes, order, extra, _) in enumerate(self._scenes):
+            T, C, Z = sizes["T"], sizes["C"], sizes["Z"]
+            pixels = types.SimpleNamespace(
+                size_t=T, size_c=C, size_z=Z, size_y=self.Y, size_x=self.X, dimension_order=order,
+                type=_OME_TYPE.get(str(self.dtype.newbyteorder("=")), str(self.dtype)),
+                physical_size_x=extra.get("physical_size_x"), physical_size_y=extra.get("physical_size_y"),
+                physical_size_z=extra.get("physical_size_z"), planes=list(range(T * C * Z)))
+            stage = types.SimpleNamespace(x=extra.get("stage_x"), y=extra.get("stage_y"), z=extra.get("stage_z"),
+                                          x_unit=extra.get("stage_x_unit"), y_unit=extra.get("stage_y_unit"),
+                                          z_unit=extra.get("stage_z_unit"))
+            name = extra.get("name") or os.path.splitext(os.path.basename(self.path))[0] + ("" if k == 0 else "_%d" % k)
+            images.append(types.SimpleNamespace(name=name, pixels=pixels, stage_label=stage))
+        return types.SimpleNamespace(images=images)
 
     def close(self):
         self._map.close()
@@ -562,7 +603,7 @@ class TiffImage:
         base = self._plane_at[int(flat[0])] + int(ys[0]) * self.X * self.dtype.itemsize
         return base, (flat.size - 1) * self.Y * self.X + len(ys) * self.X
 
-    def _read(self, index, into=None, threads=1, pool=None):
+    def _read(self, index, scene=0, into=None, threads=1, pool=None):
         """The selected block as an array.  ``into`` (a C-contiguous array of the block's shape and native dtype, e.g.
         pinned memory): filled and returned instead - a single run of bytes is read straight into it with
         ``preadv`` on ``threads`` / ``pool`` host threads (no mapping, no page faults, no intermediate copy); an XY tile
@@ -570,8 +611,9 @@ class TiffImage:
         t_ix, c_ix, z_ix, y_ix, x_ix = index
         lead = [np.atleast_1d(ix) for ix in (t_ix, c_ix, z_ix)]
         keep = [not isinstance(ix, (int, np.integer)) for ix in index]
-        planes = (lead[0][:, None, None] * self._strides["T"] + lead[1][None, :, None] * self._strides["C"]
-                  + lead[2][None, None, :] * self._strides["Z"])
+        strides = self._scene_strides[scene]
+        planes = (self._scenes[scene][3] + lead[0][:, None, None] * strides["T"] + lead[1][None, :, None] * strides["C"]
+                  + lead[2][None, None, :] * strides["Z"])
         ys, xs = np.atleast_1d(y_ix), np.atleast_1d(x_ix)
         out_shape = tuple(n for n, k in zip(planes.shape + (len(ys), len(xs)), keep) if k)
         native = self.dtype.newbyteorder("=")
