@@ -36,7 +36,6 @@ _TYPE_CODE = {1: "B", 2: "c", 3: "H", 4: "I", 6: "b", 7: "B", 8: "h", 9: "i", 11
 _SAMPLE_FORMAT = {"u": 1, "i": 2, "f": 3}
 _OME_TYPE = {"uint8": "uint8", "uint16": "uint16", "uint32": "uint32", "int8": "int8", "int16": "int16",
              "int32": "int32", "float32": "float", "float64": "double"}
-_OME_TYPE_BACK = {v: k for k, v in _OME_TYPE.items()}
 _CLASSIC_LIMIT = (1 << 32) - (1 << 16)            # stay clear of the 4 GiB offset limit of classic TIFF
 
 IMAGE_WIDTH, IMAGE_LENGTH, BITS, COMPRESSION, PHOTOMETRIC, DESCRIPTION, STRIP_OFFSETS = 256, 257, 258, 259, 262, 270, 273
