@@ -540,3 +540,37 @@ def test_movie_driver_over_the_positions_of_one_ome_tiff(tmp_path, monkeypatch):
         with open(out / ("stage_locations_position%d.pkl" % (p + 1)), "rb") as f:
             stage = pickle.load(f)
         assert stage["x"] == [(10.5, 99.0)[p]] * len(movie) and stage["physical_size_x"] == (0.2, None)[p]
+
+
+def test_imagej_big_endian_single_ifd_stack(tmp_path):
+    """What Fiji writes for large hyperstacks: big-endian, ONE IFD whose description states ``images=N``, all planes
+    back to back behind the first strip.  Frames are byte-swapped on the way into the caller's buffer."""
+    from tissue_image_processing_b200 import tiff_io
+    T, Z, C, Y, X = 2, 3, 2, 6, 5
+    a = np.random.default_rng(9).integers(0, 65535, (T, Z, C, Y, X)).astype(">u2")           # ImageJ order: T, Z, C
+    desc = ("ImageJ=1.53t\nimages=%d\nchannels=%d\nslices=%d\nframes=%d\nhyperstack=true\n" % (T * Z * C, C, Z, T)).encode() + b"\0"
+    n_tags = 10
+    ifd_at, desc_at = 8, 8 + 2 + 12 * n_tags + 4
+    data_at = desc_at + len(desc) + (len(desc) & 1)
+    tags = [(256, 3, 1, X), (257, 3, 1, Y), (258, 3, 1, 16), (259, 3, 1, 1), (262, 3, 1, 1), (270, 2, len(desc), desc_at),
+            (273, 4, 1, data_at), (277, 3, 1, 1), (278, 3, 1, Y), (279, 4, 1, Y * X * 2)]
+    body = b"".join(struct.pack(">HHI", t, ty, n) + (struct.pack(">HH", v, 0) if ty == 3 else struct.pack(">I", v))
+                    for t, ty, n, v in tags)
+    blob = struct.pack(">2sHI", b"MM", 42, ifd_at) + struct.pack(">H", n_tags) + body + struct.pack(">I", 0)
+    blob += desc + b"\0" * (len(desc) & 1) + a.tobytes()
+    path = str(tmp_path / "fiji.tif")
+    with open(path, "wb") as f:
+        f.write(blob)
+    img = tiff_io.TiffImage(path)
+    assert img.shape5 == (T, C, Z, Y, X) and img.dimension_order == "XYCZT" and img.dtype == np.dtype(">u2")
+    want = a.astype(np.uint16).transpose(0, 2, 1, 3, 4)
+    data = img.get_image_dask_data()
+    got = data.compute()
+    assert got.dtype.isnative and np.array_equal(got, want)
+    out = np.zeros((C, Z, Y, X), np.uint16)
+    data[1:2][0].read_into(out, threads=2)
+    assert np.array_equal(out, want[1])
+    with open(path, "r+b") as f:                          # a truncated file is refused, not read past its end
+        f.truncate(len(blob) - 10)
+    with pytest.raises(ValueError, match="does not fit"):
+        tiff_io.TiffImage(path)

@@ -12,8 +12,8 @@ uncompressed TIFF files, with no dependency besides numpy:
     the first page's ImageDescription (DimensionOrder derived from the array's axes, so ``TCYX`` becomes the
     ``XYCTZ`` of SP:323), physical pixel sizes taken from the metadata object when it carries them;
   * ``TiffImage``   parses classic / BigTIFF, either byte order, uncompressed strips; plane order from the OME-XML
-    (one scene per ``<Image>``, stage labels and pixel sizes kept) or ImageJ description (else: the pages are the z
-    planes of one stack).  The planes are served from one read-only
+    (one scene per ``<Image>``, stage labels and pixel sizes kept) or ImageJ description - including ImageJ's
+    single-IFD layout for stacks beyond 4 GiB - (else: the pages are the z planes of one stack).  The planes are served from one read-only
     memory mapping of the file: a (C,Z,Y,X) frame whose planes lie next to each other in the file comes back as a
     VIEW of the mapping, so the pipeline's staging threads copy it from the page cache straight into pinned memory
     (one host copy per frame, the same as for an array the caller already holds).
@@ -513,7 +513,16 @@ class TiffImage:
             if len(offs) != len(cnts) or sum(cnts) != plane_bytes:
                 raise TiffFormatError("%s: strip sizes do not add up to a plane" % path)
             self._strips.append(list(zip(offs, cnts)))
-        self._scenes = _describe(first.get(DESCRIPTION), len(pages))
+        n_pages = len(pages)
+        text = first.get(DESCRIPTION) or ""
+        stated = re.search(r"^images=(\d+)$", text, flags=re.M) if text.startswith("ImageJ=") else None
+        if stated and n_pages == 1 and int(stated.group(1)) > 1 and len(self._strips[0]) == 1:
+            # ImageJ's layout for stacks beyond 4 GiB: ONE IFD, the planes follow each other behind its strip offset
+            n_pages, at = int(stated.group(1)), self._strips[0][0][0]
+            if at + n_pages * plane_bytes > len(self._map):
+                raise TiffFormatError("%s: ImageJ stack of %d planes does not fit the file" % (path, n_pages))
+            self._strips = [[(at + k * plane_bytes, plane_bytes)] for k in range(n_pages)]
+        self._scenes = _describe(text, n_pages)
         self._scene_strides = [_plane_strides(order, sizes) for sizes, order, _, _ in self._scenes]
         # the common layout (and the one write_tiff produces): every plane one run of bytes, plane k+1 right behind k
         starts = [s[0][0] if len(s) == 1 or all(a[0] + a[1] == b[0] for a, b in zip(s, s[1:])) else None
