@@ -574,3 +574,49 @@ def test_imagej_big_endian_single_ifd_stack(tmp_path):
         f.truncate(len(blob) - 10)
     with pytest.raises(ValueError, match="does not fit"):
         tiff_io.TiffImage(path)
+
+
+def _cli_rank(rank, world, port, src, out):
+    """One rank of ``torchrun ... -m tissue_image_processing_b200.surface_projection``: the command line joins the job
+    itself (movie.init_job); only the GPU call is replaced by the oracle."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), LOCAL_RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    from tissue_image_processing_b200 import surface_projection as sp
+    from tissue_image_processing_b200.movie import FramePipeline
+    calls = []
+
+    def operator(chunk, **kw):
+        calls.append(1)
+        return orc.time_point_surface_projection(chunk, **kw)
+    sp._default_pipeline = lambda mode, out_dtype: FramePipeline(operator=operator, out_dtype=out_dtype)
+    assert sp.main(["-i", src, "-o", out, "-m", "2", "-r", "0"]) == 0
+    assert dist.is_initialized() and dist.get_world_size() == world and "gloo" in str(dist.get_backend())
+    np.save(os.path.join(out, "calls%d.npy" % rank), np.array(len(calls)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_command_line_under_a_two_rank_launch_shares_the_frames(tmp_path):
+    pytest.importorskip("torch")
+    import torch.multiprocessing as mp
+    from tissue_image_processing_b200 import tiff_io
+    movies = [np.stack([synth.synth_stack(6, 24, 28, C=1, seed=50 + k, t=t) for t in range(n)]) for k, n in ((0, 5), (1, 4))]
+    src, out = tmp_path / "in", tmp_path / "out"
+    src.mkdir(), out.mkdir()
+    for k, m in enumerate(movies):
+        tiff_io.write_tiff(str(src / ("m%d.tif" % (k + 1))), m, "TCZYX")
+    port = 29500 + (os.getpid() * 11 + 3) % 2000
+    mp.spawn(_cli_rank, args=(2, port, str(src), str(out)), nprocs=2, join=True)
+    calls = [int(np.load(out / ("calls%d.npy" % r))) for r in range(2)]
+    assert sum(calls) == 9, calls                       # every time point projected exactly once across the ranks
+    got = tiff_io.TiffImage(str(out / "position1.tif"))
+    frames = list(movies[0]) + list(movies[1])
+    want = np.stack([orc.time_point_surface_projection(f[None], "TCZYX", 0, airyscan=False).astype("uint16")
+                     for f in frames])
+    assert np.array_equal(got.get_image_data()[:, :, 0], want)
+    assert np.load(out / "zmap_position1.npy").shape == (9, 1, 1, 24, 28)
+    assert sorted(f for f in os.listdir(out) if not f.startswith("calls")) == [
+        "position1.tif", "stage_locations_position1.pkl", "zmap_position1.npy"]

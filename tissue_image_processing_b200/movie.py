@@ -47,6 +47,29 @@ def rank_world():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
 
 
+def init_job():
+    """Join the job a launcher started (``torchrun``: WORLD_SIZE > 1 in the environment) unless the caller already
+    did: a gloo process group - the ranks only meet on the control plane (frame claims, barriers) and when the output
+    arrays are assembled - and this rank's GPU, chosen from the measured host links (``topology.choose_device``).
+    Returns (rank, world_size).  A single process: nothing to do."""
+    world = int(os.environ.get("WORLD_SIZE", "1") or 1)
+    if world <= 1:
+        return rank_world()
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("gloo")
+    if torch.cuda.is_available():
+        from . import topology
+        local_rank = int(os.environ.get("LOCAL_RANK", dist.get_rank()))
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+        device, _ = topology.choose_device(local_rank, local_world)
+        torch.cuda.set_device(device)
+        _native.bind_host_thread_to_gpu(device)
+    return dist.get_rank(), dist.get_world_size()
+
+
 def as_uint16_stack(stack):
     """The dtypes the B200 path takes: uint16 as is, uint8 widened; anything else is refused (the reference converts
     every dtype with ``astype('float32')``; silently wrapping int32 / float stacks into uint16 would corrupt them)."""

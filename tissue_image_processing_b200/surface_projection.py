@@ -446,10 +446,13 @@ def _movie_file(input_dir, number):
 
 
 def main(argv=None):
-    """SP:381-423: dispatch to the fixed-sample, per-file or movie driver exactly as the reference's __main__."""
+    """SP:381-423: dispatch to the fixed-sample, per-file or movie driver exactly as the reference's __main__.
+    Launched by ``torchrun`` (one process per GPU) the ranks join one job first (``movie.init_job``)."""
     from ast import literal_eval
     from glob import glob
     options, _ = getOptions(argv)
+    from .movie import init_job
+    init_job()                                # under torchrun: one rank per GPU, the ranks share the frames / tiles
     input_dir = options.input or os.getcwd()
     output_dir = options.output or input_dir
     common = dict(method=options.method, bin_size=options.bin_size, build_manifold=options.build_manifold)
