@@ -379,3 +379,31 @@ def test_bench_movie_source_through_the_driver(tmp_path, monkeypatch):
     for t in range(7):
         want = orc.time_point_surface_projection(frames[t % 3][None], "TCZYX", 0, airyscan=False).astype("uint16")
         assert np.array_equal(tif[t], want)
+
+
+def test_save_tiff_rescale_matches_the_reference_expression():
+    """BIM:183-186 in pieces: same values as the one-line numpy expression, for sizes on both sides of the chunked
+    path, uint8 and uint16 targets, and the degenerate inputs (all zero: whatever numpy makes of 0/0)."""
+    import warnings
+    from tissue_image_processing_b200 import surface_projection as sp
+    rng = np.random.default_rng(12)
+    seen = {}
+    old, sp.tiff_writer = sp.tiff_writer, lambda path, image, axes, metadata: seen.update(image=image)
+    try:
+        for shape in ((2, 64, 64), (3, 1300, 1100)):
+            img = (rng.random(shape, dtype=np.float32) * 2900).astype(np.float64)
+            img[0, :7] = 0
+            for data_type, top in (("uint16", 65535), ("uint8", 255)):
+                sp.save_tiff("x.tif", img, axes="CYX", data_type=data_type)
+                want = np.round((img / np.max(img)) * top).astype(data_type)
+                assert seen["image"].dtype == want.dtype and np.array_equal(seen["image"], want), (shape, data_type)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            zeros = np.zeros((5, 1024, 1024))
+            sp.save_tiff("x.tif", zeros, axes="CYX", data_type="uint16")
+            assert np.array_equal(seen["image"], np.round((zeros / np.max(zeros)) * 65535).astype("uint16"))
+        already = np.arange(12, dtype=np.uint16).reshape(3, 4)
+        sp.save_tiff("x.tif", already, axes="YX", data_type="uint16")
+        assert seen["image"] is already                               # no conversion when the dtype is the target
+    finally:
+        sp.tiff_writer = old
