@@ -394,10 +394,15 @@ def large_image_projection(input_dir, output_dir, input_file_name, position=1, r
         if rank == 0:
             tag = "_position%d" % pos if many else ""
             out_proj = projection.reshape((dims.T, dims.C, dims.Y, dims.X) if dims.T > 1 else (dims.C, dims.Y, dims.X))
-            save_tiff(os.path.join(output_dir, input_file_name.replace(postfix, tag + "_projection.tif")), out_proj,
-                      axes="TCYX" if dims.T > 1 else "CYX", data_type="uint16")
-            save_npy(os.path.join(output_dir, input_file_name.replace(postfix, tag + "_zmap.npy")),
-                     zmap.reshape((dims.T, dims.Y, dims.X)))
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(max_workers=2) as writers:        # the two files side by side (see the movie driver)
+                pending = [
+                    writers.submit(save_tiff, os.path.join(output_dir, input_file_name.replace(postfix, tag + "_projection.tif")),
+                                   out_proj, axes="TCYX" if dims.T > 1 else "CYX", data_type="uint16"),
+                    writers.submit(save_npy, os.path.join(output_dir, input_file_name.replace(postfix, tag + "_zmap.npy")),
+                                   zmap.reshape((dims.T, dims.Y, dims.X)))]
+            for job in pending:
+                job.result()
         outputs.close()                                # rank 0 has saved the arrays: their backing can go
     _job_barrier()
 
