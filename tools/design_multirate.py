@@ -7,10 +7,15 @@ reference surface_projection.py:37,55) by  U @ C @ Dt :
   U   B-spline reconstruction back to the fine grid.
 Prints the worst-case (L1) and typical errors of the composite.
 """
-import sys
 import numpy as np
-sys.path.insert(0, "/root/repo")
-from oracle.surface_projection_oracle import gaussian_taps
+
+
+def gaussian_taps(sigma, truncate=4.0):
+    """scipy.ndimage.gaussian_filter1d's weights: radius int(truncate * sigma + 0.5), normalised to sum 1."""
+    radius = int(truncate * float(sigma) + 0.5)
+    k = np.arange(-radius, radius + 1, dtype=np.float64)
+    w = np.exp(-0.5 / (float(sigma) * float(sigma)) * k * k)
+    return w / w.sum()
 
 S = 8
 

@@ -1,12 +1,12 @@
 """Development probe: the movie driver from a real TIFF file on disk to real output files (tiff_io reader / writer,
 no I/O hook), timed end to end.
-    python tools/tiff_movie_probe.py [T Z Y X] [--oracle]
+    python tools/tiff_movie_probe.py [T Z Y X] [--dry]
 Writes a (T,1,Z,Y,X) uint16 movie (default 40 x 48 x 1024 x 1024 = BASELINE configs[2] frames, 3.8 GB) to a
 temporary directory, runs movie_surface_projection on it twice (the first run warms the GPU path and the page cache)
 and prints the seconds of the second run: frames are read from the file (page cache) straight into the pipeline's
 pinned staging buffers by its host threads (preadv), projected, returned as uint16 and written as position1.tif +
 zmap_position1.npy by several threads; a third run takes the frames as views of the file mapping instead (A/B).
---oracle replaces the GPU by the CPU oracle (host-logic dry run, small sizes)."""
+--dry replaces the GPU call by a toy numpy operator (host-logic dry run without a GPU, small sizes)."""
 import contextlib
 import io
 import os
@@ -24,14 +24,17 @@ from tissue_image_processing_b200 import tiff_io                                
 from tissue_image_processing_b200.movie import FramePipeline                     # noqa: E402
 
 args = [a for a in sys.argv[1:] if not a.startswith("--")]
-oracle = "--oracle" in sys.argv
+dry = "--dry" in sys.argv
 T, Z, Y, X = (int(v) for v in args[:4]) if len(args) >= 4 else (40, 48, 1024, 1024)
 
-if oracle:
-    from oracle import surface_projection_oracle as orc
-    from oracle import synth
-    distinct = [synth.synth_stack(Z, Y, X, C=1, seed=3, t=t) for t in range(min(T, 4))]
-    pipe = FramePipeline(operator=orc.time_point_surface_projection, out_dtype="uint16")
+if dry:
+    rng = np.random.default_rng(3)
+    distinct = [rng.integers(1, 4000, (1, Z, Y, X), dtype=np.uint16) for _ in range(min(T, 4))]
+
+    def toy(chunk, **kw):                                # stands in for the GPU call: the host path is what runs
+        stack = chunk[0].astype(np.float64)
+        return stack.max(axis=1), stack[0].argmax(axis=0)
+    pipe = FramePipeline(operator=toy, out_dtype="uint16")
 else:
     import torch
     import bench
@@ -67,7 +70,7 @@ try:
     first = got.get_image_dask_data()[0, 0, 0].compute()
     again = got.get_image_dask_data()[len(distinct), 0, 0].compute() if T > len(distinct) else first
     assert first.any() and np.array_equal(first, again), "frames t and t + %d hold the same stack" % len(distinct)
-    if not oracle:
+    if not dry:
         want = sp.time_point_surface_projection(movie[0:1], "TCZYX", 0, airyscan=False)
         assert np.array_equal(first, want[0].astype(np.uint16)), "file differs from the blocking operator call"
     print("output file checked", flush=True)
