@@ -152,14 +152,14 @@ def _attr(value):
 def ome_xml(shape5, order, dtype, name="image", metadata=None):
     """A minimal OME-XML block for one image of ``shape5`` = {axis: size}."""
     phys = ""
-    pixels = getattr(getattr(metadata, "images", [None])[0], "pixels", None) if metadata is not None else None
+    images = (getattr(metadata, "images", None) or [None]) if metadata is not None else [None]
+    pixels = getattr(images[0], "pixels", None)
     for key, attr in (("physical_size_x", "PhysicalSizeX"), ("physical_size_y", "PhysicalSizeY"),
                       ("physical_size_z", "PhysicalSizeZ")):
         value = getattr(pixels, key, None)
         if isinstance(value, (int, float)):
             phys += ' %s="%r"' % (attr, float(value))
-    if metadata is not None and getattr(metadata, "images", None):
-        name = getattr(metadata.images[0], "name", name) or name
+    name = getattr(images[0], "name", None) or name
     channels = "".join('<Channel ID="Channel:0:%d" SamplesPerPixel="1"/>' % c for c in range(shape5["C"]))
     return ('<?xml version="1.0" encoding="UTF-8"?>'
             '<OME xmlns="http://www.openmicroscopy.org/Schemas/OME/2016-06" Creator="tissue_image_processing_b200">'
